@@ -1,0 +1,8 @@
+"""dmsa_lidar_slam_b200 — B200-native (sm_100a) DMSA inner loop behind the reference's optimizer API.
+
+Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C-ABI of include/dmsa_b200.h),
+`api.py` (host-side mirror of DmsaOptimizer / OptimizablePointSet over the C-ABI), `synth.py`
+(deterministic synthetic windows of the BASELINE shapes) and `build.py` (in-tree nvcc build).
+"""
+from .api import (ContinuousTrajectory, DmsaError, DmsaOptimizer, DmsaOptimSettings, MapManagement,  # noqa: F401
+                  OptimizablePointSet, load_library)

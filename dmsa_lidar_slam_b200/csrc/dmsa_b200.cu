@@ -1,0 +1,1320 @@
+// dmsa_b200.cu — C-ABI implementation (include/dmsa_b200.h): context, HBM staging, the optimizeSet loop.
+//
+// Host control flow restates DmsaOptimizer.h:54-182 (optimizeSet, adaptiveStepSize); all per-point and
+// per-set work runs in the sm_100a kernels of kernels_pose.cuh / kernels_sets.cuh / kernels_cost.cuh.
+// There is NO CPU fallback: without a CUDA device dmsa_b200_create fails with DMSA_B200_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <cub/cub.cuh>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/dmsa_b200.h"
+#include "kernels_cost.cuh"
+#include "kernels_pose.cuh"
+#include "kernels_sets.cuh"
+#include "se3_math.cuh"
+
+using namespace dmsa;
+
+namespace {
+
+constexpr int CHUNK = 512;  // members per cost-kernel work unit
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostPoses {
+    int n = 0;
+    std::vector<double> relO, relT, globO, globT;  // 3 x n column-major
+    void resize(int n_) {
+        n = n_;
+        relO.assign(3 * n, 0.0);
+        relT.assign(3 * n, 0.0);
+        globO.assign(3 * n, 0.0);
+        globT.assign(3 * n, 0.0);
+    }
+    static Vec3 col(const std::vector<double>& a, int k) { return mk3(a[3 * k], a[3 * k + 1], a[3 * k + 2]); }
+    static void setcol(std::vector<double>& a, int k, const Vec3& v) {
+        a[3 * k] = v.x;
+        a[3 * k + 1] = v.y;
+        a[3 * k + 2] = v.z;
+    }
+    void relative2global() {  // ConsecutivePoses.h:26-43
+        Mat3 R = identity3();
+        Vec3 T = mk3(0, 0, 0);
+        for (int k = 0; k < n; ++k) {
+            T = add3(T, matvec3(R, col(relT, k)));
+            setcol(globT, k, T);
+            R = matmul3(R, so3_exp(col(relO, k)));
+            setcol(globO, k, so3_log(R));
+        }
+    }
+    void global2relative() {  // ConsecutivePoses.h:45-67
+        setcol(relO, 0, col(globO, 0));
+        setcol(relT, 0, col(globT, 0));
+        for (int k = n - 1; k > 0; --k) {
+            Mat3 R1 = so3_exp(col(globO, k - 1)), R2 = so3_exp(col(globO, k));
+            setcol(relO, k, so3_log(matmul3(transpose3(R1), R2)));
+            setcol(relT, k, matvec3(transpose3(R1), sub3(col(globT, k), col(globT, k - 1))));
+        }
+    }
+    void getParams(std::vector<double>& p) const {  // Poses.h:64-70
+        int m = 3 * (n - 1);
+        p.resize(2 * (size_t)m);
+        for (int i = 0; i < m; ++i) {
+            p[i] = relO[3 + i];
+            p[m + i] = relT[3 + i];
+        }
+    }
+    void setParams(const double* p) {  // Poses.h:72-76
+        int m = 3 * (n - 1);
+        for (int i = 0; i < m; ++i) {
+            relO[3 + i] = p[i];
+            relT[3 + i] = p[m + i];
+        }
+    }
+};
+
+// Eigen dynamic inverse() == PartialPivLU: explicit inverse by LU with partial pivoting (DmsaOptimizer.h:113)
+bool lu_solve_inverse(const std::vector<double>& A, int n, std::vector<double>& inv) {
+    std::vector<double> a(A);
+    std::vector<int> piv(n);
+    inv.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) piv[i] = i;
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        double best = std::fabs(a[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; ++i) {
+            double v = std::fabs(a[(size_t)i * n + k]);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        if (p != k) {
+            for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)p * n + j]);
+            std::swap(piv[k], piv[p]);
+        }
+        double d = a[(size_t)k * n + k];
+        for (int i = k + 1; i < n; ++i) {
+            double f = a[(size_t)i * n + k] / d;
+            a[(size_t)i * n + k] = f;
+            double* ai = &a[(size_t)i * n];
+            const double* ak = &a[(size_t)k * n];
+            for (int j = k + 1; j < n; ++j) ai[j] -= f * ak[j];
+        }
+    }
+    std::vector<double> x(n);
+    for (int c = 0; c < n; ++c) {
+        for (int i = 0; i < n; ++i) x[i] = (piv[i] == c) ? 1.0 : 0.0;
+        for (int i = 0; i < n; ++i) {
+            double s = x[i];
+            const double* ai = &a[(size_t)i * n];
+            for (int j = 0; j < i; ++j) s -= ai[j] * x[j];
+            x[i] = s;
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = x[i];
+            const double* ai = &a[(size_t)i * n];
+            for (int j = i + 1; j < n; ++j) s -= ai[j] * x[j];
+            x[i] = s / ai[i];
+        }
+        for (int i = 0; i < n; ++i) inv[(size_t)i * n + c] = x[i];
+    }
+    return true;
+}
+
+inline int pad32(int v) { return (v + 31) / 32 * 32; }
+
+}  // namespace
+
+enum { MODEL_NONE = 0, MODEL_TRAJ = 1, MODEL_KF = 2 };
+
+struct dmsa_b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    int model = MODEL_NONE;
+    int rank = 0, world = 1;
+
+    HostPoses poses;
+    double origin[3] = {0, 0, 0};
+    float minGridSize = 0.3f;  // OptimizablePointSet.h:24
+
+    // trajectory timing (ContinuousTrajectory.h:301-346)
+    double t0 = 0, horizon = 0, dt_res = 1e-3;
+    int n_total = 0;
+    bool useImu = false, imuSet = false;
+    std::vector<double> stamps, trajTime;
+    std::vector<int> paramIndices;
+    DBuf<double> d_stamps, d_trajTime, d_urel, d_fh;
+    DBuf<int> d_seg, d_hit, d_paramIdx;
+    DBuf<double> d_imu;  // preRot | prePos | preVel | covInv
+    double balancingImu = 0.001f, gravity[3] = {0.0, 0.0, -9.805};
+
+    // keyframe factors
+    bool useGrav = false, useOdom = false;
+    DBuf<double> d_kfD;  // measGrav | odomT | odomR
+    DBuf<int> d_plausible;
+    double balanceGrav = 1.0, balanceOdom = 1000.0;
+    std::vector<std::vector<dmsa_b200_point_normal>> kfClouds;
+    std::vector<std::vector<int>> kfRings;
+    std::vector<float> kfGrid;
+
+    // points in HBM
+    int64_t n_scan = 0, n_static = 0;
+    DBuf<unsigned char> d_stage;
+    DBuf<float4> d_local, d_world, d_normal_l, d_normal_w;
+    DBuf<int> d_tid, d_ring, d_flag;
+
+    // pose batches
+    DBuf<double> d_p, d_step, d_batch, d_globO, d_globT, d_quat, d_relO, d_extra;
+    DBuf<float> d_Mtab;
+    int curV = 0, curVld = 0;
+
+    // set construction
+    DBuf<LevelInfo> d_linfo;
+    LevelInfo h_linfo[2];
+    DBuf<int> d_keys, d_bb, d_idx, d_sidx, d_flagA, d_scanA, d_raw_start, d_raw_diff, d_acc_flag, d_acc_scan;
+    DBuf<unsigned long long> d_code, d_scode;
+    DBuf<unsigned char> d_cub;
+    DBuf<float4> d_rec, d_wrec;
+    DBuf<int> d_cell_start, d_cell_n, d_cell_level, d_cell_key, d_cell_sub, d_nchunk, d_chunk_off;
+    DBuf<float> d_cell_info, d_cell_w0, d_cell_w;
+    DBuf<Chunk> d_chunks;
+    int G = 0;
+    int64_t M = 0;
+    bool levelOn[2] = {false, false};
+    int cellCap = 0;
+
+    // cost
+    DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls;
+    DBuf<float> d_mu;
+    size_t chunkBound = 0;
+
+    // host mirrors
+    std::vector<double> h_hg, h_p;
+    double lastErr0 = 0;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return DMSA_B200_ERR_CUDA;                                                             \
+        }                                                                                          \
+    } while (0)
+#define CKRC(call)                 \
+    do {                           \
+        int rc__ = (call);         \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+#define LAUNCH(kern, grid, block, smem, ...)                       \
+    do {                                                           \
+        kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__); \
+        ctx->launches++;                                           \
+    } while (0)
+#define ARGFAIL(msg)               \
+    do {                           \
+        ctx->err = (msg);          \
+        return DMSA_B200_ERR_ARG;  \
+    } while (0)
+
+namespace {
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+__global__ void k_unpack_psi(const unsigned char* __restrict__ raw, int n, int out_off, const double* __restrict__ trajTime, int n_total, double t0,
+                             int is_static, float4* __restrict__ local, float4* __restrict__ world, int* __restrict__ ring, int* __restrict__ tid,
+                             int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = reinterpret_cast<const float4*>(raw)[2 * (size_t)i];
+    const double stamp = *reinterpret_cast<const double*>(raw + 32 * (size_t)i + 16);
+    const int id = *reinterpret_cast<const int*>(raw + 32 * (size_t)i + 24);
+    if (p.w != 1.0f) atomicOr(flag, 1);
+    const int o = out_off + i;
+    local[o] = p;
+    ring[o] = id;
+    if (is_static) {
+        world[o] = p;  // addStaticPoints: ContinuousTrajectory.h:164-171
+        tid[o] = -1;
+    } else {
+        // registerPcBuffer: std::lower_bound(trajTime, stamp - t0), clamped to n_total-1   ContinuousTrajectory.h:253-254
+        const double val = stamp - t0;
+        int lo = 0, hi = n_total;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (trajTime[mid] < val)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        tid[o] = min(lo, n_total - 1);
+    }
+}
+
+__global__ void k_unpack_pn(const unsigned char* __restrict__ raw, const int* __restrict__ rings, int n, int out_off, int kf, float4* __restrict__ local,
+                            float4* __restrict__ normal, int* __restrict__ ring, int* __restrict__ tid, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4* r = reinterpret_cast<const float4*>(raw) + 3 * (size_t)i;
+    const float4 p = r[0];
+    if (p.w != 1.0f) atomicOr(flag, 1);
+    const int o = out_off + i;
+    local[o] = p;
+    normal[o] = r[1];
+    ring[o] = rings[i];
+    tid[o] = kf;
+}
+
+// centralize / decentralize static points: point -= float(origin) / += float(origin)    ContinuousTrajectory.h:83-87, 95-99
+__global__ void k_shift_static(float4* __restrict__ local, float4* __restrict__ world, int off, int n, float ox, float oy, float oz, int sign) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = world[off + i];
+    if (sign < 0) {
+        p.x = __fsub_rn(p.x, ox);
+        p.y = __fsub_rn(p.y, oy);
+        p.z = __fsub_rn(p.z, oz);
+    } else {
+        p.x = __fadd_rn(p.x, ox);
+        p.y = __fadd_rn(p.y, oy);
+        p.z = __fadd_rn(p.z, oz);
+    }
+    world[off + i] = p;
+    local[off + i] = p;
+}
+
+int64_t numPoints(const dmsa_b200_ctx* ctx) { return ctx->n_scan + ctx->n_static; }
+int numExtra(const dmsa_b200_ctx* ctx) {
+    if (ctx->rank != 0) return 0;
+    if (ctx->model == MODEL_TRAJ) return (ctx->useImu && ctx->imuSet) ? ctx->poses.n - 1 : 0;
+    if (ctx->model == MODEL_KF) return (ctx->useGrav ? ctx->poses.n : 0) + (ctx->useOdom ? ctx->poses.n - 1 : 0);
+    return 0;
+}
+int numTableRows(const dmsa_b200_ctx* ctx) { return ctx->model == MODEL_TRAJ ? ctx->n_total : ctx->poses.n; }
+
+// pose chain (+ dense table) for the V vectors currently in d_batch
+int runPoseTables(dmsa_b200_ctx* ctx, int V) {
+    const int P = 6 * (ctx->poses.n - 1), n = ctx->poses.n, Vld = pad32(V), rows = numTableRows(ctx);
+    const int E = numExtra(ctx);
+    CK(ctx->d_globO.ensure((size_t)3 * n * Vld));
+    CK(ctx->d_globT.ensure((size_t)3 * n * Vld));
+    CK(ctx->d_quat.ensure((size_t)4 * n * Vld));
+    CK(ctx->d_Mtab.ensure((size_t)rows * Vld * 12));
+    if (E > 0) CK(ctx->d_extra.ensure((size_t)E * Vld));
+    PoseBatch pb;
+    pb.V = V;
+    pb.Vld = Vld;
+    pb.P = P;
+    pb.n = n;
+    pb.params = ctx->d_batch.p;
+    for (int a = 0; a < 3; ++a) {
+        pb.pose0[a] = ctx->poses.relO[a];
+        pb.pose0[3 + a] = ctx->poses.relT[a];
+    }
+    pb.globO_t = ctx->d_globO.p;
+    pb.globT_t = ctx->d_globT.p;
+    pb.quat_t = ctx->d_quat.p;
+    pb.relO_t = nullptr;
+    pb.extra = E > 0 ? ctx->d_extra.p : nullptr;
+    TrajTiming tt;
+    tt.n_total = ctx->n_total;
+    tt.seg = ctx->d_seg.p;
+    tt.urel = ctx->d_urel.p;
+    tt.fh = ctx->d_fh.p;
+    tt.hit = ctx->d_hit.p;
+    ImuFactors imu;
+    memset(&imu, 0, sizeof(imu));
+    KfFactors kf;
+    memset(&kf, 0, sizeof(kf));
+    const size_t smem = (size_t)n * 24 * sizeof(double);
+    if (ctx->model == MODEL_TRAJ) {
+        if (E > 0) {
+            imu.enabled = 1;
+            imu.preRot = ctx->d_imu.p;
+            imu.prePos = imu.preRot + 9 * (size_t)n;
+            imu.preVel = imu.prePos + 3 * (size_t)n;
+            imu.covInv = imu.preVel + 3 * (size_t)n;
+            imu.paramIdx = ctx->d_paramIdx.p;
+            imu.stamps = ctx->d_stamps.p;
+            imu.balancing = ctx->balancingImu;
+            imu.dt_res = ctx->dt_res;
+            for (int a = 0; a < 3; ++a) imu.gravity[a] = ctx->gravity[a];
+        }
+        LAUNCH(k_pose_chain<0>, V, 64, smem, pb, ctx->d_Mtab.p, imu, kf, tt);
+        dim3 blk(32, 4), grd(Vld / 32, cdiv(ctx->n_total, 4));
+        LAUNCH(k_dense_table, grd, blk, 0, pb, tt, ctx->d_Mtab.p);
+    } else {
+        kf.useGrav = ctx->useGrav && E > 0;
+        kf.useOdom = ctx->useOdom && E > 0;
+        kf.measGrav = ctx->d_kfD.p;
+        kf.odomT = kf.measGrav ? kf.measGrav + 3 * (size_t)n : nullptr;
+        kf.odomR = kf.odomT ? kf.odomT + 3 * (size_t)n : nullptr;
+        kf.plausible = ctx->d_plausible.p;
+        kf.balanceGrav = ctx->balanceGrav;
+        kf.balanceOdom = ctx->balanceOdom;
+        for (int a = 0; a < 3; ++a) kf.gravity[a] = ctx->gravity[a];
+        LAUNCH(k_pose_chain<1>, V, 64, smem, pb, ctx->d_Mtab.p, imu, kf, tt);
+    }
+    ctx->curV = V;
+    ctx->curVld = Vld;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int uploadParams(dmsa_b200_ctx* ctx) {
+    ctx->poses.getParams(ctx->h_p);
+    const int P = (int)ctx->h_p.size();
+    CK(ctx->d_p.ensure(std::max(P, 1)));
+    CK(ctx->d_step.ensure(std::max(P, 1)));
+    CK(ctx->d_batch.ensure((size_t)(P + 1) * std::max(P, 1)));
+    if (P > 0) CK(cudaMemcpyAsync(ctx->d_p.p, ctx->h_p.data(), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int transformBase(dmsa_b200_ctx* ctx) {
+    const int64_t N = numPoints(ctx);
+    if (N == 0) return 0;
+    CK(ctx->d_world.ensure(N));
+    const bool kfm = ctx->model == MODEL_KF;
+    if (kfm) CK(ctx->d_normal_w.ensure(N));
+    // static points (tid = -1) pass through: their world copy is maintained by centralize/decentralize
+    LAUNCH(k_transform_points, cdiv(ctx->n_scan, 256), 256, 0, ctx->d_local.p, ctx->d_tid.p, (int)ctx->n_scan, reinterpret_cast<const float4*>(ctx->d_Mtab.p),
+           ctx->curVld, 0, ctx->d_world.p, kfm ? ctx->d_normal_l.p : nullptr, kfm ? ctx->d_normal_w.p : nullptr);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
+    size_t need = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, N, 0, 64);
+    need = std::max(need, b);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, std::max(N, cells + 1));
+    need = std::max(need, b);
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, std::max(N, cells + 1));
+    need = std::max(need, b);
+    CK(ctx->d_cub.ensure(need + 256));
+    return 0;
+}
+
+// reset + both createGaussianSets + updateRebalancingWeights + work decomposition   DmsaOptimizer.h:78-96
+int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
+    const int64_t N64 = numPoints(ctx);
+    if (N64 <= 0 || N64 > 0x3fffffff) ARGFAIL("build_sets: no points staged (or more than 2^30)");
+    const int N = (int)N64;
+    const int nb = (N + DMSA_KEYS_BLOCK - 1) / DMSA_KEYS_BLOCK;
+    const int minPts = st->min_num_points_per_set;
+    const int cap = (int)std::min<int64_t>(2 * N64 / std::max(1, minPts) + 16, 2 * N64 + 16);
+    ctx->cellCap = cap;
+    CK(ctx->d_linfo.ensure(2));
+    CK(ctx->d_keys.ensure((size_t)6 * N));
+    CK(ctx->d_bb.ensure((size_t)2 * 12 * nb));
+    CK(ctx->d_code.ensure(N));
+    CK(ctx->d_scode.ensure(N));
+    CK(ctx->d_idx.ensure(N));
+    CK(ctx->d_sidx.ensure((size_t)2 * N));
+    CK(ctx->d_flagA.ensure(N));
+    CK(ctx->d_scanA.ensure(N));
+    CK(ctx->d_raw_start.ensure((size_t)N + 2));
+    CK(ctx->d_raw_diff.ensure((size_t)N + 2));
+    CK(ctx->d_acc_flag.ensure((size_t)N + 2));
+    CK(ctx->d_acc_scan.ensure((size_t)N + 2));
+    CK(ctx->d_rec.ensure((size_t)2 * N));
+    CK(ctx->d_wrec.ensure((size_t)2 * N));
+    CK(ctx->d_cell_start.ensure(cap));
+    CK(ctx->d_cell_n.ensure(cap));
+    CK(ctx->d_cell_level.ensure(cap));
+    CK(ctx->d_cell_key.ensure((size_t)3 * cap));
+    CK(ctx->d_cell_sub.ensure(cap));
+    CK(ctx->d_cell_info.ensure((size_t)9 * cap));
+    CK(ctx->d_cell_w0.ensure(cap));
+    CK(ctx->d_cell_w.ensure(cap));
+    CK(ctx->d_nchunk.ensure((size_t)cap + 1));
+    CK(ctx->d_chunk_off.ensure((size_t)cap + 1));
+    CKRC(ensureCub(ctx, N, cap));
+    CellStore cs;
+    cs.start = ctx->d_cell_start.p;
+    cs.n = ctx->d_cell_n.p;
+    cs.level = ctx->d_cell_level.p;
+    cs.key = ctx->d_cell_key.p;
+    cs.sub = ctx->d_cell_sub.p;
+    cs.info = ctx->d_cell_info.p;
+    cs.w0 = ctx->d_cell_w0.p;
+    cs.w = ctx->d_cell_w.p;
+
+    const float factors[2] = {st->grid_size_1_factor, st->grid_size_2_factor};
+    for (int l = 0; l < 2; ++l) ctx->levelOn[l] = factors[l] > std::numeric_limits<float>::min();  // DmsaOptimizer.h:81,85
+    CK(cudaMemsetAsync(ctx->d_linfo.p, 0, 2 * sizeof(LevelInfo), ctx->stream));
+    // phase 1: anchors, keys, octree roots
+    for (int l = 0; l < 2; ++l) {
+        if (!ctx->levelOn[l]) continue;
+        const float res = factors[l] * ctx->minGridSize;  // float product, DmsaOptimizer.h:82,86
+        int* keys = ctx->d_keys.p + (size_t)3 * N * l;
+        int* bb = ctx->d_bb.p + (size_t)12 * nb * l;
+        LAUNCH(k_anchor, 1, 32, 0, ctx->d_world.p, N, res, ctx->d_linfo.p + l);
+        LAUNCH(k_keys, nb, DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, ctx->d_linfo.p + l, keys, bb, bb + 3 * nb, bb + 6 * nb, bb + 9 * nb);
+        LAUNCH(k_root, 1, 256, 0, ctx->d_world.p, N, ctx->d_linfo.p + l, bb, bb + 3 * nb, bb + 6 * nb, bb + 9 * nb);
+    }
+    CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < 2; ++l)
+        if (ctx->levelOn[l] && ctx->h_linfo[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
+    // phase 2: sort, segment, accept, gather
+    size_t cubBytes = ctx->d_cub.cap;
+    int prev = -1;
+    for (int l = 0; l < 2; ++l) {
+        if (!ctx->levelOn[l]) continue;
+        LevelInfo* li = ctx->d_linfo.p + l;
+        int* keys = ctx->d_keys.p + (size_t)3 * N * l;
+        int* sidx = ctx->d_sidx.p + (size_t)N * l;
+        LAUNCH(k_morton, cdiv(N, 256), 256, 0, keys, N, li, ctx->d_code.p, ctx->d_idx.p);
+        const int end_bit = std::min(64, 3 * ctx->h_linfo[l].depth + 1);
+        CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, cubBytes, ctx->d_code.p, ctx->d_scode.p, ctx->d_idx.p, sidx, N, 0, end_bit, ctx->stream));
+        LAUNCH(k_heads, cdiv(N, 256), 256, 0, ctx->d_scode.p, N, li, ctx->d_flagA.p);
+        CK(cub::DeviceScan::InclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_flagA.p, ctx->d_scanA.p, N, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_raw_diff.p, 0, ((size_t)N + 2) * sizeof(int), ctx->stream));
+        LAUNCH(k_raw_starts, cdiv(N, 256), 256, 0, ctx->d_scode.p, ctx->d_flagA.p, ctx->d_scanA.p, N, li, ctx->d_raw_start.p);
+        LAUNCH(k_ring_diff, cdiv(N, 256), 256, 0, sidx, ctx->d_scanA.p, ctx->d_raw_start.p, ctx->d_ring.p, li, ctx->d_raw_diff.p);
+        LAUNCH(k_accept, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_raw_diff.p, li, minPts, ctx->d_acc_flag.p);
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_acc_flag.p, ctx->d_acc_scan.p, N, ctx->stream));
+        LAUNCH(k_emit_cells, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_acc_flag.p, ctx->d_acc_scan.p, sidx, keys, li,
+               prev >= 0 ? ctx->d_linfo.p + prev : nullptr, l, l * N, cs, cap);
+        LAUNCH(k_gather, cdiv(N, 256), 256, 0, sidx, li, ctx->d_local.p, ctx->d_tid.p, ctx->d_world.p, ctx->d_rec.p + (size_t)N * l,
+               ctx->d_wrec.p + (size_t)N * l);
+        prev = l;
+    }
+    CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    int G = 0;
+    for (int l = 0; l < 2; ++l)
+        if (ctx->levelOn[l]) G += ctx->h_linfo[l].G;
+    if (G > cap) ARGFAIL("build_sets: Gaussian store capacity exceeded");
+    ctx->G = G;
+    ctx->M = 0;
+    if (G == 0) return 0;
+    // phase 3: per-set statistics, weights, chunk list
+    LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G);
+    LAUNCH(k_weights, 1, 1024, 0, cs, G);
+    LAUNCH(k_chunk_counts, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->rank, ctx->world, ctx->d_nchunk.p);
+    CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), ctx->stream));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, ctx->stream));
+    ctx->chunkBound = (size_t)2 * N / CHUNK + (size_t)G + 1;
+    CK(ctx->d_chunks.ensure(ctx->chunkBound));
+    LAUNCH(k_chunk_fill, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// V cost evaluations on the tables in Mtab -> E rows [0, G) (+ extra rows)
+int runCost(dmsa_b200_ctx* ctx) {
+    const int V = ctx->curV, Vld = ctx->curVld, G = ctx->G, E = numExtra(ctx);
+    if (Vld > 1024) ARGFAIL("more than 1023 pose parameters are not supported by the cost kernels");
+    CK(ctx->d_S.ensure(ctx->chunkBound * 3 * Vld));
+    CK(ctx->d_Q.ensure(ctx->chunkBound * Vld));
+    CK(ctx->d_mu.ensure((size_t)G * 3 * Vld));
+    CK(ctx->d_E.ensure((size_t)(G + E) * Vld));
+    CostArgs a;
+    a.chunks = ctx->d_chunks.p;
+    a.n_chunks = ctx->d_chunk_off.p + G;
+    a.rec = ctx->d_rec.p;
+    a.Mtab = reinterpret_cast<const float4*>(ctx->d_Mtab.p);
+    a.V = V;
+    a.Vld = Vld;
+    a.info = ctx->d_cell_info.p;
+    a.w = ctx->d_cell_w.p;
+    a.cell_n = ctx->d_cell_n.p;
+    a.nchunk = ctx->d_nchunk.p;
+    a.chunk_off = ctx->d_chunk_off.p;
+    a.S = ctx->d_S.p;
+    a.mu = ctx->d_mu.p;
+    a.Q = ctx->d_Q.p;
+    a.E = ctx->d_E.p;
+    const unsigned grid = (unsigned)ctx->chunkBound;
+    LAUNCH(k_cost_sum, grid, Vld, 0, a);
+    LAUNCH(k_cost_mean, G, Vld, 0, a, G);
+    LAUNCH(k_cost_quad, grid, Vld, 0, a);
+    LAUNCH(k_cost_fin, G, Vld, 0, a, G);
+    if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// forward-difference batch -> tables (parameters must be uploaded)
+int prepareFdBatch(dmsa_b200_ctx* ctx) {
+    const int P = 6 * (ctx->poses.n - 1);
+    // `1.0 * sqrt(std::numeric_limits<float>::epsilon())` resolves to sqrt(float)       DmsaOptimizer.h:209
+    const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
+    LAUNCH(k_make_fd_batch, cdiv((size_t)(P + 1) * P, 256), 256, 0, ctx->d_p.p, P, h, ctx->d_batch.p);
+    return runPoseTables(ctx, P + 1);
+}
+
+int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
+    const int P = 6 * (ctx->poses.n - 1), R = ctx->G + numExtra(ctx), Vld = ctx->curVld;
+    const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
+    const double inv_h = 1.0 / h;  // one_div_incr, DmsaOptimizer.h:210
+    int nsplit = std::max(1, std::min(64, (R + 511) / 512));
+    int rps = ((R + nsplit - 1) / nsplit + JTJ_T - 1) / JTJ_T * JTJ_T;
+    nsplit = (R + rps - 1) / rps;
+    const int n1 = P + 1, nt = (n1 + JTJ_T - 1) / JTJ_T;
+    CK(ctx->d_jpart.ensure((size_t)nsplit * n1 * n1));
+    CK(cudaMemsetAsync(ctx->d_jpart.p, 0, (size_t)nsplit * n1 * n1 * sizeof(double), ctx->stream));
+    dim3 grid(nt * (nt + 1) / 2, nsplit);
+    LAUNCH(k_jtj, grid, 256, 0, ctx->d_E.p, R, Vld, P, inv_h, rps, ctx->d_jpart.p);
+    LAUNCH(k_jtj_reduce, cdiv((size_t)n1 * n1, 256), 256, 0, ctx->d_jpart.p, nsplit, P, hg_dev);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) {
+    const int P = 6 * (ctx->poses.n - 1);
+    CK(cudaMemcpyAsync(ctx->d_step.p, step_host, P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(k_make_ls_batch, cdiv((size_t)9 * P, 256), 256, 0, ctx->d_p.p, ctx->d_step.p, P, ctx->d_batch.p);
+    CKRC(runPoseTables(ctx, 9));
+    CKRC(runCost(ctx));
+    LAUNCH(k_col_sumsq, 9, 256, 0, ctx->d_E.p, ctx->G + numExtra(ctx), ctx->curVld, ls_dev);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// H.diag += lambda; step = -alpha * H^-1 * (J^T e0); NaN guard; infinity-norm clamp      DmsaOptimizer.h:107-128
+// returns 1 if the step contains NaN
+int solveStep(const dmsa_b200_settings* st, const double* hg, int P, std::vector<double>& step) {
+    std::vector<double> H(hg, hg + (size_t)P * P), Hinv;
+    const double* g = hg + (size_t)P * P;
+    for (int i = 0; i < P; ++i) H[(size_t)i * P + i] += (double)st->lambda_diag;
+    lu_solve_inverse(H, P, Hinv);
+    step.assign(P, 0.0);
+    bool nan = false;
+    for (int a = 0; a < P; ++a) {
+        double s = 0;
+        for (int b = 0; b < P; ++b) s += (-st->step_length_optim * Hinv[(size_t)a * P + b]) * g[b];
+        step[a] = s;
+        if (std::isnan(s)) nan = true;
+    }
+    if (nan) return 1;
+    double mx = -std::numeric_limits<double>::infinity(), mn = std::numeric_limits<double>::infinity();
+    for (double v : step) {
+        mx = std::max(mx, v);
+        mn = std::min(mn, v);
+    }
+    const double maxElem = std::max(mx, -mn);
+    if (maxElem > st->max_step)
+        for (double& v : step) v = (st->max_step / maxElem) * v;
+    return 0;
+}
+
+int updateGlobalPointsImpl(dmsa_b200_ctx* ctx) {
+    if (ctx->model == MODEL_NONE) ARGFAIL("no model staged");
+    ctx->poses.relative2global();
+    CKRC(uploadParams(ctx));
+    const int P = 6 * (ctx->poses.n - 1);
+    if (P > 0) CK(cudaMemcpyAsync(ctx->d_batch.p, ctx->d_p.p, P * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CKRC(runPoseTables(ctx, 1));
+    return transformBase(ctx);
+}
+
+int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* stop, dmsa_b200_report* rep, double* step_out, double* ls_out) {
+    const int P = 6 * (ctx->poses.n - 1);
+    if (P <= 0) ARGFAIL("need at least two poses");
+    *stop = DMSA_B200_STOP_MAX_ITER;
+    // getPoseParameters + updateGlobalPoints at the base pose (the forward-difference batch's vector 0)   :72-75
+    ctx->poses.relative2global();
+    CKRC(uploadParams(ctx));
+    std::vector<double> paramVec = ctx->h_p;
+    CKRC(prepareFdBatch(ctx));
+    CKRC(transformBase(ctx));
+    CKRC(buildSets(ctx, st));  // :78-86, :96
+    if (rep) {
+        rep->num_gaussians = ctx->G;
+        rep->num_extra = numExtra(ctx);
+    }
+    if (ctx->G < st->min_num_gaussians) {  // :89-93
+        *stop = DMSA_B200_STOP_FEW_GAUSSIANS;
+        return 0;
+    }
+    CKRC(runCost(ctx));  // e0 and the P perturbed evaluations in one batch   :99-104
+    CK(ctx->d_hg.ensure((size_t)P * P + P + 1));
+    CK(ctx->d_ls.ensure(16));
+    CKRC(jtjInto(ctx, ctx->d_hg.p));  // :107
+    ctx->h_hg.resize((size_t)P * P + P + 1);
+    CK(cudaMemcpyAsync(ctx->h_hg.data(), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double error0 = ctx->h_hg[(size_t)P * P + P];
+    ctx->lastErr0 = error0;
+    std::vector<double> step;
+    if (solveStep(st, ctx->h_hg.data(), P, step)) {  // :113-122
+        ctx->poses.setParams(paramVec.data());
+        if (ctx->model == MODEL_KF) ctx->poses.relative2global();
+        *stop = DMSA_B200_STOP_NAN;
+        return 0;
+    }
+    // adaptiveStepSize :152-182 — the 9 trial costs in one batch
+    CKRC(lineSearchInto(ctx, step.data(), ctx->d_ls.p));
+    double ls[9];
+    CK(cudaMemcpyAsync(ls, ctx->d_ls.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double minError = error0;
+    int best = 0;
+    for (int k = 1; k < 10; ++k)
+        if (ls[k - 1] < minError) {
+            minError = ls[k - 1];
+            best = k;
+        }
+    double nrm = 0;
+    for (double v : step) nrm += v * v;
+    nrm = std::sqrt(nrm);
+    if (rep) {
+        rep->best_step = best;
+        rep->error0 = error0;
+        rep->step_norm = nrm;
+    }
+    if (step_out) std::copy(step.begin(), step.end(), step_out);
+    if (ls_out) std::copy(ls, ls + 9, ls_out);
+    std::vector<double> pnew(P);
+    if (best == 0) {
+        // :130-134 — no restore: the set stays at the last trial point p + 0.9*step
+        for (int i = 0; i < P; ++i) pnew[i] = paramVec[i] + 0.1 * 9.0 * step[i];
+        ctx->poses.setParams(pnew.data());
+        if (ctx->model == MODEL_KF) ctx->poses.relative2global();
+        *stop = DMSA_B200_STOP_NO_IMPROVEMENT;
+        return 0;
+    }
+    for (int i = 0; i < P; ++i) pnew[i] = paramVec[i] + 0.1 * (double)best * step[i];
+    ctx->poses.setParams(pnew.data());  // :136
+    if (ctx->model == MODEL_KF) ctx->poses.relative2global();
+    if (nrm < st->epsilon) *stop = DMSA_B200_STOP_EPSILON;  // :139-143
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int dmsa_b200_version(void) { return 100; }
+
+int dmsa_b200_create(dmsa_b200_ctx** out, int device, void* cuda_stream) {
+    if (!out) return DMSA_B200_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return DMSA_B200_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return DMSA_B200_ERR_CUDA;
+    dmsa_b200_ctx* ctx = new dmsa_b200_ctx();
+    ctx->device = device;
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return DMSA_B200_ERR_CUDA;
+        }
+        ctx->own_stream = true;
+    }
+    if (ctx->d_flag.ensure(4) != cudaSuccess) {
+        delete ctx;
+        return DMSA_B200_ERR_CUDA;
+    }
+    cudaMemsetAsync(ctx->d_flag.p, 0, 4 * sizeof(int), ctx->stream);
+    *out = ctx;
+    return DMSA_B200_OK;
+}
+
+void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+#define REL(b) ctx->b.release()
+    REL(d_stamps); REL(d_trajTime); REL(d_urel); REL(d_fh); REL(d_seg); REL(d_hit); REL(d_paramIdx); REL(d_imu); REL(d_kfD); REL(d_plausible);
+    REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
+    REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_relO); REL(d_extra); REL(d_Mtab);
+    REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
+    REL(d_acc_scan); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
+    REL(d_cell_key); REL(d_cell_sub); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_mu);
+#undef REL
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* dmsa_b200_last_error(const dmsa_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t dmsa_b200_launch_count(const dmsa_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int dmsa_b200_synchronize(dmsa_b200_ctx* ctx) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- trajectory model ---------------------------------------------------------------------------
+int dmsa_b200_traj_init(dmsa_b200_ctx* ctx, double t_min, double t_max, int32_t n_poses, int32_t use_imu, double dt_res) {
+    if (n_poses < 3) ARGFAIL("traj_init: barycentric_rational of order 2 needs at least 3 control poses");
+    CK(cudaSetDevice(ctx->device));
+    ctx->model = MODEL_TRAJ;
+    ctx->dt_res = dt_res;
+    ctx->useImu = use_imu != 0;
+    ctx->imuSet = false;
+    ctx->t0 = t_min;
+    ctx->horizon = t_max - t_min + dt_res;                             // :309
+    ctx->n_total = (int)std::round(ctx->horizon / dt_res) + 1;          // :310
+    const int nt = ctx->n_total, n = n_poses;
+    auto linspaced = [](int m, double lo, double hi, std::vector<double>& v) {  // Eigen LinSpaced: lo + i*step, last == hi
+        v.resize(m);
+        double step = (m > 1) ? (hi - lo) / (double)(m - 1) : 0.0;
+        for (int i = 0; i < m; ++i) v[i] = lo + (double)i * step;
+        v[m - 1] = hi;
+    };
+    linspaced(nt, 0.0, ctx->horizon, ctx->trajTime);  // :323
+    linspaced(n, 0.0, ctx->horizon, ctx->stamps);     // :332
+    ctx->paramIndices.resize(n);
+    for (int i = 0; i < n; ++i) ctx->paramIndices[i] = (int)std::round(ctx->stamps[i] / dt_res);  // :336
+    ctx->poses.resize(n);
+    ctx->gravity[0] = 0.0;
+    ctx->gravity[1] = 0.0;
+    ctx->gravity[2] = -9.805;  // :345
+    ctx->n_scan = ctx->n_static = 0;
+    // per-sample interpolation constants: getInterpRotation's index/fraction (:573-581) and the barycentric-rational
+    // quotients w_i / (t - s_i) of order 2 (:214; Boost calculate_weights / operator())
+    const double* s = ctx->stamps.data();
+    std::vector<int> seg(nt), hit(nt);
+    std::vector<double> urel(nt), fh((size_t)nt * n), w(n, 0.0);
+    const int d = 2;
+    for (int k = 0; k < n; ++k) {
+        int i_min = std::max(k - d, 0), i_max = (k >= n - d) ? n - d - 1 : k;
+        for (int i = i_min; i <= i_max; ++i) {
+            double inv_product = 1;
+            int j_max = std::min(i + d, n - 1);
+            for (int j = i; j <= j_max; ++j) {
+                if (j == k) continue;
+                inv_product *= (s[k] - s[j]);
+            }
+            if (i % 2 == 0)
+                w[k] += 1 / inv_product;
+            else
+                w[k] -= 1 / inv_product;
+        }
+    }
+    for (int j = 0; j < nt; ++j) {
+        double t = ctx->trajTime[j];
+        int r = (int)(std::lower_bound(s, s + n - 1, t) - s);
+        seg[j] = r;
+        urel[j] = (r != 0) ? (t - s[r - 1]) / (s[r] - s[r - 1]) : 1.0;
+        hit[j] = -1;
+        for (int i = 0; i < n; ++i) {
+            if (t == s[i]) {
+                hit[j] = i;
+                break;
+            }
+        }
+        for (int i = 0; i < n; ++i) fh[(size_t)j * n + i] = (hit[j] >= 0) ? 0.0 : w[i] / (t - s[i]);
+    }
+    CK(ctx->d_stamps.ensure(n));
+    CK(ctx->d_trajTime.ensure(nt));
+    CK(ctx->d_urel.ensure(nt));
+    CK(ctx->d_fh.ensure((size_t)nt * n));
+    CK(ctx->d_seg.ensure(nt));
+    CK(ctx->d_hit.ensure(nt));
+    CK(ctx->d_paramIdx.ensure(n));
+    CK(cudaMemcpyAsync(ctx->d_stamps.p, s, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_trajTime.p, ctx->trajTime.data(), nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_urel.p, urel.data(), nt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_fh.p, fh.data(), (size_t)nt * n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_seg.p, seg.data(), nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_hit.p, hit.data(), nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_paramIdx.p, ctx->paramIndices.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
+    return 0;
+}
+
+int dmsa_b200_traj_register_scans(dmsa_b200_ctx* ctx, int32_t n_scans, const dmsa_b200_point_stamp_id* const* scans, const int64_t* sizes,
+                                  const float* grid_sizes) {
+    if (ctx->model != MODEL_TRAJ) ARGFAIL("register_scans: call traj_init first");
+    CK(cudaSetDevice(ctx->device));
+    int64_t total = 0;
+    float mg = std::numeric_limits<float>::max();
+    for (int s = 0; s < n_scans; ++s) {
+        total += sizes[s];
+        if (grid_sizes) mg = std::min(mg, grid_sizes[s]);  // :235-238
+    }
+    if (grid_sizes && n_scans > 0) ctx->minGridSize = mg;
+    if (total > 0x3fffffff) ARGFAIL("register_scans: too many points");
+    const size_t cap = (size_t)total + (size_t)ctx->n_static + 16;
+    // static points (if any) are re-appended by the caller after registering (the reference resizes globalPoints, :232)
+    ctx->n_static = 0;
+    CK(ctx->d_local.ensure(cap));
+    CK(ctx->d_world.ensure(cap));
+    CK(ctx->d_tid.ensure(cap));
+    CK(ctx->d_ring.ensure(cap));
+    CK(ctx->d_stage.ensure((size_t)total * 32 + 64));
+    CK(cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), ctx->stream));
+    int64_t off = 0;
+    for (int s = 0; s < n_scans; ++s) {
+        if (sizes[s] == 0) continue;
+        unsigned char* dst = ctx->d_stage.p + (size_t)off * 32;
+        CK(cudaMemcpyAsync(dst, scans[s], (size_t)sizes[s] * 32, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_unpack_psi, cdiv(sizes[s], 256), 256, 0, dst, (int)sizes[s], (int)off, ctx->d_trajTime.p, ctx->n_total, ctx->t0, 0, ctx->d_local.p,
+               ctx->d_world.p, ctx->d_ring.p, ctx->d_tid.p, ctx->d_flag.p);
+        off += sizes[s];
+    }
+    ctx->n_scan = total;
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (flag) {
+        ctx->err = "register_scans: a point has homogeneous coordinate w != 1 (PCL_ADD_POINT4D sets 1)";
+        return DMSA_B200_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+int dmsa_b200_traj_add_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_stamp_id* pts, int64_t n) {
+    if (ctx->model != MODEL_TRAJ) ARGFAIL("add_static_points: call traj_init first");
+    CK(cudaSetDevice(ctx->device));
+    if (n <= 0) return 0;
+    const size_t newN = (size_t)ctx->n_scan + ctx->n_static + n;
+    if (newN > ctx->d_local.cap) {
+        // grow, preserving contents
+        DBuf<float4> nl, nw;
+        DBuf<int> nt, nr;
+        CK(nl.ensure(newN));
+        CK(nw.ensure(newN));
+        CK(nt.ensure(newN));
+        CK(nr.ensure(newN));
+        const size_t old = (size_t)ctx->n_scan + ctx->n_static;
+        if (old) {
+            CK(cudaMemcpyAsync(nl.p, ctx->d_local.p, old * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(nw.p, ctx->d_world.p, old * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(nt.p, ctx->d_tid.p, old * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(nr.p, ctx->d_ring.p, old * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->d_local.release();
+        ctx->d_world.release();
+        ctx->d_tid.release();
+        ctx->d_ring.release();
+        ctx->d_local = nl;
+        ctx->d_world = nw;
+        ctx->d_tid = nt;
+        ctx->d_ring = nr;
+    }
+    CK(ctx->d_stage.ensure((size_t)n * 32 + 64));
+    CK(cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_stage.p, pts, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(k_unpack_psi, cdiv(n, 256), 256, 0, ctx->d_stage.p, (int)n, (int)(ctx->n_scan + ctx->n_static), ctx->d_trajTime.p, ctx->n_total, ctx->t0, 1,
+           ctx->d_local.p, ctx->d_world.p, ctx->d_ring.p, ctx->d_tid.p, ctx->d_flag.p);
+    ctx->n_static += n;
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (flag) {
+        ctx->err = "add_static_points: a point has homogeneous coordinate w != 1";
+        return DMSA_B200_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+int dmsa_b200_traj_remove_static_points(dmsa_b200_ctx* ctx) {
+    ctx->n_static = 0;  // :174-187
+    return 0;
+}
+
+int dmsa_b200_traj_get_timing(dmsa_b200_ctx* ctx, int32_t* n_total, double* horizon, double* ctrl_stamps, double* traj_time, int32_t* param_indices) {
+    if (ctx->model != MODEL_TRAJ) ARGFAIL("get_timing: no trajectory model");
+    if (n_total) *n_total = ctx->n_total;
+    if (horizon) *horizon = ctx->horizon;
+    if (ctrl_stamps) std::copy(ctx->stamps.begin(), ctx->stamps.end(), ctrl_stamps);
+    if (traj_time) std::copy(ctx->trajTime.begin(), ctx->trajTime.end(), traj_time);
+    if (param_indices) std::copy(ctx->paramIndices.begin(), ctx->paramIndices.end(), param_indices);
+    return 0;
+}
+
+int dmsa_b200_traj_get_tform_ids(dmsa_b200_ctx* ctx, int32_t* out) {
+    if (ctx->model != MODEL_TRAJ) ARGFAIL("get_tform_ids: no trajectory model");
+    CK(cudaMemcpyAsync(out, ctx->d_tid.p, (size_t)ctx->n_scan * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int dmsa_b200_traj_set_imu_factors(dmsa_b200_ctx* ctx, const double* preint_rot, const double* preint_pos, const double* preint_vel,
+                                   const double* cov_inv, double balancing_imu, const double* gravity3) {
+    if (ctx->model != MODEL_TRAJ) ARGFAIL("set_imu_factors: no trajectory model");
+    const int n = ctx->poses.n;
+    CK(ctx->d_imu.ensure((size_t)n * (9 + 3 + 3 + 81)));
+    double* d = ctx->d_imu.p;
+    CK(cudaMemcpyAsync(d, preint_rot, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + 9 * (size_t)n, preint_pos, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + 12 * (size_t)n, preint_vel, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + 15 * (size_t)n, cov_inv, (size_t)n * 81 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->balancingImu = balancing_imu;
+    if (gravity3)
+        for (int a = 0; a < 3; ++a) ctx->gravity[a] = gravity3[a];
+    ctx->imuSet = true;
+    return 0;
+}
+
+// ---- keyframe model -----------------------------------------------------------------------------
+int dmsa_b200_kf_init(dmsa_b200_ctx* ctx, int32_t n_keyframes) {
+    if (n_keyframes < 2) ARGFAIL("kf_init: need at least two keyframes");
+    ctx->model = MODEL_KF;
+    ctx->poses.resize(n_keyframes);
+    ctx->kfClouds.assign(n_keyframes, {});
+    ctx->kfRings.assign(n_keyframes, {});
+    ctx->kfGrid.assign(n_keyframes, 0.3f);
+    ctx->useGrav = ctx->useOdom = false;
+    ctx->n_scan = ctx->n_static = 0;
+    ctx->n_total = 0;
+    ctx->gravity[0] = ctx->gravity[1] = 0.0;
+    ctx->gravity[2] = -9.805;
+    return 0;
+}
+
+int dmsa_b200_kf_set_keyframe(dmsa_b200_ctx* ctx, int32_t k, const dmsa_b200_point_normal* pts, const int32_t* ring_ids, int64_t n, float grid_size) {
+    if (ctx->model != MODEL_KF || k < 0 || k >= ctx->poses.n) ARGFAIL("kf_set_keyframe: bad keyframe index");
+    ctx->kfClouds[k].assign(pts, pts + n);
+    ctx->kfRings[k].assign(ring_ids, ring_ids + n);
+    ctx->kfGrid[k] = grid_size;
+    return 0;
+}
+
+int dmsa_b200_kf_commit(dmsa_b200_ctx* ctx) {
+    if (ctx->model != MODEL_KF) ARGFAIL("kf_commit: no keyframe model");
+    CK(cudaSetDevice(ctx->device));
+    int64_t total = 0;
+    float mg = std::numeric_limits<float>::max();
+    size_t mx = 0;
+    for (int k = 0; k < ctx->poses.n; ++k) {
+        total += (int64_t)ctx->kfClouds[k].size();
+        mx = std::max(mx, ctx->kfClouds[k].size());
+        mg = std::min(mg, ctx->kfGrid[k]);  // MapManagement.h:126-131
+    }
+    if (total > 0x3fffffff) ARGFAIL("kf_commit: too many points");
+    ctx->minGridSize = mg;
+    CK(ctx->d_local.ensure(total + 16));
+    CK(ctx->d_world.ensure(total + 16));
+    CK(ctx->d_normal_l.ensure(total + 16));
+    CK(ctx->d_normal_w.ensure(total + 16));
+    CK(ctx->d_tid.ensure(total + 16));
+    CK(ctx->d_ring.ensure(total + 16));
+    CK(ctx->d_stage.ensure(mx * 48 + mx * 4 + 64));
+    CK(cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), ctx->stream));
+    int64_t off = 0;
+    for (int k = 0; k < ctx->poses.n; ++k) {
+        const size_t n = ctx->kfClouds[k].size();
+        if (n == 0) continue;
+        int* drings = reinterpret_cast<int*>(ctx->d_stage.p + mx * 48);
+        CK(cudaMemcpyAsync(ctx->d_stage.p, ctx->kfClouds[k].data(), n * 48, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(drings, ctx->kfRings[k].data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_unpack_pn, cdiv(n, 256), 256, 0, ctx->d_stage.p, drings, (int)n, (int)off, k, ctx->d_local.p, ctx->d_normal_l.p, ctx->d_ring.p, ctx->d_tid.p,
+               ctx->d_flag.p);
+        CK(cudaStreamSynchronize(ctx->stream));  // staging buffer is reused
+        off += (int64_t)n;
+    }
+    ctx->n_scan = total;
+    ctx->n_static = 0;
+    int flag = 0;
+    CK(cudaMemcpy(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaGetLastError());
+    if (flag) {
+        ctx->err = "kf_commit: a point has homogeneous coordinate w != 1";
+        return DMSA_B200_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+int dmsa_b200_kf_set_gravity_terms(dmsa_b200_ctx* ctx, const double* measured_gravity, const int32_t* plausible, double balance) {
+    if (ctx->model != MODEL_KF) ARGFAIL("kf_set_gravity_terms: no keyframe model");
+    const int n = ctx->poses.n;
+    CK(ctx->d_kfD.ensure((size_t)n * 15));
+    CK(ctx->d_plausible.ensure(n));
+    CK(cudaMemcpy(ctx->d_kfD.p, measured_gravity, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_plausible.p, plausible, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    ctx->balanceGrav = balance;
+    ctx->useGrav = true;
+    return 0;
+}
+
+int dmsa_b200_kf_set_odometry_terms(dmsa_b200_ctx* ctx, const double* rel_transl, const double* rel_orient_mat, double balance) {
+    if (ctx->model != MODEL_KF) ARGFAIL("kf_set_odometry_terms: no keyframe model");
+    const int n = ctx->poses.n;
+    CK(ctx->d_kfD.ensure((size_t)n * 15));
+    CK(ctx->d_plausible.ensure(n));
+    CK(cudaMemcpy(ctx->d_kfD.p + 3 * (size_t)n, rel_transl, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_kfD.p + 6 * (size_t)n, rel_orient_mat, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->balanceOdom = balance;
+    ctx->useOdom = true;
+    return 0;
+}
+
+// ---- poses ----------------------------------------------------------------------------------------
+int dmsa_b200_set_relative_poses(dmsa_b200_ctx* ctx, const double* rel_orient, const double* rel_transl) {
+    if (ctx->model == MODEL_NONE) ARGFAIL("set_relative_poses: no model");
+    const int n = ctx->poses.n;
+    std::copy(rel_orient, rel_orient + 3 * n, ctx->poses.relO.begin());
+    std::copy(rel_transl, rel_transl + 3 * n, ctx->poses.relT.begin());
+    ctx->poses.relative2global();
+    return 0;
+}
+int dmsa_b200_get_poses(dmsa_b200_ctx* ctx, double* rel_orient, double* rel_transl, double* glob_orient, double* glob_transl) {
+    const int n3 = 3 * ctx->poses.n;
+    if (rel_orient) std::copy(ctx->poses.relO.begin(), ctx->poses.relO.begin() + n3, rel_orient);
+    if (rel_transl) std::copy(ctx->poses.relT.begin(), ctx->poses.relT.begin() + n3, rel_transl);
+    if (glob_orient) std::copy(ctx->poses.globO.begin(), ctx->poses.globO.begin() + n3, glob_orient);
+    if (glob_transl) std::copy(ctx->poses.globT.begin(), ctx->poses.globT.begin() + n3, glob_transl);
+    return 0;
+}
+int32_t dmsa_b200_num_params(const dmsa_b200_ctx* ctx) { return 6 * (ctx->poses.n - 1); }
+int dmsa_b200_get_pose_parameters(dmsa_b200_ctx* ctx, double* params) {
+    std::vector<double> p;
+    ctx->poses.getParams(p);
+    std::copy(p.begin(), p.end(), params);
+    return 0;
+}
+int dmsa_b200_set_pose_parameters(dmsa_b200_ctx* ctx, const double* params) {
+    ctx->poses.setParams(params);
+    if (ctx->model == MODEL_KF) ctx->poses.relative2global();  // MapManagement.h:197-202
+    return 0;
+}
+int dmsa_b200_centralize(dmsa_b200_ctx* ctx) {
+    if (ctx->model != MODEL_TRAJ) return 0;  // MapManagement.h:73-79: early return
+    CK(cudaSetDevice(ctx->device));
+    for (int a = 0; a < 3; ++a) {
+        ctx->origin[a] = ctx->poses.relT[a];
+        ctx->poses.relT[a] = 0.0;
+    }
+    ctx->poses.relative2global();
+    if (ctx->n_static > 0) {
+        LAUNCH(k_shift_static, cdiv(ctx->n_static, 256), 256, 0, ctx->d_local.p, ctx->d_world.p, (int)ctx->n_scan, (int)ctx->n_static, (float)ctx->origin[0],
+               (float)ctx->origin[1], (float)ctx->origin[2], -1);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+int dmsa_b200_decentralize(dmsa_b200_ctx* ctx) {
+    if (ctx->model != MODEL_TRAJ) return 0;
+    CK(cudaSetDevice(ctx->device));
+    ctx->poses.global2relative();
+    for (int a = 0; a < 3; ++a) ctx->poses.relT[a] = ctx->origin[a];
+    ctx->poses.relative2global();
+    if (ctx->n_static > 0) {
+        LAUNCH(k_shift_static, cdiv(ctx->n_static, 256), 256, 0, ctx->d_local.p, ctx->d_world.p, (int)ctx->n_scan, (int)ctx->n_static, (float)ctx->origin[0],
+               (float)ctx->origin[1], (float)ctx->origin[2], +1);
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// ---- hot path, step by step -------------------------------------------------------------------------
+int dmsa_b200_update_global_points(dmsa_b200_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return updateGlobalPointsImpl(ctx);
+}
+int64_t dmsa_b200_num_points(const dmsa_b200_ctx* ctx) { return numPoints(ctx); }
+int dmsa_b200_get_global_points(dmsa_b200_ctx* ctx, float* xyzw, float* normals) {
+    const int64_t N = numPoints(ctx);
+    if (xyzw) CK(cudaMemcpyAsync(xyzw, ctx->d_world.p, (size_t)N * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (normals && ctx->model == MODEL_KF) CK(cudaMemcpyAsync(normals, ctx->d_normal_w.p, (size_t)N * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+int dmsa_b200_traj_get_dense_tforms(dmsa_b200_ctx* ctx, float* out) {
+    if (ctx->model != MODEL_TRAJ || ctx->curVld == 0) ARGFAIL("get_dense_tforms: call update_global_points first");
+    // column v = 0 of the table
+    CK(cudaMemcpy2DAsync(out, 48, ctx->d_Mtab.p, (size_t)ctx->curVld * 48, 48, ctx->n_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int dmsa_b200_build_sets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, int32_t* num_gaussians, int64_t* num_memberships) {
+    CK(cudaSetDevice(ctx->device));
+    CKRC(buildSets(ctx, settings));
+    if (num_gaussians) *num_gaussians = ctx->G;
+    if (num_memberships) {
+        std::vector<int> n(ctx->G);
+        if (ctx->G) CK(cudaMemcpy(n.data(), ctx->d_cell_n.p, (size_t)ctx->G * sizeof(int), cudaMemcpyDeviceToHost));
+        int64_t M = 0;
+        for (int v : n) M += v;
+        ctx->M = M;
+        *num_memberships = M;
+    }
+    return 0;
+}
+
+int dmsa_b200_get_sets(dmsa_b200_ctx* ctx, int64_t* offsets, int32_t* members, float* info, float* weights, int32_t* level, int32_t* key, int32_t* sub) {
+    const int G = ctx->G;
+    const int64_t N = numPoints(ctx);
+    std::vector<int> start(G), n(G);
+    if (G) {
+        CK(cudaMemcpy(start.data(), ctx->d_cell_start.p, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(n.data(), ctx->d_cell_n.p, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (offsets) {
+        offsets[0] = 0;
+        for (int g = 0; g < G; ++g) offsets[g + 1] = offsets[g] + n[g];
+    }
+    if (members && G) {
+        std::vector<int> sidx((size_t)2 * N);
+        CK(cudaMemcpy(sidx.data(), ctx->d_sidx.p, (size_t)2 * N * sizeof(int), cudaMemcpyDeviceToHost));
+        int64_t o = 0;
+        for (int g = 0; g < G; ++g) {
+            std::copy(sidx.begin() + start[g], sidx.begin() + start[g] + n[g], members + o);
+            o += n[g];
+        }
+    }
+    if (info && G) CK(cudaMemcpy(info, ctx->d_cell_info.p, (size_t)G * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (weights && G) CK(cudaMemcpy(weights, ctx->d_cell_w.p, (size_t)G * sizeof(float), cudaMemcpyDeviceToHost));
+    if (level && G) CK(cudaMemcpy(level, ctx->d_cell_level.p, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
+    if (key && G) CK(cudaMemcpy(key, ctx->d_cell_key.p, (size_t)G * 3 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (sub && G) CK(cudaMemcpy(sub, ctx->d_cell_sub.p, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int dmsa_b200_get_voxel_keys(dmsa_b200_ctx* ctx, int32_t level, int32_t* keys, int64_t* root_lo, int32_t* depth) {
+    if (level < 0 || level > 1 || !ctx->levelOn[level]) ARGFAIL("get_voxel_keys: level not built");
+    const int64_t N = numPoints(ctx);
+    if (keys) CK(cudaMemcpy(keys, ctx->d_keys.p + (size_t)3 * N * level, (size_t)3 * N * sizeof(int), cudaMemcpyDeviceToHost));
+    if (root_lo)
+        for (int a = 0; a < 3; ++a) root_lo[a] = ctx->h_linfo[level].lo[a];
+    if (depth) *depth = ctx->h_linfo[level].depth;
+    return 0;
+}
+
+int dmsa_b200_eval_cost(dmsa_b200_ctx* ctx, const double* params, int32_t n_vectors, double* e) {
+    CK(cudaSetDevice(ctx->device));
+    const int P = 6 * (ctx->poses.n - 1), V = n_vectors;
+    if (V < 1) ARGFAIL("eval_cost: n_vectors < 1");
+    if (ctx->G <= 0) ARGFAIL("eval_cost: build_sets first");
+    CK(ctx->d_batch.ensure((size_t)std::max(V, P + 1) * P));
+    CK(cudaMemcpyAsync(ctx->d_batch.p, params, (size_t)V * P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CKRC(runPoseTables(ctx, V));
+    CKRC(runCost(ctx));
+    const int R = ctx->G + numExtra(ctx), Vld = ctx->curVld;
+    std::vector<double> buf((size_t)R * Vld);
+    CK(cudaMemcpyAsync(buf.data(), ctx->d_E.p, buf.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int v = 0; v < V; ++v)
+        for (int r = 0; r < R; ++r) e[(size_t)v * R + r] = buf[(size_t)r * Vld + v];
+    return 0;
+}
+
+int dmsa_b200_cost_jacobian(dmsa_b200_ctx* ctx, double* H, double* g, double* err0, double* e0, double* J) {
+    CK(cudaSetDevice(ctx->device));
+    const int P = 6 * (ctx->poses.n - 1);
+    if (ctx->G <= 0) ARGFAIL("cost_jacobian: build_sets first");
+    CKRC(uploadParams(ctx));
+    CKRC(prepareFdBatch(ctx));
+    CKRC(runCost(ctx));
+    CK(ctx->d_hg.ensure((size_t)P * P + P + 1));
+    CKRC(jtjInto(ctx, ctx->d_hg.p));
+    ctx->h_hg.resize((size_t)P * P + P + 1);
+    CK(cudaMemcpyAsync(ctx->h_hg.data(), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    const int R = ctx->G + numExtra(ctx), Vld = ctx->curVld;
+    std::vector<double> buf;
+    if (e0 || J) {
+        buf.resize((size_t)R * Vld);
+        CK(cudaMemcpyAsync(buf.data(), ctx->d_E.p, buf.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (H) std::copy(ctx->h_hg.begin(), ctx->h_hg.begin() + (size_t)P * P, H);
+    if (g) std::copy(ctx->h_hg.begin() + (size_t)P * P, ctx->h_hg.begin() + (size_t)P * P + P, g);
+    if (err0) *err0 = ctx->h_hg[(size_t)P * P + P];
+    if (e0)
+        for (int r = 0; r < R; ++r) e0[r] = buf[(size_t)r * Vld];
+    if (J) {
+        const double inv_h = 1.0 / (1.0 * (double)sqrtf(FLT_EPSILON));
+        for (int k = 0; k < P; ++k)
+            for (int r = 0; r < R; ++r) J[(size_t)k * R + r] = inv_h * (buf[(size_t)r * Vld + k + 1] - buf[(size_t)r * Vld]);
+    }
+    return 0;
+}
+
+int dmsa_b200_iteration(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, int32_t* stop, dmsa_b200_report* report, double* step, double* ls_cost) {
+    CK(cudaSetDevice(ctx->device));
+    int32_t s = 0;
+    dmsa_b200_report rep;
+    memset(&rep, 0, sizeof(rep));
+    int rc = iterationImpl(ctx, settings, &s, &rep, step, ls_cost);
+    rep.iterations = 1;
+    rep.stop_reason = s;
+    if (stop) *stop = s;
+    if (report) *report = rep;
+    return rc;
+}
+
+int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, dmsa_b200_report* report) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->model == MODEL_NONE) ARGFAIL("optimize: no model staged");
+    dmsa_b200_report rep;
+    memset(&rep, 0, sizeof(rep));
+    if (settings->use_centralization) CKRC(dmsa_b200_centralize(ctx));  // :66-67
+    int it = 0;
+    int32_t stop = DMSA_B200_STOP_MAX_ITER;
+    for (; it < settings->num_iter; ++it) {  // :69
+        CKRC(iterationImpl(ctx, settings, &stop, &rep, nullptr, nullptr));
+        if (stop != DMSA_B200_STOP_MAX_ITER) {
+            ++it;
+            break;
+        }
+    }
+    if (settings->use_centralization) CKRC(dmsa_b200_decentralize(ctx));  // :146-147
+    CKRC(updateGlobalPointsImpl(ctx));                                     // :149
+    CK(cudaStreamSynchronize(ctx->stream));
+    rep.iterations = it;
+    rep.stop_reason = stop;
+    if (report) *report = rep;
+    return 0;
+}
+
+// ---- multi-GPU row sharding -----------------------------------------------------------------------------
+int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world) {
+    if (world < 1 || rank < 0 || rank >= world) ARGFAIL("set_shard: bad rank/world");
+    ctx->rank = rank;
+    ctx->world = world;
+    return 0;
+}
+int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->G <= 0) ARGFAIL("cost_jacobian_dev: build_sets first");
+    CKRC(uploadParams(ctx));
+    CKRC(prepareFdBatch(ctx));
+    CKRC(runCost(ctx));
+    return jtjInto(ctx, hg_dev);
+}
+int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, double* ls_dev) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->G <= 0) ARGFAIL("line_search_costs_dev: build_sets first");
+    CKRC(uploadParams(ctx));
+    return lineSearchInto(ctx, step, ls_dev);
+}
+
+}  // extern "C"

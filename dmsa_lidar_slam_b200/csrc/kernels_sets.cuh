@@ -1,0 +1,548 @@
+// kernels_sets.cuh — device-side Gaussian-set construction.
+//
+// Restates on the GPU:
+//   DmsaOptimizer.h:275-350  createGaussianSets  (voxel partition, acceptance test n >= minPts && ids not all equal)
+//   PCL 1.10 OctreePointCloud::addPointsFromInputCloud / adoptBoundingBoxToPoint / getKeyBitSize /
+//            genOctreeKeyforPoint and the depth-first leaf iterator (third-party, restated from the published algorithm)
+//   Gaussians.h:130-168      addPointSet (covariance), :181-201 limitCovariance, :170-179 updateRebalancingWeights
+//
+// Pipeline per resolution level: anchor -> voxel keys (+ per-block key boxes) -> octree root growth replay ->
+// Morton codes (x most significant == PCL child index (x<<2)|(y<<1)|z) -> stable radix sort (members stay in
+// ascending point index) -> run heads -> ring test -> accept/compact -> gather member records -> per-set
+// covariance / eigen clamp / information matrix.  All of it streams the point set a constant number of times:
+// HBM-bandwidth bound.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace dmsa {
+
+#define DMSA_KEYS_BLOCK 256
+
+__device__ __forceinline__ float fmul_(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd_(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub_(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv_(float a, float b) { return __fdiv_rn(a, b); }
+
+struct LevelInfo {
+    double min0[3];   // lattice anchor: octree min after the first point (PCL getKeyBitSize on the empty tree)
+    double max0[3];
+    double res;
+    int first;        // index of the first finite point
+    int kmin[3], kmax[3];
+    long long lo[3];  // octree root origin in anchor-relative key units after all growth steps
+    int depth;
+    int n_valid;      // finite points
+    int R;            // raw (non-empty) leaves
+    int G;            // accepted sets of this level
+    int gbase;        // first set index of this level in the store
+    int error;        // 1: depth > 21
+};
+
+// ---- anchor (one thread) ---------------------------------------------------------------------
+__global__ void k_anchor(const float4* __restrict__ world, int N, float res_f, LevelInfo* info) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double res = (double)res_f;  // OctreePointCloud(const double resolution)
+    const double minValue = 1.1920928955078125e-07;  // std::numeric_limits<float>::epsilon()
+    int i = 0;
+    while (i < N) {
+        float4 p = world[i];
+        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) break;
+        ++i;
+    }
+    info->first = i;
+    info->res = res;
+    info->error = 0;
+    info->R = 0;
+    info->G = 0;
+    info->n_valid = 0;
+    for (int a = 0; a < 3; ++a) {
+        info->kmin[a] = 2147483647;
+        info->kmax[a] = -2147483647 - 1;
+        info->lo[a] = 0;
+    }
+    info->depth = 1;
+    if (i >= N) {
+        for (int a = 0; a < 3; ++a) info->min0[a] = info->max0[a] = 0.0;
+        return;
+    }
+    float4 p = world[i];
+    double c[3] = {(double)p.x, (double)p.y, (double)p.z};
+    // adoptBoundingBoxToPoint (box undefined): min = p - res/2, max = p + res/2; getKeyBitSize(): depth 1,
+    // oversize = (2 res - (max - min)) / 2 applied on both sides when > eps
+    const double side = 2.0 * res;
+    for (int a = 0; a < 3; ++a) {
+        double mn = c[a] - res / 2, mx = c[a] + res / 2;
+        double over = (side - (mx - mn)) / 2.0;
+        if (over > minValue) {
+            mn -= over;
+            mx += over;
+        }
+        info->min0[a] = mn;
+        info->max0[a] = mx;
+    }
+}
+
+// ---- voxel keys: key_a = floor((double(x_a) - min0_a) / res)   (genOctreeKeyforPoint, root-growth invariant) -------
+// Per 256-point block it also records the key box (bbmin/bbmax) and the key box of "edge" points (ebmin/ebmax):
+// points closer to a voxel face than PCL's bounding-box fudge (float eps on the upper side) or than the rounding
+// noise of the lattice arithmetic; only those can make the exact double test of k_root disagree with the integer test.
+__global__ void k_keys(const float4* __restrict__ world, int N, LevelInfo* __restrict__ info, int* __restrict__ keys, int* __restrict__ bbmin,
+                       int* __restrict__ bbmax, int* __restrict__ ebmin, int* __restrict__ ebmax) {
+    __shared__ int smin[3][DMSA_KEYS_BLOCK / 32], smax[3][DMSA_KEYS_BLOCK / 32];
+    __shared__ int semin[3][DMSA_KEYS_BLOCK / 32], semax[3][DMSA_KEYS_BLOCK / 32];
+    int ek[3] = {2147483647, 2147483647, 2147483647};
+    int ekx[3] = {-2147483647 - 1, -2147483647 - 1, -2147483647 - 1};
+    const int i = blockIdx.x * DMSA_KEYS_BLOCK + threadIdx.x;
+    const double res = info->res;
+    int k[3] = {2147483647, 2147483647, 2147483647};
+    int kx[3] = {-2147483647 - 1, -2147483647 - 1, -2147483647 - 1};
+    bool valid = false;
+    if (i < N) {
+        float4 p = world[i];
+        valid = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+        if (valid) {
+            double c[3] = {(double)p.x, (double)p.y, (double)p.z};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                double q = (c[a] - info->min0[a]) / res;
+                double fl = floor(q);
+                k[a] = kx[a] = (int)fl;
+                double frac = q - fl;
+                if (frac < 1e-9 || (1.0 - frac) * res <= 2.4e-7) ek[a] = ekx[a] = (int)fl;
+            }
+        }
+        keys[3 * (size_t)i + 0] = valid ? k[0] : (-2147483647 - 1);
+        keys[3 * (size_t)i + 1] = valid ? k[1] : (-2147483647 - 1);
+        keys[3 * (size_t)i + 2] = valid ? k[2] : (-2147483647 - 1);
+    }
+    // block bounding box of keys
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        int mn = k[a], mx = kx[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        int emn = ek[a], emx = ekx[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            emn = min(emn, __shfl_xor_sync(0xffffffffu, emn, o));
+            emx = max(emx, __shfl_xor_sync(0xffffffffu, emx, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            smin[a][threadIdx.x >> 5] = mn;
+            smax[a][threadIdx.x >> 5] = mx;
+            semin[a][threadIdx.x >> 5] = emn;
+            semax[a][threadIdx.x >> 5] = emx;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int a = threadIdx.x;
+        int mn = smin[a][0], mx = smax[a][0], emn = semin[a][0], emx = semax[a][0];
+        for (int w = 1; w < DMSA_KEYS_BLOCK / 32; ++w) {
+            mn = min(mn, smin[a][w]);
+            mx = max(mx, smax[a][w]);
+            emn = min(emn, semin[a][w]);
+            emx = max(emx, semax[a][w]);
+        }
+        bbmin[3 * blockIdx.x + a] = mn;
+        bbmax[3 * blockIdx.x + a] = mx;
+        ebmin[3 * blockIdx.x + a] = emn;
+        ebmax[3 * blockIdx.x + a] = emx;
+        if (mn <= mx) {
+            atomicMin(&info->kmin[a], mn);
+            atomicMax(&info->kmax[a], mx);
+        }
+    }
+}
+
+// ---- octree root growth replay (adoptBoundingBoxToPoint for every later point, in index order) -----------------
+// One block.  The box only grows, so violators are found in increasing index order; per-block key boxes skip
+// blocks that cannot contain a violator (conservative integer test), candidates are re-tested exactly in double.
+__global__ void k_root(const float4* __restrict__ world, int N, LevelInfo* __restrict__ info, const int* __restrict__ bbmin,
+                       const int* __restrict__ bbmax, const int* __restrict__ ebmin, const int* __restrict__ ebmax) {
+    __shared__ double mn[3], mx[3];
+    __shared__ long long lo[3];
+    __shared__ int depth, found, cand;
+    const double minValue = 1.1920928955078125e-07;
+    const int nb = (N + DMSA_KEYS_BLOCK - 1) / DMSA_KEYS_BLOCK;
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = info->min0[a];
+            mx[a] = info->max0[a];
+            lo[a] = 0;
+        }
+        depth = 1;
+    }
+    __syncthreads();
+    const double res = info->res;
+    int b = 0;  // first block not yet cleared
+    while (b < nb) {
+        // 1. first candidate block >= b
+        if (threadIdx.x == 0) cand = nb;
+        __syncthreads();
+        for (int base = b; base < nb; base += blockDim.x) {
+            int bi = base + threadIdx.x;
+            bool c = false;
+            if (bi < nb) {
+                long long side = ((long long)1 << depth);
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    int kmn = bbmin[3 * bi + a], kmx = bbmax[3 * bi + a];
+                    if (kmn <= kmx) c = c || ((long long)kmn < lo[a]) || ((long long)kmx >= lo[a] + side);
+                    int emn = ebmin[3 * bi + a], emx = ebmax[3 * bi + a];
+                    if (emn <= emx) c = c || ((long long)emn <= lo[a]) || ((long long)emx >= lo[a] + side - 1);
+                }
+            }
+            if (c) atomicMin(&cand, bi);
+            __syncthreads();
+            const int cv = cand;
+            __syncthreads();
+            if (cv < nb) break;
+        }
+        __syncthreads();
+        if (cand >= nb) break;
+        b = cand;
+        // 2. exact test of the candidate block's points, repeatedly (each growth step may leave later violators)
+        while (true) {
+            if (threadIdx.x == 0) found = 2147483647;
+            __syncthreads();
+            for (int off = threadIdx.x; off < DMSA_KEYS_BLOCK; off += blockDim.x) {
+                int i = b * DMSA_KEYS_BLOCK + off;
+                if (i < N) {
+                    float4 p = world[i];
+                    if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+                        double c[3] = {(double)p.x, (double)p.y, (double)p.z};
+                        bool viol = false;
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) viol = viol || (c[a] < mn[a]) || (c[a] >= mx[a]);
+                        if (viol) atomicMin(&found, i);
+                    }
+                }
+            }
+            __syncthreads();
+            if (found == 2147483647) break;
+            if (threadIdx.x == 0) {
+                float4 p = world[found];
+                double c[3] = {(double)p.x, (double)p.y, (double)p.z};
+                while (true) {
+                    bool up[3], any = false;
+                    for (int a = 0; a < 3; ++a) {
+                        bool lowv = c[a] < mn[a];
+                        up[a] = c[a] >= mx[a];
+                        any = any || lowv || up[a];
+                    }
+                    if (!any) break;
+                    double side = (double)(1u << depth) * res;
+                    for (int a = 0; a < 3; ++a)
+                        if (!up[a]) {
+                            mn[a] -= side;
+                            lo[a] -= (long long)1 << depth;
+                        }
+                    depth++;
+                    side = (double)(1u << depth) * res - minValue;
+                    for (int a = 0; a < 3; ++a) mx[a] = mn[a] + side;
+                    if (depth > 21) break;
+                }
+            }
+            __syncthreads();
+            if (depth > 21) break;
+        }
+        if (depth > 21) break;
+        b = b + 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) info->lo[a] = lo[a];
+        info->depth = depth;
+        info->error = depth > 21 ? 1 : 0;
+    }
+}
+
+__device__ __forceinline__ unsigned long long spread3(unsigned long long x) {  // 21 bits -> every third bit
+    x &= 0x1fffffull;
+    x = (x | (x << 32)) & 0x1f00000000ffffull;
+    x = (x | (x << 16)) & 0x1f0000ff0000ffull;
+    x = (x | (x << 8)) & 0x100f00f00f00f00full;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+
+// Morton code of (key - root origin): depth-first leaf order of the octree (x is the most significant axis)
+__global__ void k_morton(const int* __restrict__ keys, int N, const LevelInfo* __restrict__ info, unsigned long long* __restrict__ code,
+                         int* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int kx = keys[3 * (size_t)i], ky = keys[3 * (size_t)i + 1], kz = keys[3 * (size_t)i + 2];
+    unsigned long long m;
+    if (kx == (-2147483647 - 1)) {
+        m = 1ull << (3 * info->depth);  // non-finite points sort behind every leaf (PCL skips them)
+    } else {
+        unsigned long long x = (unsigned long long)((long long)kx - info->lo[0]);
+        unsigned long long y = (unsigned long long)((long long)ky - info->lo[1]);
+        unsigned long long z = (unsigned long long)((long long)kz - info->lo[2]);
+        m = (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
+    }
+    code[i] = m;
+    idx[i] = i;
+}
+
+__global__ void k_heads(const unsigned long long* __restrict__ code, int N, const LevelInfo* __restrict__ info, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned long long inval = 1ull << (3 * info->depth);
+    unsigned long long m = code[i];
+    flag[i] = (m < inval) && (i == 0 || code[i - 1] != m) ? 1 : 0;
+}
+
+// scan = inclusive scan of flag.  Writes raw leaf starts, leaf count, finite count.
+__global__ void k_raw_starts(const unsigned long long* __restrict__ code, const int* __restrict__ flag, const int* __restrict__ scan, int N,
+                             LevelInfo* __restrict__ info, int* __restrict__ raw_start) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned long long inval = 1ull << (3 * info->depth);
+    const bool valid = code[i] < inval;
+    if (flag[i]) raw_start[scan[i] - 1] = i;
+    if (valid && (i == N - 1 || code[i + 1] >= inval)) {
+        info->n_valid = i + 1;
+        info->R = scan[i];
+        raw_start[scan[i]] = i + 1;
+    }
+}
+
+// DmsaOptimizer.h:303-307: max(ring) != min(ring)  <=>  some member's ring differs from the first member's
+__global__ void k_ring_diff(const int* __restrict__ idx, const int* __restrict__ scan, const int* __restrict__ raw_start, const int* __restrict__ ring,
+                            const LevelInfo* __restrict__ info, int* __restrict__ raw_diff) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= info->n_valid) return;
+    const int c = scan[i] - 1;
+    if (ring[idx[i]] != ring[idx[raw_start[c]]]) raw_diff[c] = 1;
+}
+
+__global__ void k_accept(const int* __restrict__ raw_start, const int* __restrict__ raw_diff, const LevelInfo* __restrict__ info, int minPts,
+                         int* __restrict__ acc_flag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= info->R) return;
+    int n = raw_start[c + 1] - raw_start[c];
+    acc_flag[c] = (n >= minPts && raw_diff[c]) ? 1 : 0;
+}
+
+struct CellStore {
+    int* start;   // first member record (index into the 2N-long sorted member arrays)
+    int* n;       // members
+    int* level;
+    int* key;     // 3 per set
+    int* sub;
+    float* info;  // 9 per set, row-major
+    float* w0;    // (1/n) * observation weight
+    float* w;     // rebalancing weight
+};
+
+// acc_scan = exclusive scan of acc_flag.  gbase_src: LevelInfo of the previous level (or null).
+__global__ void k_emit_cells(const int* __restrict__ raw_start, const int* __restrict__ acc_flag, const int* __restrict__ acc_scan,
+                             const int* __restrict__ idx, const int* __restrict__ keys, LevelInfo* __restrict__ info,
+                             const LevelInfo* __restrict__ prev, int level, int mbase, CellStore cs, int cap) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = info->R;
+    const int gbase = prev ? prev->gbase + prev->G : 0;
+    if (c == 0) {
+        info->gbase = gbase;
+        info->G = R > 0 ? acc_scan[R - 1] + acc_flag[R - 1] : 0;
+    }
+    if (c >= R || !acc_flag[c]) return;
+    const int g = gbase + acc_scan[c];
+    if (g >= cap) return;
+    const int s = raw_start[c];
+    cs.start[g] = mbase + s;
+    cs.n[g] = raw_start[c + 1] - s;
+    cs.level[g] = level;
+    cs.sub[g] = 0;
+    const int p = idx[s];
+    cs.key[3 * g] = keys[3 * (size_t)p];
+    cs.key[3 * g + 1] = keys[3 * (size_t)p + 1];
+    cs.key[3 * g + 2] = keys[3 * (size_t)p + 2];
+}
+
+// Member records in sorted order: rec = (local xyz, transform-row index as int bits; -1 = static point, no transform),
+// wrec = world xyz at the base pose (input of the covariance).
+__global__ void k_gather(const int* __restrict__ idx, const LevelInfo* __restrict__ info, const float4* __restrict__ local,
+                         const int* __restrict__ tid, const float4* __restrict__ world, float4* __restrict__ rec, float4* __restrict__ wrec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= info->n_valid) return;
+    const int p = idx[i];
+    float4 l = local[p];
+    l.w = __int_as_float(tid[p]);
+    rec[i] = l;
+    wrec[i] = world[p];
+}
+
+// cyclic Jacobi, symmetric 3x3, double
+__device__ inline void jacobi3(const double Ain[9], double l[3], double V[9]) {
+    double A[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        A[i] = Ain[i];
+        V[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    }
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = A[1] * A[1] + A[2] * A[2] + A[5] * A[5];
+        if (off < 1e-300) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = (pq == 2) ? 1 : 0;
+            const int q = (pq == 0) ? 1 : 2;
+            const int r = 3 - p - q;
+            double apq = A[p * 3 + q];
+            if (apq == 0.0) continue;
+            double app = A[p * 3 + p], aqq = A[q * 3 + q];
+            double theta = (aqq - app) / (2.0 * apq);
+            double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            double c = 1.0 / sqrt(t * t + 1.0);
+            double s = t * c;
+            double arp = A[r * 3 + p], arq = A[r * 3 + q];
+            A[p * 3 + p] = app - t * apq;
+            A[q * 3 + q] = aqq + t * apq;
+            A[p * 3 + q] = A[q * 3 + p] = 0.0;
+            A[r * 3 + p] = A[p * 3 + r] = c * arp - s * arq;
+            A[r * 3 + q] = A[q * 3 + r] = s * arp + c * arq;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+                V[k * 3 + p] = c * vkp - s * vkq;
+                V[k * 3 + q] = s * vkp + c * vkq;
+            }
+        }
+    }
+    l[0] = A[0];
+    l[1] = A[4];
+    l[2] = A[8];
+}
+
+__device__ __forceinline__ float cof3(const float* m, int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return fsub_(fmul_(m[i1 * 3 + j1], m[i2 * 3 + j2]), fmul_(m[i1 * 3 + j2], m[i2 * 3 + j1]));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One warp per accepted set.  Gaussians.h:146-154, 181-201 (covariance, eigenvalue clamp, information matrix).
+__global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= G) return;
+    const int s = cs.start[g], n = cs.n[g];
+    // colwise().mean(): exactly-rounded sum, float division
+    double sx = 0, sy = 0, sz = 0;
+    for (int j = lane; j < n; j += 32) {
+        float4 p = wrec[s + j];
+        sx += (double)p.x;
+        sy += (double)p.y;
+        sz += (double)p.z;
+    }
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    sz = warp_sum(sz);
+    const float nf = (float)n;
+    const float mx = fdiv_((float)sx, nf), my = fdiv_((float)sy, nf), mz = fdiv_((float)sz, nf);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
+    for (int j = lane; j < n; j += 32) {
+        float4 p = wrec[s + j];
+        double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
+        a0 += cx * cx;
+        a1 += cx * cy;
+        a2 += cx * cz;
+        a3 += cy * cy;
+        a4 += cy * cz;
+        a5 += cz * cz;
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    a3 = warp_sum(a3);
+    a4 = warp_sum(a4);
+    a5 = warp_sum(a5);
+    if (lane != 0) return;
+    const float den = (float)(n - 1);
+    const float cxx = fdiv_((float)a0, den), cxy = fdiv_((float)a1, den), cxz = fdiv_((float)a2, den);
+    const float cyy = fdiv_((float)a3, den), cyz = fdiv_((float)a4, den), czz = fdiv_((float)a5, den);
+    double A[9] = {cxx, cxy, cxz, cxy, cyy, cyz, cxz, cyz, czz};
+    double l[3], V[9];
+    jacobi3(A, l, V);
+    double lf[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) lf[k] = (double)fmaxf((float)l[k], 0.0001f);  // Gaussians.h:191-194
+    float cov[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int rr = r < c ? r : c, cc = r < c ? c : r;
+            double v = V[rr * 3 + 0] * lf[0] * V[cc * 3 + 0] + V[rr * 3 + 1] * lf[1] * V[cc * 3 + 1] + V[rr * 3 + 2] * lf[2] * V[cc * 3 + 2];
+            cov[r * 3 + c] = (float)v;
+        }
+    // Gaussians.h:154 cov.inverse(): Eigen fixed-size 3x3 cofactor inverse, float
+    float c0 = cof3(cov, 0, 0), c1 = cof3(cov, 1, 0), c2 = cof3(cov, 2, 0);
+    float det = fadd_(fmul_(c0, cov[0]), fadd_(fmul_(c1, cov[3]), fmul_(c2, cov[6])));
+    float invdet = fdiv_(1.0f, det);
+    float* I = cs.info + 9 * (size_t)g;
+    I[0] = fmul_(c0, invdet);
+    I[1] = fmul_(c1, invdet);
+    I[2] = fmul_(c2, invdet);
+    I[3] = fmul_(cof3(cov, 0, 1), invdet);
+    I[4] = fmul_(cof3(cov, 1, 1), invdet);
+    I[7] = fmul_(cof3(cov, 1, 2), invdet);
+    I[5] = fmul_(cof3(cov, 2, 1), invdet);
+    I[6] = fmul_(cof3(cov, 0, 2), invdet);
+    I[8] = fmul_(cof3(cov, 2, 2), invdet);
+    cs.w0[g] = fmul_(fdiv_(1.0f, nf), 1.0f);  // Gaussians.h:172-175, observation weight 1 (OptimizablePointSet.h:52)
+}
+
+// Gaussians.h:177: w / w.mean()   (one block; deterministic double reduction, one rounding)
+__global__ void k_weights(CellStore cs, int G) {
+    __shared__ double part[1024];
+    double s = 0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) s += (double)cs.w0[g];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    const float mean = fdiv_((float)part[0], (float)G);
+    for (int g = threadIdx.x; g < G; g += blockDim.x) cs.w[g] = fdiv_(cs.w0[g], mean);
+}
+
+// ---- work decomposition for the cost kernels: fixed-size chunks of members ----------------------------------------
+struct Chunk {
+    int cell, start, count, first;  // first: index of the set's first chunk
+};
+__global__ void k_chunk_counts(CellStore cs, int G, int CH, int rank, int world, int* __restrict__ nchunk) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    nchunk[g] = (g % world == rank) ? (cs.n[g] + CH - 1) / CH : 0;
+}
+// chunk_off = exclusive scan of nchunk (G+1 entries, last = total)
+__global__ void k_chunk_fill(CellStore cs, int G, int CH, const int* __restrict__ nchunk, const int* __restrict__ chunk_off, Chunk* __restrict__ chunks) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int nc = nchunk[g], o = chunk_off[g], s = cs.start[g], n = cs.n[g];
+    for (int c = 0; c < nc; ++c) {
+        Chunk ch;
+        ch.cell = g;
+        ch.start = s + c * CH;
+        ch.count = min(CH, n - c * CH);
+        ch.first = o;
+        chunks[o + c] = ch;
+    }
+}
+
+}  // namespace dmsa

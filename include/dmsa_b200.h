@@ -1,0 +1,188 @@
+/* ============================================================================
+ * dmsa_b200.h — C-ABI of libdmsa_b200.so: the B200-native (sm_100a) DMSA inner loop.
+ *
+ * Drop-in boundary for ONE hot path of davidskdds/DMSA_LiDAR_SLAM (@2d20a58):
+ *     DmsaOptimizer<PointT>::optimizeSet(OptimizablePointSet<PointT>&, DmsaOptimSettings)
+ *     include/DMSA/DmsaOptimizer.h:54-150 and everything it calls per cost evaluation.
+ * The reference has no FFI; its boundary is the C++ virtual interface
+ * include/DMSA/OptimizablePointSet.h:18-56.  Because the optimizer calls back into the two
+ * concrete point-set models on every cost evaluation (ContinuousTrajectory, MapManagement),
+ * the GPU path absorbs the hot members of both models; the entry
+ * points below are what a C++ adapter with the reference's own signature binds to
+ * (see INTEGRATION.md and dmsa_lidar_slam_b200/host/DmsaOptimizerB200.h).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns an int
+ * status (0 = DMSA_B200_OK); no exceptions cross the ABI; host buffers are caller-owned,
+ * device buffers are context-owned; one context per optimizer instance; a context is not
+ * thread-safe (the reference optimizer is not re-entrant either: DmsaOptimizer.h:45-48).
+ * Pose arrays are 3 x n column-major doubles exactly like Eigen::Matrix3Xd (Poses.h:19-20).
+ * ========================================================================== */
+#ifndef DMSA_B200_H
+#define DMSA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dmsa_b200_ctx dmsa_b200_ctx;
+
+enum {
+    DMSA_B200_OK = 0,
+    DMSA_B200_ERR_CUDA = 1,          /* a CUDA runtime call or kernel failed (see dmsa_b200_last_error) */
+    DMSA_B200_ERR_ARG = 2,           /* invalid argument / call order */
+    DMSA_B200_ERR_NO_DEVICE = 3,     /* no CUDA device: the product has NO CPU fallback */
+    DMSA_B200_ERR_UNSUPPORTED = 4    /* input outside the supported envelope (e.g. homogeneous w != 1) */
+};
+
+/* Stop reasons of the optimisation loop (the reference prints a message and breaks). */
+enum {
+    DMSA_B200_STOP_MAX_ITER = 0,     /* loop ran num_iter iterations                       DmsaOptimizer.h:69   */
+    DMSA_B200_STOP_FEW_GAUSSIANS = 1,/* numPointSets < min_num_gaussians                   DmsaOptimizer.h:89-93 */
+    DMSA_B200_STOP_NAN = 2,          /* NaN in the step; parameters restored               DmsaOptimizer.h:116-122 */
+    DMSA_B200_STOP_NO_IMPROVEMENT = 3,/* line search found nothing; set left at p+0.9*step DmsaOptimizer.h:130-134 */
+    DMSA_B200_STOP_EPSILON = 4       /* ||step|| < epsilon                                  DmsaOptimizer.h:139-143 */
+};
+
+/* Field-for-field mirror of struct DmsaOptimSettings, DmsaOptimizer.h:25-39 (bool -> int32). */
+typedef struct dmsa_b200_settings {
+    int32_t num_iter;               /* = 15      */
+    double epsilon;                 /* = 1e-5    */
+    int32_t use_analytic_jacobi;    /* = false; never read by the reference (DmsaOptimizer.h:29) nor here */
+    double step_length_optim;       /* = 0.05    */
+    double max_step;                /* = 0.01    */
+    int32_t gauss_split;            /* = false   */
+    float grid_size_1_factor;       /* = 2.0     */
+    float grid_size_2_factor;       /* = 5.0     */
+    int32_t min_num_points_per_set; /* = 6       */
+    int32_t min_num_gaussians;      /* = 30      */
+    float lambda_diag;              /* = 0.00001 */
+    int32_t use_centralization;     /* = true    */
+} dmsa_b200_settings;
+
+/* PointStampId, include/DMSA/PointStampId.h:33-45 (32 bytes, 16-aligned). */
+typedef struct dmsa_b200_point_stamp_id {
+    float x, y, z, w;
+    double stamp;
+    int32_t id;
+    int32_t isStatic;
+} dmsa_b200_point_stamp_id;
+
+/* pcl::PointNormal (48 bytes): data[4], data_n[4], curvature, 3 floats padding. */
+typedef struct dmsa_b200_point_normal {
+    float x, y, z, w;
+    float nx, ny, nz, nw;
+    float curvature;
+    float pad[3];
+} dmsa_b200_point_normal;
+
+/* Result of dmsa_b200_optimize / per-iteration trace. */
+typedef struct dmsa_b200_report {
+    int32_t iterations;      /* loop bodies executed (incl. the one that stopped) */
+    int32_t stop_reason;     /* DMSA_B200_STOP_* */
+    int32_t num_gaussians;   /* G of the last iteration */
+    int64_t num_memberships; /* M of the last iteration */
+    int32_t num_extra;       /* E additional residual rows */
+    int32_t best_step;       /* line-search winner k (0..9) of the last iteration */
+    double error0;           /* e0^T e0 of the last iteration */
+    double step_norm;        /* ||clamped step||_2 of the last iteration */
+} dmsa_b200_report;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL for an own stream. */
+int dmsa_b200_create(dmsa_b200_ctx** out, int device, void* cuda_stream);
+void dmsa_b200_destroy(dmsa_b200_ctx* ctx);
+const char* dmsa_b200_last_error(const dmsa_b200_ctx* ctx);
+int dmsa_b200_version(void);
+/* number of kernels this library has launched on the context's stream since creation */
+int64_t dmsa_b200_launch_count(const dmsa_b200_ctx* ctx);
+int dmsa_b200_synchronize(dmsa_b200_ctx* ctx);
+
+/* ---- sliding-window model: hot members of ContinuousTrajectory ---------------------------- */
+/* initTraj(t_min, t_max, numControlPoses, useImu, dt_res)        ContinuousTrajectory.h:301-346 */
+int dmsa_b200_traj_init(dmsa_b200_ctx* ctx, double t_min, double t_max, int32_t n_poses, int32_t use_imu, double dt_res);
+/* registerPcBuffer: scans in chronological ring-buffer order; computes tformIdPerPoint on device,
+ * minGridSize = min(grid_sizes)                                  ContinuousTrajectory.h:228-261 */
+int dmsa_b200_traj_register_scans(dmsa_b200_ctx* ctx, int32_t n_scans, const dmsa_b200_point_stamp_id* const* scans,
+                                  const int64_t* sizes, const float* grid_sizes);
+/* addStaticPoints / removeStaticPoints                            ContinuousTrajectory.h:158-187 */
+int dmsa_b200_traj_add_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_stamp_id* pts, int64_t n);
+int dmsa_b200_traj_remove_static_points(dmsa_b200_ctx* ctx);
+/* window timing as computed by initTraj (any pointer may be NULL) */
+int dmsa_b200_traj_get_timing(dmsa_b200_ctx* ctx, int32_t* n_total, double* horizon, double* ctrl_stamps /*n_poses*/,
+                              double* traj_time /*n_total*/, int32_t* param_indices /*n_poses*/);
+/* per-point dense-pose index (tformIdPerPoint), n_scan_points entries */
+int dmsa_b200_traj_get_tform_ids(dmsa_b200_ctx* ctx, int32_t* out);
+/* IMU factor constants consumed by updateImuError                  ContinuousTrajectory.h:520-553, 603-663
+ * preint_rot: n_poses x 9 row-major, preint_pos/vel: n_poses x 3, cov_inv: n_poses x 81 row-major (index 0 unused) */
+int dmsa_b200_traj_set_imu_factors(dmsa_b200_ctx* ctx, const double* preint_rot, const double* preint_pos, const double* preint_vel,
+                                   const double* cov_inv, double balancing_imu, const double* gravity3);
+
+/* ---- keyframe-submap model: hot members of MapManagement ---------------------------------- */
+int dmsa_b200_kf_init(dmsa_b200_ctx* ctx, int32_t n_keyframes);
+/* keyframe k: local PointNormal cloud + ring ids + gridSize       KeyframeData.h:17-33 */
+int dmsa_b200_kf_set_keyframe(dmsa_b200_ctx* ctx, int32_t k, const dmsa_b200_point_normal* pts, const int32_t* ring_ids, int64_t n,
+                              float grid_size);
+int dmsa_b200_kf_commit(dmsa_b200_ctx* ctx);
+/* gravity / odometry factors                                      MapManagement.h:210-252 */
+int dmsa_b200_kf_set_gravity_terms(dmsa_b200_ctx* ctx, const double* measured_gravity /*n x 3*/, const int32_t* plausible, double balance);
+int dmsa_b200_kf_set_odometry_terms(dmsa_b200_ctx* ctx, const double* rel_transl /*n x 3*/, const double* rel_orient_mat /*n x 9 row-major*/,
+                                    double balance);
+
+/* ---- poses / parameters (both models) ------------------------------------------------------ */
+/* relativePoses.Orientations / .Translations, 3 x n_poses column-major                  Poses.h:19-20 */
+int dmsa_b200_set_relative_poses(dmsa_b200_ctx* ctx, const double* rel_orient, const double* rel_transl);
+int dmsa_b200_get_poses(dmsa_b200_ctx* ctx, double* rel_orient, double* rel_transl, double* glob_orient, double* glob_transl);
+int32_t dmsa_b200_num_params(const dmsa_b200_ctx* ctx);                 /* P = 6 (n_poses - 1)            Poses.h:59-62 */
+int dmsa_b200_get_pose_parameters(dmsa_b200_ctx* ctx, double* params);  /* getParamsAsVector              Poses.h:64-70 */
+int dmsa_b200_set_pose_parameters(dmsa_b200_ctx* ctx, const double* params); /* setParamsFromVector       Poses.h:72-76 */
+int dmsa_b200_centralize(dmsa_b200_ctx* ctx);    /* ContinuousTrajectory.h:75-88  (no-op for keyframes: MapManagement.h:73-79) */
+int dmsa_b200_decentralize(dmsa_b200_ctx* ctx);  /* ContinuousTrajectory.h:89-100 */
+
+/* ---- the hot path, step by step ------------------------------------------------------------ */
+/* updateGlobalPoints at the current parameters (device resident)   ContinuousTrajectory.h:129-156 | MapManagement.h:120-149 */
+int dmsa_b200_update_global_points(dmsa_b200_ctx* ctx);
+int64_t dmsa_b200_num_points(const dmsa_b200_ctx* ctx);
+/* download globalPoints as N x 4 floats (xyzw); normals N x 4 (keyframe model only, may be NULL) */
+int dmsa_b200_get_global_points(dmsa_b200_ctx* ctx, float* xyzw, float* normals);
+/* dense local->global transforms of the current parameters: n_total x 12 floats (rows 0..2 of Matrix4f) */
+int dmsa_b200_traj_get_dense_tforms(dmsa_b200_ctx* ctx, float* out);
+
+/* reset + createGaussianSets(res1) + createGaussianSets(res2) + updateRebalancingWeights on the current
+ * global points                                   DmsaOptimizer.h:78-96, 275-350; Gaussians.h:130-201 */
+int dmsa_b200_build_sets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, int32_t* num_gaussians, int64_t* num_memberships);
+/* debug getters (any pointer may be NULL): CSR offsets[G+1], members[M] (ascending point index per set), info[G*9] row-major,
+ * weights[G], level[G] (0/1), key[G*3] (voxel key relative to the octree anchor), sub[G] (0 unsplit, 1/2 split halves).
+ * Row order == the reference's leaf-iterator order. */
+int dmsa_b200_get_sets(dmsa_b200_ctx* ctx, int64_t* offsets, int32_t* members, float* info, float* weights, int32_t* level, int32_t* key,
+                       int32_t* sub);
+/* per-point voxel keys of one resolution level (3 ints per point) + octree root origin/depth as PCL would hold them */
+int dmsa_b200_get_voxel_keys(dmsa_b200_ctx* ctx, int32_t level, int32_t* keys /*N*3*/, int64_t* root_lo /*3*/, int32_t* depth);
+
+/* updateErrorTerms for a batch of V parameter vectors (row-major V x P) -> e row-major V x (G+E)
+ * one call == V cost evaluations of SURVEY §3.3                    DmsaOptimizer.h:234-273 */
+int dmsa_b200_eval_cost(dmsa_b200_ctx* ctx, const double* params, int32_t n_vectors, double* e);
+/* calcNumericJacobian + H = J^T J + g = J^T e0 at the current parameters.
+ * H: P x P row-major (symmetric, WITHOUT lambda), g: P, err0 = e0^T e0; e0 (G+E) and J ((G+E) x P column-major like
+ * Eigen::MatrixXd) are optional (NULL to skip)                      DmsaOptimizer.h:99-107, 199-232 */
+int dmsa_b200_cost_jacobian(dmsa_b200_ctx* ctx, double* H, double* g, double* err0, double* e0, double* J);
+/* one loop body (DmsaOptimizer.h:69-144) at the current state; *stop = DMSA_B200_STOP_* (0 = continue).
+ * trace pointers optional: step[P] (clamped), ls_cost[9]. */
+int dmsa_b200_iteration(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, int32_t* stop, dmsa_b200_report* report, double* step,
+                        double* ls_cost);
+/* the whole optimizeSet: centralize, loop, decentralize, final updateGlobalPoints   DmsaOptimizer.h:54-150 */
+int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, dmsa_b200_report* report);
+
+/* ---- multi-GPU row sharding: this rank owns the Gaussians g with g % world == rank ------------- */
+int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world);
+/* device-resident variants for NCCL: pointers are DEVICE memory owned by the caller (e.g. torch tensors).
+ * hg_dev: P*P + P + 1 doubles = [H | g | err0] partial sums over this rank's rows. */
+int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev);
+/* 9 partial line-search costs for step (host P doubles) into ls_dev[9] (device) */
+int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, double* ls_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMSA_B200_H */
