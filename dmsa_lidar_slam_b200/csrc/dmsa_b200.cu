@@ -644,6 +644,23 @@ int updateGlobalPointsImpl(dmsa_b200_ctx* ctx) {
     return transformBase(ctx);
 }
 
+// Reference quirk that changes results: ContinuousTrajectory::setPoseParameters (ContinuousTrajectory.h:124-127) only
+// writes the RELATIVE poses; the global poses are refreshed by the next updateGlobalPoints().  Hence, when the loop
+// ends, decentralize() (:89-93) runs global2relative() on the global poses of the LAST COST EVALUATION (the k = 9
+// line-search trial, or the last forward-difference vector on the NaN path) and overwrites the accepted relative
+// poses with them.  We keep the host pose state exactly like that: global poses <- chain(p_last_eval), relative
+// poses <- p_current.  MapManagement::setPoseParameters (MapManagement.h:197-202) refreshes the chain itself.
+void staleGlobal(dmsa_b200_ctx* ctx, const double* p_last_eval, const double* p_current) {
+    if (ctx->model == MODEL_KF) {
+        ctx->poses.setParams(p_current);
+        ctx->poses.relative2global();
+        return;
+    }
+    ctx->poses.setParams(p_last_eval);
+    ctx->poses.relative2global();
+    ctx->poses.setParams(p_current);
+}
+
 int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* stop, dmsa_b200_report* rep, double* step_out, double* ls_out) {
     const int P = 6 * (ctx->poses.n - 1);
     if (P <= 0) ARGFAIL("need at least two poses");
@@ -674,8 +691,10 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     ctx->lastErr0 = error0;
     std::vector<double> step;
     if (solveStep(st, ctx->h_hg.data(), P, step)) {  // :113-122
-        ctx->poses.setParams(paramVec.data());
-        if (ctx->model == MODEL_KF) ctx->poses.relative2global();
+        // the last cost evaluation of calcNumericJacobian was p + h e_{P-1}: its global poses stay behind (see staleGlobal)
+        std::vector<double> plast = paramVec;
+        plast[P - 1] += 1.0 * (double)sqrtf(FLT_EPSILON);
+        staleGlobal(ctx, plast.data(), paramVec.data());
         *stop = DMSA_B200_STOP_NAN;
         return 0;
     }
@@ -701,18 +720,16 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     }
     if (step_out) std::copy(step.begin(), step.end(), step_out);
     if (ls_out) std::copy(ls, ls + 9, ls_out);
-    std::vector<double> pnew(P);
+    std::vector<double> pnew(P), plast(P);
+    for (int i = 0; i < P; ++i) plast[i] = paramVec[i] + 0.1 * 9.0 * step[i];  // last trial point of adaptiveStepSize
     if (best == 0) {
         // :130-134 — no restore: the set stays at the last trial point p + 0.9*step
-        for (int i = 0; i < P; ++i) pnew[i] = paramVec[i] + 0.1 * 9.0 * step[i];
-        ctx->poses.setParams(pnew.data());
-        if (ctx->model == MODEL_KF) ctx->poses.relative2global();
+        staleGlobal(ctx, plast.data(), plast.data());
         *stop = DMSA_B200_STOP_NO_IMPROVEMENT;
         return 0;
     }
     for (int i = 0; i < P; ++i) pnew[i] = paramVec[i] + 0.1 * (double)best * step[i];
-    ctx->poses.setParams(pnew.data());  // :136
-    if (ctx->model == MODEL_KF) ctx->poses.relative2global();
+    staleGlobal(ctx, plast.data(), pnew.data());  // :136 setPoseParameters(paramVec)
     if (nrm < st->epsilon) *stop = DMSA_B200_STOP_EPSILON;  // :139-143
     return 0;
 }
