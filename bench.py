@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — DMSA iterations/s (and point-Jacobians/s) on B200 vs the CPU reference path.
+
+A "step" is ONE DMSA iteration = the loop body DmsaOptimizer.h:69-144: base transform, two voxel-set builds,
+weights, e0, the P forward-difference cost evaluations, H = J^T J, the LM step and the 9-point line search
+(P + 10 cost evaluations).  Workload at N = 1: BASELINE.json configs[1] (sliding window, 10 scans x 65 536 points
++ 50 000 static points, 20 control poses).  N > 1 (default): one independent window per rank ("replicas only" for the
+sliding-window pass, north star); `--workload keyframe` runs the keyframe-bundle pass with an NCCL all-reduce.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference            # the CPU path (oracle port) on the host cores, same JSON shape
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SETTINGS = dict(num_iter=1, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10, min_num_gaussians=30)
+METRIC = "DMSA iterations/sec"
+UNIT = "iterations/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, val in zip(names, r[5:9]):
+                    if val.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def oracle_cpu_baseline(win, threads, iters=2):
+    """The CPU path (oracle port of the reference arithmetic, oracle/dmsa_oracle.cpp) timed on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+
+    m = ob.OracleModel.from_window(win)
+    m.set_threads(threads)
+    m.set_mode(0)
+    m.centralize()
+    st = ob.settings(**SETTINGS)
+    p0 = m.get_params()
+    t, status = m.time_iteration(st)  # warm (page faults)
+    ts = []
+    for _ in range(iters):
+        m.set_params(p0)
+        t, status = m.time_iteration(st)
+        ts.append(t)
+    s = m.sets()
+    return dict(seconds_per_iteration=float(np.median(ts)), M=int(s["M"]), G=int(s["G"]), status=status, threads=threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from dmsa_lidar_slam_b200 import synth
+
+    win = synth.make_config(args.config)
+    threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+
+    m = ob.OracleModel.from_window(win)
+    m.set_threads(threads)
+    m.set_mode(0)
+    m.centralize()
+    st = ob.settings(**SETTINGS)
+    p0 = m.get_params()
+    for _ in range(max(1, min(args.warmup, 2))):
+        m.set_params(p0)
+        m.time_iteration(st)
+    t_total = 0.0
+    steps = min(args.steps, 10)  # bounded: each step is one full CPU iteration of the same workload
+    for _ in range(steps):
+        m.set_params(p0)
+        t, _ = m.time_iteration(st)
+        t_total += t
+    s = m.sets()
+    P = m.P
+    val = steps / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: sliding-window DMSA iteration, N={m.N} points, {win['n_poses']} control poses (P={P}), {P + 10} cost evaluations/step",
+                   "M": int(s["M"]), "G": int(s["G"])},
+        "point_jacobians_per_s": val * int(s["M"]),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{steps} full iterations; oracle/dmsa_oracle.cpp -O2 -fopenmp (the reference needs Eigen/PCL/Boost: unbuildable here)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def pinned_copy(arr):
+    import torch
+
+    t = torch.empty(arr.nbytes, dtype=torch.uint8, pin_memory=True)
+    v = t.numpy().view(arr.dtype).reshape(arr.shape)
+    v[...] = arr
+    return t, v
+
+
+def run_sliding(args):
+    import torch
+    import torch.distributed as dist
+
+    from dmsa_lidar_slam_b200 import ContinuousTrajectory, DmsaOptimSettings, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    win = synth.make_config(args.config, seed=None if world == 1 else 100 + rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    s = DmsaOptimSettings(**SETTINGS)
+    traj = ContinuousTrajectory.from_window(win, device=local, stream=stream)
+    traj.centralize()
+    P = traj.numParams
+    rel_o, rel_t = win["rel_orient"].copy(), win["rel_transl"].copy()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # the window stays centralised between steps; resetting the poses re-applies the centralised pose 0
+    pose0 = traj.getPoses()
+
+    def reset_poses():
+        traj.setRelativePoses(pose0["rel_orient"], pose0["rel_transl"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident-data throughput (value) ----------------
+    last = None
+    for _ in range(max(args.warmup, 3)):
+        reset_poses()
+        last = traj.iteration(s)
+    G, M = traj.buildSets(s)  # sizes of the first iteration's sets (reported with every figure)
+    reset_poses()
+    traj.profileEnable(True)
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = traj.ctx.launch_count
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)  # L2 flush between timed steps (256 MiB write), outside the timed span
+        reset_poses()
+        ev[k][0].record()
+        last = traj.iteration(s)
+        ev[k][1].record()
+    barrier()
+    launches = traj.ctx.launch_count - l0
+    prof = traj.profileRead()
+    traj.profileEnable(False)
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end to end through the C-ABI with HOST buffers (e2e) ----------------
+    pinned = [pinned_copy(sc) for sc in win["scans"]]
+    pstat = pinned_copy(win["static"])
+    h2d = sum(sc.nbytes for sc in win["scans"]) + win["static"].nbytes + 2 * rel_o.nbytes
+    d2h = 4 * rel_o.nbytes + 64
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        traj.initTraj(win["t_min"], win["t_max"], win["n_poses"], False, win["dt_res"])
+        traj.registerPcBuffer([p[1] for p in pinned], win["grid_sizes"])
+        traj.addStaticPoints(pstat[1])
+        traj.setRelativePoses(rel_o, rel_t)
+        traj.centralize()
+        d = traj.iteration(s)
+        poses = traj.getPoses()  # result read-back
+        return d, poses
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        ev2[k][0].record()
+        e2e_step()
+        ev2[k][1].record()
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
+    t = torch.tensor([max(ms_e2e, 1e3 * wall_e2e)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps / (float(t.item()) * 1e-3)
+    clk = clocks.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---------------- roofline of the dominant kernel ----------------
+    peak, peak_src = load_peaks()
+    dom = max((k for k in prof if k.startswith("k_cost")), key=lambda k: prof[k][0])
+    dom_ms, dom_n = prof[dom]
+    V = P + 1 if dom.endswith("_fd") else 9
+    alg_bytes = 24.0 * M + 48.0 * G  # 24 B per membership + 48 B per set, once for all V vectors of the pass
+    avg_ms = dom_ms / max(dom_n, 1)
+    ach = alg_bytes / (avg_ms * 1e-3) / 1e9
+    flop_alg = 50.0 * M * V  # SURVEY §8d F_alg per pass
+    breakdown = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items() if v[1]}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 point arithmetic / f64 pose chain, sums, J^T J (the reference's types)", "data": "synthetic",
+        "config": {"workload": f"{args.config}: sliding-window DMSA iteration (DmsaOptimizer.h:69-144), {len(win['scans'])} scans x {len(win['scans'][0])} pts + "
+                               f"{len(win['static'])} static, {win['n_poses']} control poses, P={P}, {P + 10} cost evaluations/step; "
+                               + ("1 window" if world == 1 else f"{world} independent windows (replicas, no collective)"),
+                   "N": int(traj.numPoints), "M": int(M), "G": int(G), "l2": "flushed between timed steps (256 MiB write, untimed)",
+                   "settings": SETTINGS},
+        "point_jacobians_per_s": value * M,
+        "membership_evals_per_s": value * M * (P + 10),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "what": "traj_init + register_scans + add_static_points (pinned host AoS PointStampId) + set poses + centralize + 1 iteration + pose read-back"},
+        "gpu_launches": int(launches),
+        "gpu_launches_note": "hand-written kernels only (CUB radix-sort/scan launches inside the set build are not counted)",
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "fp32": {"algorithmic_flop_per_launch": flop_alg, "achieved_tflops": flop_alg / (avg_ms * 1e-3) / 1e12,
+                              "note": "the forward-difference formulation is FP32-issue bound, not HBM bound (SURVEY §8d, DESIGN.md)"}},
+        "device_ms_per_step_breakdown": breakdown,
+        "clocks": clk,
+        "last_step": {"G": last["num_gaussians"], "error0": last["error0"], "best_step": last["best_step"], "stop": last["stop"]},
+    }
+    if world == 1:
+        threads = os.cpu_count() or 1
+        cb = oracle_cpu_baseline(win, threads)
+        line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_iteration"], "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "median of 2 full iterations of the same workload; oracle/dmsa_oracle.cpp -O2 -fopenmp, faithful arithmetic"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="sliding", choices=["sliding", "keyframe"])
+    ap.add_argument("--config", default="cfg2")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "keyframe":
+        from dmsa_lidar_slam_b200 import distributed
+
+        return distributed.bench_keyframe(args)
+    return run_sliding(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -222,7 +222,67 @@ struct dmsa_b200_ctx {
     // host mirrors
     std::vector<double> h_hg, h_p;
     double lastErr0 = 0;
+
+    // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
+    bool profiling = false;
+    int phase = 0;  // 0: forward-difference batch, 1: line-search batch
+    std::vector<cudaEvent_t> evPool;
+    struct Span { int id; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double profMs[32] = {0};
+    int64_t profCount[32] = {0};
 };
+
+enum {
+    PROF_POSE_FD = 0, PROF_POSE_LS, PROF_TRANSFORM, PROF_SETS_KEYS, PROF_SETS_SORT, PROF_SETS_STATS,
+    PROF_SUM_FD, PROF_SUM_LS, PROF_MEAN_FD, PROF_MEAN_LS, PROF_QUAD_FD, PROF_QUAD_LS, PROF_FIN_FD, PROF_FIN_LS, PROF_JTJ, PROF_COLSUM,
+    PROF_NUM
+};
+static const char* kProfNames[PROF_NUM] = {
+    "pose_tables_fd", "pose_tables_ls", "transform_points", "sets_keys_root", "sets_sort_segment", "sets_gaussians_chunks",
+    "k_cost_sum_fd", "k_cost_sum_ls", "k_cost_mean_fd", "k_cost_mean_ls", "k_cost_quad_fd", "k_cost_quad_ls", "k_cost_fin_fd", "k_cost_fin_ls",
+    "k_jtj", "k_col_sumsq"};
+
+static cudaEvent_t profEvent(dmsa_b200_ctx* ctx) {
+    cudaEvent_t e;
+    if (!ctx->evPool.empty()) {
+        e = ctx->evPool.back();
+        ctx->evPool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+struct ProfScope {
+    dmsa_b200_ctx* ctx;
+    int id;
+    cudaEvent_t a = nullptr;
+    ProfScope(dmsa_b200_ctx* c, int i) : ctx(c), id(i) {
+        if (ctx->profiling) {
+            a = profEvent(ctx);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~ProfScope() {
+        if (a) {
+            cudaEvent_t b = profEvent(ctx);
+            cudaEventRecord(b, ctx->stream);
+            ctx->spans.push_back({id, a, b});
+        }
+    }
+};
+static void profCollect(dmsa_b200_ctx* ctx) {  // call after a stream synchronize
+    for (auto& sp : ctx->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            ctx->profMs[sp.id] += ms;
+            ctx->profCount[sp.id]++;
+        }
+        ctx->evPool.push_back(sp.a);
+        ctx->evPool.push_back(sp.b);
+    }
+    ctx->spans.clear();
+}
 
 #define CK(call)                                                                                   \
     do {                                                                                           \
@@ -358,6 +418,7 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
     KfFactors kf;
     memset(&kf, 0, sizeof(kf));
     const size_t smem = (size_t)n * 24 * sizeof(double);
+    ProfScope prof_(ctx, ctx->phase ? PROF_POSE_LS : PROF_POSE_FD);
     if (ctx->model == MODEL_TRAJ) {
         if (E > 0) {
             imu.enabled = 1;
@@ -409,6 +470,7 @@ int transformBase(dmsa_b200_ctx* ctx) {
     const bool kfm = ctx->model == MODEL_KF;
     if (kfm) CK(ctx->d_normal_w.ensure(N));
     // static points (tid = -1) pass through: their world copy is maintained by centralize/decentralize
+    ProfScope prof_(ctx, PROF_TRANSFORM);
     LAUNCH(k_transform_points, cdiv(ctx->n_scan, 256), 256, 0, ctx->d_local.p, ctx->d_tid.p, (int)ctx->n_scan, reinterpret_cast<const float4*>(ctx->d_Mtab.p),
            ctx->curVld, 0, ctx->d_world.p, kfm ? ctx->d_normal_l.p : nullptr, kfm ? ctx->d_normal_w.p : nullptr);
     CK(cudaGetLastError());
@@ -476,6 +538,8 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     for (int l = 0; l < 2; ++l) ctx->levelOn[l] = factors[l] > std::numeric_limits<float>::min();  // DmsaOptimizer.h:81,85
     CK(cudaMemsetAsync(ctx->d_linfo.p, 0, 2 * sizeof(LevelInfo), ctx->stream));
     // phase 1: anchors, keys, octree roots
+    {
+    ProfScope prof_(ctx, PROF_SETS_KEYS);
     for (int l = 0; l < 2; ++l) {
         if (!ctx->levelOn[l]) continue;
         const float res = factors[l] * ctx->minGridSize;  // float product, DmsaOptimizer.h:82,86
@@ -485,6 +549,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
         LAUNCH(k_keys, nb, DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, ctx->d_linfo.p + l, keys, bb, bb + 3 * nb, bb + 6 * nb, bb + 9 * nb);
         LAUNCH(k_root, 1, 256, 0, ctx->d_world.p, N, ctx->d_linfo.p + l, bb, bb + 3 * nb, bb + 6 * nb, bb + 9 * nb);
     }
+    }
     CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (int l = 0; l < 2; ++l)
@@ -492,6 +557,8 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     // phase 2: sort, segment, accept, gather
     size_t cubBytes = ctx->d_cub.cap;
     int prev = -1;
+    {
+    ProfScope prof_(ctx, PROF_SETS_SORT);
     for (int l = 0; l < 2; ++l) {
         if (!ctx->levelOn[l]) continue;
         LevelInfo* li = ctx->d_linfo.p + l;
@@ -513,6 +580,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
                ctx->d_wrec.p + (size_t)N * l);
         prev = l;
     }
+    }
     CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
@@ -524,6 +592,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     ctx->M = 0;
     if (G == 0) return 0;
     // phase 3: per-set statistics, weights, chunk list
+    ProfScope prof_(ctx, PROF_SETS_STATS);
     LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G);
     LAUNCH(k_weights, 1, 1024, 0, cs, G);
     LAUNCH(k_chunk_counts, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->rank, ctx->world, ctx->d_nchunk.p);
@@ -561,10 +630,23 @@ int runCost(dmsa_b200_ctx* ctx) {
     a.Q = ctx->d_Q.p;
     a.E = ctx->d_E.p;
     const unsigned grid = (unsigned)ctx->chunkBound;
-    LAUNCH(k_cost_sum, grid, Vld, 0, a);
-    LAUNCH(k_cost_mean, G, Vld, 0, a, G);
-    LAUNCH(k_cost_quad, grid, Vld, 0, a);
-    LAUNCH(k_cost_fin, G, Vld, 0, a, G);
+    const int ph = ctx->phase ? 1 : 0;
+    {
+        ProfScope p_(ctx, PROF_SUM_FD + ph);
+        LAUNCH(k_cost_sum, grid, Vld, 0, a);
+    }
+    {
+        ProfScope p_(ctx, PROF_MEAN_FD + ph);
+        LAUNCH(k_cost_mean, G, Vld, 0, a, G);
+    }
+    {
+        ProfScope p_(ctx, PROF_QUAD_FD + ph);
+        LAUNCH(k_cost_quad, grid, Vld, 0, a);
+    }
+    {
+        ProfScope p_(ctx, PROF_FIN_FD + ph);
+        LAUNCH(k_cost_fin, G, Vld, 0, a, G);
+    }
     if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaGetLastError());
     return 0;
@@ -590,6 +672,7 @@ int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
     CK(ctx->d_jpart.ensure((size_t)nsplit * n1 * n1));
     CK(cudaMemsetAsync(ctx->d_jpart.p, 0, (size_t)nsplit * n1 * n1 * sizeof(double), ctx->stream));
     dim3 grid(nt * (nt + 1) / 2, nsplit);
+    ProfScope prof_(ctx, PROF_JTJ);
     LAUNCH(k_jtj, grid, 256, 0, ctx->d_E.p, R, Vld, P, inv_h, rps, ctx->d_jpart.p);
     LAUNCH(k_jtj_reduce, cdiv((size_t)n1 * n1, 256), 256, 0, ctx->d_jpart.p, nsplit, P, hg_dev);
     CK(cudaGetLastError());
@@ -600,8 +683,12 @@ int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) 
     const int P = 6 * (ctx->poses.n - 1);
     CK(cudaMemcpyAsync(ctx->d_step.p, step_host, P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     LAUNCH(k_make_ls_batch, cdiv((size_t)9 * P, 256), 256, 0, ctx->d_p.p, ctx->d_step.p, P, ctx->d_batch.p);
-    CKRC(runPoseTables(ctx, 9));
-    CKRC(runCost(ctx));
+    ctx->phase = 1;
+    int rc = runPoseTables(ctx, 9);
+    if (rc == 0) rc = runCost(ctx);
+    ctx->phase = 0;
+    if (rc) return rc;
+    ProfScope prof_(ctx, PROF_COLSUM);
     LAUNCH(k_col_sumsq, 9, 256, 0, ctx->d_E.p, ctx->G + numExtra(ctx), ctx->curVld, ls_dev);
     CK(cudaGetLastError());
     return 0;
@@ -703,6 +790,7 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     double ls[9];
     CK(cudaMemcpyAsync(ls, ctx->d_ls.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->profiling) profCollect(ctx);
     double minError = error0;
     int best = 0;
     for (int k = 1; k < 10; ++k)
@@ -1309,6 +1397,26 @@ int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, d
     rep.iterations = it;
     rep.stop_reason = stop;
     if (report) *report = rep;
+    return 0;
+}
+
+// ---- per-kernel timing (CUDA events on the launching stream) ------------------------------------------------
+int dmsa_b200_profile_enable(dmsa_b200_ctx* ctx, int32_t on) {
+    ctx->profiling = on != 0;
+    for (int i = 0; i < PROF_NUM; ++i) {
+        ctx->profMs[i] = 0;
+        ctx->profCount[i] = 0;
+    }
+    return 0;
+}
+int32_t dmsa_b200_profile_num(void) { return PROF_NUM; }
+const char* dmsa_b200_profile_name(int32_t id) { return (id >= 0 && id < PROF_NUM) ? kProfNames[id] : ""; }
+int dmsa_b200_profile_read(dmsa_b200_ctx* ctx, int32_t id, double* total_ms, int64_t* count) {
+    if (id < 0 || id >= PROF_NUM) ARGFAIL("profile_read: bad id");
+    CK(cudaStreamSynchronize(ctx->stream));
+    profCollect(ctx);
+    if (total_ms) *total_ms = ctx->profMs[id];
+    if (count) *count = ctx->profCount[id];
     return 0;
 }
 

@@ -174,6 +174,12 @@ int dmsa_b200_iteration(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, 
 /* the whole optimizeSet: centralize, loop, decentralize, final updateGlobalPoints   DmsaOptimizer.h:54-150 */
 int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, dmsa_b200_report* report);
 
+/* ---- per-kernel device timing (CUDA events on the context's stream; used by bench.py for the roofline) ---- */
+int dmsa_b200_profile_enable(dmsa_b200_ctx* ctx, int32_t on); /* also resets the accumulators */
+int32_t dmsa_b200_profile_num(void);
+const char* dmsa_b200_profile_name(int32_t id);
+int dmsa_b200_profile_read(dmsa_b200_ctx* ctx, int32_t id, double* total_ms, int64_t* count);
+
 /* ---- multi-GPU row sharding: this rank owns the Gaussians g with g % world == rank ------------- */
 int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world);
 /* device-resident variants for NCCL: pointers are DEVICE memory owned by the caller (e.g. torch tensors).

@@ -1,0 +1,427 @@
+"""Parity of the CUDA path (through the C-ABI / reference-shaped host API) with the CPU oracle.  `-m gpu`.
+
+Contract (BASELINE.json north_star):
+  * voxel membership lists ("neighbour index sets"), voxel keys, leaf order, octree root: BIT-EXACT;
+  * world points, dense transforms, information matrices, weights: bit-exact (float, same operation order);
+  * e, J, H = J^T J, g = J^T e0: |X_gpu - X_oracle| <= 1e-4 |X_oracle| against the FAITHFUL oracle (tolerance of the
+    north star), and ~1e-9 against the oracle's exact-mean mode whose arithmetic the kernels reproduce operation for
+    operation (the only non-associative reduction of the hot loop, the per-cell float mean, is exactly rounded).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from dmsa_lidar_slam_b200 import ContinuousTrajectory, DmsaOptimizer, DmsaOptimSettings, MapManagement, synth
+from golden.make_golden import CASES
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_NORTH_STAR = 1e-4  # relative, J^T J and J^T r vs the CPU reference arithmetic
+TOL_SAME_ARITH = 1e-9  # relative, vs the oracle mode with the same (order-free) mean
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) / (nb if nb else 1.0))
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+CASE_ST = dict(CASES)
+CASE_ST["cfg2"] = dict(num_iter=3, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10, min_num_gaussians=30)
+
+
+def make_pair(name, mode=2):
+    st = CASE_ST[name]
+    win = synth.make_config(name)
+    traj = ContinuousTrajectory.from_window(win)
+    om = ob.OracleModel.from_window(win)
+    om.set_threads(os.cpu_count() or 8)
+    om.set_mode(mode)
+    return win, traj, om, DmsaOptimSettings(**st), ob.settings(**st)
+
+
+@pytest.fixture(scope="module", params=["tiny", "cfg1", "cfg2"])
+def staged(request):
+    win, traj, om, s, so = make_pair(request.param)
+    traj.centralize()
+    om.centralize()
+    traj.updateGlobalPoints()
+    om.update_global_points()
+    G, M = traj.buildSets(s)
+    Go = om.build_sets(so)
+    return dict(name=request.param, win=win, traj=traj, om=om, s=s, so=so, G=G, M=M, Go=Go)
+
+
+def test_registration_and_timing(staged):
+    traj, om, win = staged["traj"], staged["om"], staged["win"]
+    n_scan = sum(len(x) for x in win["scans"])
+    assert (traj.tformIdPerPoint(n_scan) == om.tid).all()  # registerPcBuffer, ContinuousTrajectory.h:251-254
+    tim = traj.timing()
+    assert tim["n_total"] == om.timing["n_total"]
+    assert (tim["stamps"] == om.timing["stamps"]).all() and (tim["traj_time"] == om.timing["traj_time"]).all()
+    assert (tim["param_indices"] == om.timing["param_indices"]).all()
+
+
+def test_world_points_and_dense_transforms_bit_exact(staged):
+    traj, om = staged["traj"], staged["om"]
+    Mg, (Mo, _, _) = traj.denseTforms(), om.dense_tforms()
+    # double-precision libm differences may flip the float rounding of an isolated entry: allow <= 1e-5 of them
+    assert (bits(Mg) != bits(Mo)).mean() <= 1e-5
+    assert np.abs(Mg - Mo).max() <= 4e-6
+    wg, wo = traj.globalPoints(), om.world_points()
+    assert (bits(wg) != bits(wo)).mean() <= 1e-4
+    assert np.abs(wg - wo).max() <= 8e-6
+
+
+def test_voxel_membership_bit_exact(staged):
+    traj, om = staged["traj"], staged["om"]
+    assert staged["G"] == staged["Go"]
+    sg, so = traj.getSets(), om.sets()
+    assert so["lattice_mismatch"] == 0
+    assert sg["M"] == so["M"]
+    assert (sg["offs"] == so["offs"]).all()
+    assert (sg["members"] == so["members"]).all()  # neighbour index sets, ascending point index, PCL leaf order
+    assert (sg["key"] == so["key"]).all() and (sg["level"] == so["level"]).all()
+    assert (bits(sg["info"]) != bits(so["info"])).mean() <= 1e-4
+    assert rel(sg["info"], so["info"]) < 1e-6
+    assert rel(sg["w"], so["w"]) < 1e-7
+
+
+def test_octree_root_matches_pcl_replay(staged):
+    import ctypes as C
+
+    traj, om = staged["traj"], staged["om"]
+    W = np.ascontiguousarray(om.world_points())
+    for lvl, fac in ((0, 2.0), (1, 5.0)):
+        keys, lo, depth = traj.voxelKeys(lvl)
+        res = np.float32(fac) * np.float32(0.3)
+        ck = np.zeros((len(W), 3), dtype=np.int32)
+        fin = np.zeros(len(W), dtype=np.uint8)
+        lo_o = np.zeros(3, dtype=np.int64)
+        d_o, mm = C.c_int32(), C.c_int64()
+        ob.lib().orc_lattice(ob._p(W), len(W), res, ob._p(ck), ob._p(fin), ob._p(lo_o), C.byref(d_o), C.byref(mm))
+        assert (keys == ck).all()
+        assert (lo == lo_o).all() and depth == d_o.value
+
+
+def test_cost_batch(staged):
+    traj, om = staged["traj"], staged["om"]
+    p = traj.getPoseParameters()
+    rng = np.random.default_rng(7)
+    batch = np.stack([p, p + rng.normal(0, 1e-3, p.shape), p + rng.normal(0, 1e-2, p.shape)])
+    eg = traj.evalCost(batch)
+    for v in range(3):
+        om.set_mode(2)
+        assert rel(eg[v], om.cost(batch[v])) < TOL_SAME_ARITH
+        om.set_mode(0)
+        assert rel(eg[v], om.cost(batch[v])) < 1e-5
+    om.set_mode(2)
+    # a batch evaluates exactly what single evaluations do
+    assert (traj.evalCost(batch[1:2])[0] == eg[1]).all()
+
+
+def test_jacobian_H_g(staged):
+    traj, om = staged["traj"], staged["om"]
+    cj = traj.costJacobian(with_rows=True)
+    out = {}
+    for mode in (2, 0):
+        om.set_mode(mode)
+        e0, J = om.jacobian()
+        out[mode] = dict(e0=e0, J=J, H=J.T @ J, g=J.T @ e0)
+    om.set_mode(2)
+    for k in ("e0", "J", "H", "g"):
+        assert rel(cj[k], out[2][k]) < TOL_SAME_ARITH, k
+    # north-star tolerance against the faithful reference arithmetic
+    assert rel(cj["H"], out[0]["H"]) < TOL_NORTH_STAR
+    assert rel(cj["g"], out[0]["g"]) < TOL_NORTH_STAR
+    assert np.abs(cj["H"] - out[0]["H"]).max() < TOL_NORTH_STAR * np.abs(out[0]["H"]).max()
+    # internal consistency
+    assert rel(cj["H"], cj["J"].T @ cj["J"]) < 1e-12 and rel(cj["g"], cj["J"].T @ cj["e0"]) < 1e-12
+    assert abs(cj["err0"] - float(cj["e0"] @ cj["e0"])) < 1e-10 * cj["err0"]
+    assert np.allclose(cj["H"], cj["H"].T, rtol=0, atol=1e-9 * np.abs(cj["H"]).max())
+
+
+def test_row_sharding_sums_to_the_whole(staged):
+    """H, g, err0 are sums over residual rows -> two shards add up to the unsharded result."""
+    traj = staged["traj"]
+    full = traj.costJacobian()
+    parts = []
+    for r in range(2):
+        traj.setShard(r, 2)
+        traj.buildSets(staged["s"])
+        parts.append(traj.costJacobian())
+    traj.setShard(0, 1)
+    traj.buildSets(staged["s"])
+    assert rel(parts[0]["H"] + parts[1]["H"], full["H"]) < 1e-12
+    assert rel(parts[0]["g"] + parts[1]["g"], full["g"]) < 1e-12
+    assert abs(parts[0]["err0"] + parts[1]["err0"] - full["err0"]) < 1e-12 * full["err0"]
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])
+def test_iterations_follow_the_oracle(name):
+    win, traj, om, s, so = make_pair(name)
+    traj.centralize()
+    om.centralize()
+    for it in range(2):
+        d = traj.iteration(s)
+        r = om.iteration(so)
+        tr = om.last_trace()
+        assert d["stop_reason"] == r
+        assert d["num_gaussians"] == len(tr["e0"])
+        assert abs(d["error0"] - float(tr["e0"] @ tr["e0"])) < 1e-9 * d["error0"]
+        assert d["best_step"] == tr["best_k"]
+        assert rel(d["ls_cost"], tr["ls_cost"]) < 1e-8
+        assert rel(d["step"], tr["step"]) < 1e-5  # H^-1 amplifies the 1e-16 noise of H by cond(H)
+        assert rel(traj.getPoseParameters(), om.get_params()) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+def test_optimizeSet_against_golden_and_oracle(name):
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    win, traj, om, s, so = make_pair(name)
+    rep = DmsaOptimizer().optimizeSet(traj, s)
+    assert rep["iterations"] == int(g["opt_iters"]) and rep["stop_reason"] == int(g["opt_reason"])
+    p = traj.getPoses()
+    np.testing.assert_allclose(p["rel_transl"], g["opt_rel_transl"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(p["rel_orient"], g["opt_rel_orient"], rtol=1e-5, atol=1e-7)
+    it, reason = om.optimize(so)
+    po = om.get_poses()
+    assert rel(p["glob_transl"], po["glob_transl"]) < 1e-6
+    assert np.abs(traj.globalPoints() - om.world_points()).max() < 1e-4  # final updateGlobalPoints, DmsaOptimizer.h:149
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1"])
+def test_golden_fixtures(name):
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    st = CASES[name]
+    win = synth.make_config(name)
+    traj = ContinuousTrajectory.from_window(win)
+    s = DmsaOptimSettings(**st)
+    traj.centralize()
+    traj.updateGlobalPoints()
+    G, M = traj.buildSets(s)
+    assert (G, M) == (int(g["G"]), int(g["M"]))
+    sg = traj.getSets()
+    assert (sg["members"] == g["members"]).all() and (sg["offs"] == g["offs"]).all() and (sg["key"] == g["key"]).all()
+    assert rel(sg["info"], g["info"]) < 1e-6 and rel(sg["w"], g["w"]) < 1e-7
+    cj = traj.costJacobian(with_rows=True)
+    lam = np.eye(len(cj["g"])) * float(np.float32(st.get("lambda_diag", 0.00001)))
+    assert rel(cj["e0"], g["exactmean_e0"]) < TOL_SAME_ARITH
+    assert rel(cj["H"] + lam, g["exactmean_H"]) < TOL_SAME_ARITH and rel(cj["g"], g["exactmean_g"]) < TOL_SAME_ARITH
+    assert rel(cj["H"] + lam, g["faithful_H"]) < TOL_NORTH_STAR and rel(cj["g"], g["faithful_g"]) < TOL_NORTH_STAR
+
+
+def test_stop_conditions():
+    win = synth.make_config("tiny")
+    # too few Gaussians -> abort before any evaluation (DmsaOptimizer.h:89-93)
+    traj = ContinuousTrajectory.from_window(win)
+    rep = DmsaOptimizer().optimizeSet(traj, DmsaOptimSettings(num_iter=3, min_num_gaussians=100000, min_num_points_per_set=6))
+    assert rep["stop"] == "few_gaussians" and rep["iterations"] == 1
+    # epsilon stop (:139-143): a huge epsilon stops after the first iteration, parameters updated
+    traj = ContinuousTrajectory.from_window(win)
+    rep = DmsaOptimizer().optimizeSet(traj, DmsaOptimSettings(num_iter=5, epsilon=1e9, step_length_optim=0.2, max_step=0.3, min_num_gaussians=10))
+    assert rep["stop"] == "epsilon" and rep["iterations"] == 1
+    # no improvement (:130-134): an absurd step length overshoots every trial; the set stays at p + 0.9 step
+    traj = ContinuousTrajectory.from_window(win)
+    om = ob.OracleModel.from_window(win)
+    om.set_mode(2)
+    bad = dict(num_iter=4, step_length_optim=500.0, max_step=50.0, min_num_gaussians=10, min_num_points_per_set=6)
+    rep = DmsaOptimizer().optimizeSet(traj, DmsaOptimSettings(**bad))
+    it, reason = om.optimize(ob.settings(**bad))
+    assert rep["stop_reason"] == reason and rep["iterations"] == it
+    assert rel(traj.getPoses()["rel_transl"], om.get_poses()["rel_transl"]) < 1e-6
+
+
+def test_empty_ragged_and_degenerate_inputs():
+    win = synth.make_config("tiny")
+    # no static points, ragged scan sizes, one empty scan
+    w2 = dict(win)
+    w2["static"] = win["static"][:0]
+    w2["scans"] = [win["scans"][0][:1500], win["scans"][1][:0], win["scans"][1][100:]]
+    w2["grid_sizes"] = [0.3, 0.4, 0.3]
+    traj = ContinuousTrajectory.from_window(w2)
+    om = ob.OracleModel.from_window(w2)
+    om.set_mode(2)
+    st = dict(num_iter=1, min_num_points_per_set=6, min_num_gaussians=5, step_length_optim=0.2, max_step=0.3)
+    traj.centralize(); om.centralize()
+    traj.updateGlobalPoints(); om.update_global_points()
+    G, M = traj.buildSets(DmsaOptimSettings(**st))
+    assert G == om.build_sets(ob.settings(**st)) and G > 5
+    assert (traj.getSets()["members"] == om.sets()["members"]).all()
+    # non-finite points are skipped by the octree (PCL isFinite) and belong to no set
+    w3 = dict(win)
+    sc = [s.copy() for s in win["scans"]]
+    sc[0]["x"][10] = np.nan
+    sc[1]["z"][5] = np.inf
+    w3["scans"] = sc
+    traj = ContinuousTrajectory.from_window(w3)
+    om = ob.OracleModel.from_window(w3)
+    traj.centralize(); om.centralize()
+    traj.updateGlobalPoints(); om.update_global_points()
+    G, M = traj.buildSets(DmsaOptimSettings(**st))
+    assert G == om.build_sets(ob.settings(**st))
+    mem = traj.getSets()["members"]
+    assert (mem == om.sets()["members"]).all()
+    assert 10 not in mem and (len(sc[0]) + 5) not in mem
+    # a second resolution level can be switched off (factor <= FLT_MIN, DmsaOptimizer.h:81-86)
+    one = dict(st, grid_size_2_factor=0.0)
+    traj = ContinuousTrajectory.from_window(win)
+    om = ob.OracleModel.from_window(win)
+    traj.centralize(); om.centralize()
+    traj.updateGlobalPoints(); om.update_global_points()
+    G, _ = traj.buildSets(DmsaOptimSettings(**one))
+    assert G == om.build_sets(ob.settings(**one)) and (traj.getSets()["level"] == 0).all()
+
+
+def test_deterministic_across_runs():
+    win = synth.make_config("cfg1")
+    s = DmsaOptimSettings(**CASES["cfg1"])
+    outs = []
+    for _ in range(2):
+        traj = ContinuousTrajectory.from_window(win)
+        traj.centralize()
+        traj.updateGlobalPoints()
+        traj.buildSets(s)
+        cj = traj.costJacobian()
+        outs.append((cj["H"].copy(), cj["g"].copy()))
+    assert (outs[0][0] == outs[1][0]).all() and (outs[0][1] == outs[1][1]).all()  # no atomics on the numeric path
+
+
+def test_full_size_properties_cfg3():
+    """BASELINE config 3 (10 x 131k + 200k static, 20 poses): too big for an oracle run inside the suite ->
+    size-independent properties."""
+    win = synth.make_config("cfg3")
+    s = DmsaOptimSettings(num_iter=1, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10)
+    traj = ContinuousTrajectory.from_window(win)
+    traj.centralize()
+    traj.updateGlobalPoints()
+    G, M = traj.buildSets(s)
+    N = traj.numPoints
+    assert N == 10 * 131072 + 200000 and G > 1000 and N < M <= 2 * N
+    sg = traj.getSets()
+    n = np.diff(sg["offs"])
+    assert n.min() >= 10 and n.sum() == M
+    for lvl in (0, 1):  # every point is in at most one set per level; members ascending within a set
+        sel = np.nonzero(sg["level"] == lvl)[0]
+        mem = np.concatenate([sg["members"][sg["offs"][g]:sg["offs"][g + 1]] for g in sel])
+        assert len(np.unique(mem)) == len(mem)
+    d = np.diff(sg["members"])
+    starts = sg["offs"][1:-1]
+    interior = np.ones(len(d), dtype=bool)
+    interior[starts - 1] = False
+    assert (d[interior] > 0).all()
+    np.testing.assert_allclose(sg["w"], (1.0 / n) / np.mean(1.0 / n), rtol=1e-5)
+    cj = traj.costJacobian(with_rows=True)
+    assert rel(cj["H"], cj["J"].T @ cj["J"]) < 1e-12
+    assert np.linalg.eigvalsh(cj["H"]).min() > -1e-8 * np.abs(cj["H"]).max()
+    # the batched cost equals single evaluations; line-search costs equal evalCost at the trial points
+    p = traj.getPoseParameters()
+    d = traj.iteration(s)
+    traj2 = ContinuousTrajectory.from_window(win)
+    traj2.centralize()
+    traj2.updateGlobalPoints()
+    traj2.buildSets(s)
+    trials = np.stack([p + 0.1 * k * d["step"] for k in range(1, 10)])
+    e = traj2.evalCost(trials)
+    np.testing.assert_allclose((e ** 2).sum(axis=1), d["ls_cost"], rtol=1e-12)
+
+
+def test_keyframe_model_matches_oracle():
+    sm = synth.make_keyframe_submap(n_keyframes=5, n_points=4000, seed=2)
+    st = dict(num_iter=2, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=6, min_num_gaussians=10, gauss_split=0, epsilon=1e-4)
+    kf = MapManagement.from_submap(sm)
+    om = ob.OracleModel.from_submap(sm)
+    om.set_mode(2)
+    s, so = DmsaOptimSettings(**st), ob.settings(**st)
+    kf.updateGlobalPoints()
+    om.update_global_points()
+    wg, ng = kf.globalPoints(normals=True)
+    assert np.abs(wg - om.world_points()).max() <= 8e-6
+    assert np.abs(ng - om.world_normals()).max() <= 1e-6
+    G, M = kf.buildSets(s)
+    assert G == om.build_sets(so)
+    assert (kf.getSets()["members"] == om.sets()["members"]).all()
+    cj = kf.costJacobian(with_rows=True)
+    e0, J = om.jacobian()
+    assert rel(cj["e0"], e0) < TOL_SAME_ARITH and rel(cj["J"], J) < 1e-7
+    assert rel(cj["H"], J.T @ J) < 1e-7
+    for it in range(2):
+        d = kf.iteration(s)
+        r = om.iteration(so)
+        assert d["stop_reason"] == r and d["best_step"] == om.last_trace()["best_k"]
+    assert rel(kf.getPoseParameters(), om.get_params()) < 1e-6
+
+
+def test_keyframe_additional_factors():
+    sm = synth.make_keyframe_submap(n_keyframes=4, n_points=3000, seed=5)
+    n = sm["n_keyframes"]
+    rng = np.random.default_rng(3)
+    st = dict(num_iter=1, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=6, min_num_gaussians=10)
+    kf = MapManagement.from_submap(sm)
+    om = ob.OracleModel.from_submap(sm)
+    om.set_mode(2)
+    from scipy.spatial.transform import Rotation as Rot
+
+    grav = np.tile([0.0, 0.0, -9.805], (n, 1)) + rng.normal(0, 0.05, (n, 3))
+    plaus = np.array([1, 1, 0, 1], dtype=np.int32)
+    odomT = sm["rel_transl"].T + rng.normal(0, 0.01, (n, 3))
+    odomR = np.stack([Rot.from_rotvec(sm["rel_orient"][:, k] + rng.normal(0, 0.002, 3)).as_matrix().ravel() for k in range(n)])
+    kf.setGravityTerms(grav, plaus, 1.0)
+    kf.setOdometryTerms(odomT, odomR, 1000.0)
+    g_, p_, t_, r_ = ob.c64(grav), np.ascontiguousarray(plaus), ob.c64(odomT), ob.c64(odomR)
+    om.L.orc_kf_set_gravity(om.h, ob._p(g_), ob._p(p_), 1.0)
+    om.L.orc_kf_set_odometry(om.h, ob._p(t_), ob._p(r_), 1000.0)
+    s, so = DmsaOptimSettings(**st), ob.settings(**st)
+    kf.updateGlobalPoints()
+    om.update_global_points()
+    G, _ = kf.buildSets(s)
+    assert G == om.build_sets(so)
+    E = 2 * n - 1
+    assert kf.numExtra() == E == om.E
+    cj = kf.costJacobian(with_rows=True)
+    e0, J = om.jacobian()
+    assert len(cj["e0"]) == G + E
+    assert rel(cj["e0"][G:], e0[G:]) < 1e-12  # gravity rows then odometry rows (MapManagement.h:185-187)
+    assert rel(cj["J"][G:], J[G:]) < 1e-6
+    assert rel(cj["H"], J.T @ J) < 1e-7
+
+
+def test_imu_factor_rows():
+    win = synth.make_config("tiny")
+    n = win["n_poses"]
+    rng = np.random.default_rng(11)
+    from scipy.spatial.transform import Rotation as Rot
+
+    traj = ContinuousTrajectory.from_window(win, use_imu=True)
+    om = ob.OracleModel.from_window(win)
+    om.set_mode(2)
+    preR = np.stack([Rot.from_rotvec(win["rel_orient"][:, k] + rng.normal(0, 0.002, 3)).as_matrix().ravel() for k in range(n)])
+    preP = rng.normal(0, 0.1, (n, 3))
+    preV = rng.normal(0, 0.1, (n, 3))
+    cov = np.zeros((n, 81))
+    for k in range(n):
+        A = rng.normal(size=(9, 9))
+        cov[k] = (A @ A.T + 9 * np.eye(9)).ravel()
+    bal = float(np.float32(0.001))  # `double balancingImu = 0.001f`, ContinuousTrajectory.h:52
+    traj.setImuFactors(preR, preP, preV, cov, bal)
+    a = [ob.c64(x) for x in (preR, preP, preV, cov)]
+    grav = ob.c64([0.0, 0.0, -9.805])
+    pi = np.ascontiguousarray(om.timing["param_indices"], dtype=np.int32)
+    om.L.orc_traj_set_imu(om.h, ob._p(pi), ob._p(a[0]), ob._p(a[1]), ob._p(a[2]), ob._p(a[3]), bal, ob._p(grav))
+    st = dict(num_iter=1, step_length_optim=0.07, max_step=0.05, min_num_points_per_set=6, min_num_gaussians=10)
+    s, so = DmsaOptimSettings(**st), ob.settings(**st)
+    traj.centralize(); om.centralize()
+    traj.updateGlobalPoints(); om.update_global_points()
+    G, _ = traj.buildSets(s)
+    assert G == om.build_sets(so)
+    assert traj.numExtra() == n - 1 == om.E
+    cj = traj.costJacobian(with_rows=True)
+    e0, J = om.jacobian()
+    assert rel(cj["e0"][G:], e0[G:]) < 1e-10  # ContinuousTrajectory.h:603-663
+    assert rel(cj["J"][G:], J[G:]) < 1e-5
+    assert rel(cj["H"], J.T @ J) < 1e-6

@@ -1,0 +1,103 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol the header declares, the
+settings/report/point structs have the reference's layout, the synthetic generator is deterministic."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+from dmsa_lidar_slam_b200 import api, build, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dmsa_b200.h")
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    build.build_library()
+    L = api.load_library()
+    src = open(HEADER).read()
+    declared = sorted(set(re.findall(r"\b(dmsa_b200_[a-z0-9_]+)\s*\(", src)))
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/dmsa_b200.h but not exported"
+    assert sorted(api.EXPORTED_SYMBOLS) == declared
+    assert L.dmsa_b200_version() >= 100
+
+
+def test_struct_layouts_match_the_header():
+    prog = r"""
+#include <stdio.h>
+#include <stddef.h>
+#include "dmsa_b200.h"
+int main(void){
+ printf("%zu %zu %zu %zu ", sizeof(dmsa_b200_settings), sizeof(dmsa_b200_point_stamp_id), sizeof(dmsa_b200_point_normal), sizeof(dmsa_b200_report));
+ printf("%zu %zu %zu %zu ", offsetof(dmsa_b200_settings, epsilon), offsetof(dmsa_b200_settings, max_step), offsetof(dmsa_b200_settings, lambda_diag), offsetof(dmsa_b200_settings, use_centralization));
+ printf("%zu %zu %zu\n", offsetof(dmsa_b200_point_stamp_id, stamp), offsetof(dmsa_b200_point_stamp_id, id), offsetof(dmsa_b200_report, error0));
+ return 0; }
+"""
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(prog)
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).decode().split()
+    v = list(map(int, out))
+    S, R = api.DmsaOptimSettings, api.Report
+    assert v[0] == C.sizeof(S) and v[1] == synth.POINT_STAMP_ID.itemsize == 32 and v[2] == synth.POINT_NORMAL.itemsize == 48 and v[3] == C.sizeof(R)
+    assert v[4:8] == [S.epsilon.offset, S.max_step.offset, S.lambda_diag.offset, S.use_centralization.offset]
+    assert v[8] == synth.POINT_STAMP_ID.fields["stamp"][1] == 16 and v[9] == synth.POINT_STAMP_ID.fields["id"][1] == 24
+    assert v[10] == R.error0.offset
+
+
+def test_settings_defaults_are_the_references():
+    s = api.DmsaOptimSettings()  # DmsaOptimizer.h:27-38
+    assert (s.num_iter, s.epsilon, s.use_analytic_jacobi, s.step_length_optim, s.max_step) == (15, 1e-5, 0, 0.05, 0.01)
+    assert (s.gauss_split, s.grid_size_1_factor, s.grid_size_2_factor, s.min_num_points_per_set, s.min_num_gaussians) == (0, 2.0, 5.0, 6, 30)
+    assert abs(s.lambda_diag - 1e-5) < 1e-12 and s.use_centralization == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.DmsaError, match="no CPU fallback"):
+        api.ContinuousTrajectory()
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "dmsa_lidar_slam_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle_binding" not in txt and "libdmsa_oracle" not in txt and "/oracle/" not in txt, f
+
+
+def test_synth_is_deterministic_and_shaped():
+    a, b = synth.make_config("tiny"), synth.make_config("tiny")
+    assert all((x == y).all() for x, y in zip(a["scans"], b["scans"])) and (a["static"] == b["static"]).all()
+    assert (a["rel_orient"] == b["rel_orient"]).all()
+    w = synth.make_config("cfg1")
+    assert sum(len(s) for s in w["scans"]) == 20000 and len(w["static"]) == 5000 and w["n_poses"] == 4
+    pts = np.concatenate(w["scans"])
+    assert (pts["w"] == 1).all() and pts["id"].min() == 0 and pts["id"].max() == 19
+    r = np.sqrt(pts["x"] ** 2 + pts["y"] ** 2 + pts["z"] ** 2)
+    assert r.min() > 0.5 and r.max() < 51.0
+    assert (w["static"]["isStatic"] == 1).all() and (w["static"]["stamp"] == -1000.0).all()
+    kf = synth.make_keyframe_submap(3, 500, seed=1)
+    nn = np.stack([kf["clouds"][0]["nx"], kf["clouds"][0]["ny"], kf["clouds"][0]["nz"]], 1)
+    np.testing.assert_allclose(np.linalg.norm(nn, axis=1), 1.0, atol=1e-5)
+
+
+def test_window_timing_matches_reference_formulas():
+    import oracle_binding as ob
+
+    t = ob.window_timing(0.0, 0.9999, 20, 1e-3)
+    assert t["n_total"] == 1002 and t["traj_time"][0] == 0 and t["traj_time"][-1] == t["horizon"]
+    assert t["param_indices"][0] == 0 and t["param_indices"][-1] == 1001
+    ids = ob.tform_ids(np.array([0.0, 0.00049, 0.0005, 0.9999, 5.0]), 0.0, t["traj_time"])
+    assert list(ids) == [0, 1, 1, 1000, 1001]
