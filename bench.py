@@ -85,6 +85,27 @@ class ClockSampler:
         return out
 
 
+def best_thread_count(win):
+    """OpenMP team size that runs the oracle's cost evaluation fastest on this host (cgroup quotas make nproc a poor guess)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+
+    m = ob.OracleModel.from_window(win)
+    m.centralize()
+    m.update_global_points()
+    m.build_sets(ob.settings(**SETTINGS))
+    n = os.cpu_count() or 1
+    cands = sorted({max(1, n >> k) for k in range(0, 6)} | {min(n, 8)})
+    best, best_t = 1, float("inf")
+    for c in cands:
+        m.set_threads(c)
+        m.time_cost_evals(1)
+        t = m.time_cost_evals(2)
+        if t < best_t:
+            best, best_t = c, t
+    return best
+
+
 def oracle_cpu_baseline(win, threads, iters=2):
     """The CPU path (oracle port of the reference arithmetic, oracle/dmsa_oracle.cpp) timed on the host cores."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -113,7 +134,7 @@ def run_reference(args):
     from dmsa_lidar_slam_b200 import synth
 
     win = synth.make_config(args.config)
-    threads = os.cpu_count() or 1
+    threads = best_thread_count(win)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
 
@@ -294,7 +315,7 @@ def run_sliding(args):
         "last_step": {"G": last["num_gaussians"], "error0": last["error0"], "best_step": last["best_step"], "stop": last["stop"]},
     }
     if world == 1:
-        threads = os.cpu_count() or 1
+        threads = best_thread_count(win)
         cb = oracle_cpu_baseline(win, threads)
         line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_iteration"], "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "median of 2 full iterations of the same workload; oracle/dmsa_oracle.cpp -O2 -fopenmp, faithful arithmetic"}

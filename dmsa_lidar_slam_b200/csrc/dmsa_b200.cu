@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -235,13 +236,13 @@ struct dmsa_b200_ctx {
 
 enum {
     PROF_POSE_FD = 0, PROF_POSE_LS, PROF_TRANSFORM, PROF_SETS_KEYS, PROF_SETS_SORT, PROF_SETS_STATS,
-    PROF_SUM_FD, PROF_SUM_LS, PROF_MEAN_FD, PROF_MEAN_LS, PROF_QUAD_FD, PROF_QUAD_LS, PROF_FIN_FD, PROF_FIN_LS, PROF_JTJ, PROF_COLSUM,
+    PROF_SUM_FD, PROF_SUM_LS, PROF_MEAN_FD, PROF_MEAN_LS, PROF_QUAD_FD, PROF_QUAD_LS, PROF_FIN_FD, PROF_FIN_LS, PROF_JTJ, PROF_COLSUM, PROF_HOST_SOLVE, PROF_HOST_ITER,
     PROF_NUM
 };
 static const char* kProfNames[PROF_NUM] = {
     "pose_tables_fd", "pose_tables_ls", "transform_points", "sets_keys_root", "sets_sort_segment", "sets_gaussians_chunks",
     "k_cost_sum_fd", "k_cost_sum_ls", "k_cost_mean_fd", "k_cost_mean_ls", "k_cost_quad_fd", "k_cost_quad_ls", "k_cost_fin_fd", "k_cost_fin_ls",
-    "k_jtj", "k_col_sumsq"};
+    "k_jtj", "k_col_sumsq", "host_lm_solve_wall", "host_iteration_wall"};
 
 static cudaEvent_t profEvent(dmsa_b200_ctx* ctx) {
     cudaEvent_t e;
@@ -752,6 +753,17 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     const int P = 6 * (ctx->poses.n - 1);
     if (P <= 0) ARGFAIL("need at least two poses");
     *stop = DMSA_B200_STOP_MAX_ITER;
+    struct WallTimer {
+        dmsa_b200_ctx* c;
+        int id;
+        std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~WallTimer() {
+            if (c->profiling) {
+                c->profMs[id] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                c->profCount[id]++;
+            }
+        }
+    } wall_{ctx, PROF_HOST_ITER};
     // getPoseParameters + updateGlobalPoints at the base pose (the forward-difference batch's vector 0)   :72-75
     ctx->poses.relative2global();
     CKRC(uploadParams(ctx));
@@ -777,7 +789,12 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     const double error0 = ctx->h_hg[(size_t)P * P + P];
     ctx->lastErr0 = error0;
     std::vector<double> step;
-    if (solveStep(st, ctx->h_hg.data(), P, step)) {  // :113-122
+    int nanStep;
+    {
+        WallTimer ws{ctx, PROF_HOST_SOLVE};
+        nanStep = solveStep(st, ctx->h_hg.data(), P, step);
+    }
+    if (nanStep) {  // :113-122
         // the last cost evaluation of calcNumericJacobian was p + h e_{P-1}: its global poses stay behind (see staleGlobal)
         std::vector<double> plast = paramVec;
         plast[P - 1] += 1.0 * (double)sqrtf(FLT_EPSILON);

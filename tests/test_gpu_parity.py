@@ -121,6 +121,7 @@ def test_cost_batch(staged):
         om.set_mode(0)
         assert rel(eg[v], om.cost(batch[v])) < 1e-5
     om.set_mode(2)
+    om.set_params(p)  # the oracle keeps the last evaluated parameters (like the reference's set); restore
     # a batch evaluates exactly what single evaluations do
     assert (traj.evalCost(batch[1:2])[0] == eg[1]).all()
 
