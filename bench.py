@@ -218,6 +218,7 @@ def run_sliding(args):
         reset_poses()
         last = traj.iteration(s)
     G, M = traj.buildSets(s)  # sizes of the first iteration's sets (reported with every figure)
+    sets = traj.getSets()
     reset_poses()
     traj.profileEnable(True)
     clocks = ClockSampler(local)
@@ -286,10 +287,21 @@ def run_sliding(args):
     dom = max((k for k in prof if k.startswith("k_cost")), key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]
     V = P + 1 if dom.endswith("_fd") else 9
-    alg_bytes = 24.0 * M + 48.0 * G  # 24 B per membership + 48 B per set, once for all V vectors of the pass
+    T = traj.L.dmsa_b200_fuse_threshold()
+    n_per_set = np.diff(sets["offs"])
+    small = n_per_set <= T
+    if "fused" in dom:
+        # both passes of the sets it owns: SURVEY §8d Jacobian-pass figure, 24 B per membership + 48 B per set, once for all V vectors
+        units_M, units_G = int(n_per_set[small].sum()), int(small.sum())
+        alg_bytes = 24.0 * units_M + 48.0 * units_G
+        flop_alg = 50.0 * units_M * V
+    else:
+        # one of the two passes over the big sets: one 16-byte member record per membership + the per-set record
+        units_M, units_G = int(n_per_set[~small].sum()), int((~small).sum())
+        alg_bytes = 16.0 * units_M + 48.0 * units_G
+        flop_alg = 25.0 * units_M * V
     avg_ms = dom_ms / max(dom_n, 1)
     ach = alg_bytes / (avg_ms * 1e-3) / 1e9
-    flop_alg = 50.0 * M * V  # SURVEY §8d F_alg per pass
     breakdown = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items() if v[1]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -307,7 +319,8 @@ def run_sliding(args):
         "gpu_launches": int(launches),
         "gpu_launches_note": "hand-written kernels only (CUB radix-sort/scan launches inside the set build are not counted)",
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "memberships_per_launch": units_M, "sets_per_launch": units_G,
+                     "vectors_per_launch": V, "peak_source": peak_src,
                      "fp32": {"algorithmic_flop_per_launch": flop_alg, "achieved_tflops": flop_alg / (avg_ms * 1e-3) / 1e12,
                               "note": "the forward-difference formulation is FP32-issue bound, not HBM bound (SURVEY §8d, DESIGN.md)"}},
         "device_ms_per_step_breakdown": breakdown,

@@ -76,6 +76,7 @@ def load_library():
         "dmsa_b200_destroy": (None, [vp]),
         "dmsa_b200_last_error": (C.c_char_p, [vp]),
         "dmsa_b200_version": (i32, []),
+        "dmsa_b200_fuse_threshold": (i32, []),
         "dmsa_b200_launch_count": (i64, [vp]),
         "dmsa_b200_synchronize": (i32, [vp]),
         "dmsa_b200_traj_init": (i32, [vp, f64, f64, i32, i32, f64]),
@@ -125,7 +126,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "dmsa_b200_create", "dmsa_b200_destroy", "dmsa_b200_last_error", "dmsa_b200_version", "dmsa_b200_launch_count", "dmsa_b200_synchronize",
+    "dmsa_b200_create", "dmsa_b200_destroy", "dmsa_b200_last_error", "dmsa_b200_version", "dmsa_b200_fuse_threshold", "dmsa_b200_launch_count", "dmsa_b200_synchronize",
     "dmsa_b200_traj_init", "dmsa_b200_traj_register_scans", "dmsa_b200_traj_add_static_points", "dmsa_b200_traj_remove_static_points",
     "dmsa_b200_traj_get_timing", "dmsa_b200_traj_get_tform_ids", "dmsa_b200_traj_set_imu_factors", "dmsa_b200_kf_init",
     "dmsa_b200_kf_set_keyframe", "dmsa_b200_kf_commit", "dmsa_b200_kf_set_gravity_terms", "dmsa_b200_kf_set_odometry_terms",

@@ -13,7 +13,9 @@ OUT = os.path.join(_HERE, "lib", "libdmsa_b200.so")
 
 # -fmad=false: the reference's float arithmetic has no FMA contraction (CMakeLists.txt:13-17, baseline x86-64);
 # the kernels use explicit fma() where fusion is wanted (J^T J) and explicit *_rn intrinsics on the parity-critical path.
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-shared",
+              # host side (LM solve): AVX2 vector loops, still no FMA contraction so results equal the scalar sequence
+              "-Xcompiler", "-O3,-mavx2,-ffp-contract=off"]
 
 
 def nvcc_path():

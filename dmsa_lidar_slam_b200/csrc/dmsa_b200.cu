@@ -26,7 +26,8 @@ using namespace dmsa;
 
 namespace {
 
-constexpr int CHUNK = 512;  // members per cost-kernel work unit
+constexpr int CHUNK = COST_CHUNK;     // members per work unit of the chunked cost kernels (big sets)
+constexpr int FUSE_MAX = COST_CHUNK;  // sets up to this many members are evaluated by one block of the fused cost kernel
 
 template <class T>
 struct DBuf {
@@ -101,11 +102,12 @@ struct HostPoses {
     }
 };
 
-// Eigen dynamic inverse() == PartialPivLU: explicit inverse by LU with partial pivoting (DmsaOptimizer.h:113)
+// Eigen dynamic inverse() == PartialPivLU: explicit inverse by LU with partial pivoting (DmsaOptimizer.h:113).
+// All n right-hand sides are substituted together, row by row (contiguous axpy loops the host compiler vectorises);
+// every element still sees exactly the operation sequence of a column-by-column substitution (j ascending).
 bool lu_solve_inverse(const std::vector<double>& A, int n, std::vector<double>& inv) {
     std::vector<double> a(A);
     std::vector<int> piv(n);
-    inv.assign((size_t)n * n, 0.0);
     for (int i = 0; i < n; ++i) piv[i] = i;
     for (int k = 0; k < n; ++k) {
         int p = k;
@@ -121,31 +123,41 @@ bool lu_solve_inverse(const std::vector<double>& A, int n, std::vector<double>& 
             for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)p * n + j]);
             std::swap(piv[k], piv[p]);
         }
-        double d = a[(size_t)k * n + k];
+        const double d = a[(size_t)k * n + k];
+        const double* __restrict__ ak = &a[(size_t)k * n];
         for (int i = k + 1; i < n; ++i) {
-            double f = a[(size_t)i * n + k] / d;
-            a[(size_t)i * n + k] = f;
-            double* ai = &a[(size_t)i * n];
-            const double* ak = &a[(size_t)k * n];
+            double* __restrict__ ai = &a[(size_t)i * n];
+            const double f = ai[k] / d;
+            ai[k] = f;
             for (int j = k + 1; j < n; ++j) ai[j] -= f * ak[j];
         }
     }
-    std::vector<double> x(n);
-    for (int c = 0; c < n; ++c) {
-        for (int i = 0; i < n; ++i) x[i] = (piv[i] == c) ? 1.0 : 0.0;
-        for (int i = 0; i < n; ++i) {
-            double s = x[i];
+    inv.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) inv[(size_t)i * n + piv[i]] = 1.0;  // P * I
+    // (measured: an OpenMP team costs more than it saves at P = 114; the blocks stay a plain loop)
+    const int nblk = 1;
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int c0 = (int)((long long)n * blk / nblk), c1 = (int)((long long)n * (blk + 1) / nblk);
+        for (int i = 0; i < n; ++i) {  // forward substitution, unit lower triangle
+            double* __restrict__ xi = &inv[(size_t)i * n];
             const double* ai = &a[(size_t)i * n];
-            for (int j = 0; j < i; ++j) s -= ai[j] * x[j];
-            x[i] = s;
+            for (int j = 0; j < i; ++j) {
+                const double l = ai[j];
+                const double* __restrict__ xj = &inv[(size_t)j * n];
+                for (int c = c0; c < c1; ++c) xi[c] -= l * xj[c];
+            }
         }
-        for (int i = n - 1; i >= 0; --i) {
-            double s = x[i];
+        for (int i = n - 1; i >= 0; --i) {  // back substitution
+            double* __restrict__ xi = &inv[(size_t)i * n];
             const double* ai = &a[(size_t)i * n];
-            for (int j = i + 1; j < n; ++j) s -= ai[j] * x[j];
-            x[i] = s / ai[i];
+            for (int j = i + 1; j < n; ++j) {
+                const double u = ai[j];
+                const double* __restrict__ xj = &inv[(size_t)j * n];
+                for (int c = c0; c < c1; ++c) xi[c] -= u * xj[c];
+            }
+            const double dinv = ai[i];
+            for (int c = c0; c < c1; ++c) xi[c] = xi[c] / dinv;
         }
-        for (int i = 0; i < n; ++i) inv[(size_t)i * n + c] = x[i];
     }
     return true;
 }
@@ -207,12 +219,13 @@ struct dmsa_b200_ctx {
     DBuf<unsigned long long> d_code, d_scode;
     DBuf<unsigned char> d_cub;
     DBuf<float4> d_rec, d_wrec;
-    DBuf<int> d_cell_start, d_cell_n, d_cell_level, d_cell_key, d_cell_sub, d_nchunk, d_chunk_off;
+    DBuf<int> d_cell_start, d_cell_n, d_cell_level, d_cell_key, d_cell_sub, d_cell_kind, d_nchunk, d_chunk_off, d_okey, d_oval;
     DBuf<float> d_cell_info, d_cell_w0, d_cell_w;
     DBuf<Chunk> d_chunks;
     int G = 0;
     int64_t M = 0;
     bool levelOn[2] = {false, false};
+    int cachedDepth[2] = {0, 0};
     int cellCap = 0;
 
     // cost
@@ -236,12 +249,12 @@ struct dmsa_b200_ctx {
 
 enum {
     PROF_POSE_FD = 0, PROF_POSE_LS, PROF_TRANSFORM, PROF_SETS_KEYS, PROF_SETS_SORT, PROF_SETS_STATS,
-    PROF_SUM_FD, PROF_SUM_LS, PROF_MEAN_FD, PROF_MEAN_LS, PROF_QUAD_FD, PROF_QUAD_LS, PROF_FIN_FD, PROF_FIN_LS, PROF_JTJ, PROF_COLSUM, PROF_HOST_SOLVE, PROF_HOST_ITER,
+    PROF_FUSED_FD, PROF_FUSED_LS, PROF_SUM_FD, PROF_SUM_LS, PROF_MEAN_FD, PROF_MEAN_LS, PROF_QUAD_FD, PROF_QUAD_LS, PROF_FIN_FD, PROF_FIN_LS, PROF_JTJ, PROF_COLSUM, PROF_HOST_SOLVE, PROF_HOST_ITER,
     PROF_NUM
 };
 static const char* kProfNames[PROF_NUM] = {
     "pose_tables_fd", "pose_tables_ls", "transform_points", "sets_keys_root", "sets_sort_segment", "sets_gaussians_chunks",
-    "k_cost_sum_fd", "k_cost_sum_ls", "k_cost_mean_fd", "k_cost_mean_ls", "k_cost_quad_fd", "k_cost_quad_ls", "k_cost_fin_fd", "k_cost_fin_ls",
+    "k_cost_fused_fd", "k_cost_fused_ls", "k_cost_sum_fd", "k_cost_sum_ls", "k_cost_mean_fd", "k_cost_mean_ls", "k_cost_quad_fd", "k_cost_quad_ls", "k_cost_fin_fd", "k_cost_fin_ls",
     "k_jtj", "k_col_sumsq", "host_lm_solve_wall", "host_iteration_wall"};
 
 static cudaEvent_t profEvent(dmsa_b200_ctx* ctx) {
@@ -391,7 +404,7 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
     CK(ctx->d_globO.ensure((size_t)3 * n * Vld));
     CK(ctx->d_globT.ensure((size_t)3 * n * Vld));
     CK(ctx->d_quat.ensure((size_t)4 * n * Vld));
-    CK(ctx->d_Mtab.ensure((size_t)rows * Vld * 12));
+    CK(ctx->d_Mtab.ensure((size_t)(rows + 1) * Vld * 12));  // + the identity row used by static points
     if (E > 0) CK(ctx->d_extra.ensure((size_t)E * Vld));
     PoseBatch pb;
     pb.V = V;
@@ -434,7 +447,7 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
             for (int a = 0; a < 3; ++a) imu.gravity[a] = ctx->gravity[a];
         }
         LAUNCH(k_pose_chain<0>, V, 64, smem, pb, ctx->d_Mtab.p, imu, kf, tt);
-        dim3 blk(32, 4), grd(Vld / 32, cdiv(ctx->n_total, 4));
+        dim3 blk(32, 4), grd(Vld / 32, cdiv(ctx->n_total + 1, 4));
         LAUNCH(k_dense_table, grd, blk, 0, pb, tt, ctx->d_Mtab.p);
     } else {
         kf.useGrav = ctx->useGrav && E > 0;
@@ -486,6 +499,8 @@ int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
     need = std::max(need, b);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, std::max(N, cells + 1));
     need = std::max(need, b);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, b, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, cells, 0, 10);
+    need = std::max(need, b);
     CK(ctx->d_cub.ensure(need + 256));
     return 0;
 }
@@ -494,6 +509,11 @@ int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
 int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     const int64_t N64 = numPoints(ctx);
     if (N64 <= 0 || N64 > 0x3fffffff) ARGFAIL("build_sets: no points staged (or more than 2^30)");
+    if (st->gauss_split && ctx->model == MODEL_KF) {
+        // Gaussians.h:27-85 splitSet<PointNormal> is restated in the oracle only so far; refuse loudly
+        ctx->err = "gauss_split on the keyframe model is not implemented on the GPU yet";
+        return DMSA_B200_ERR_UNSUPPORTED;
+    }
     const int N = (int)N64;
     const int nb = (N + DMSA_KEYS_BLOCK - 1) / DMSA_KEYS_BLOCK;
     const int minPts = st->min_num_points_per_set;
@@ -519,6 +539,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     CK(ctx->d_cell_level.ensure(cap));
     CK(ctx->d_cell_key.ensure((size_t)3 * cap));
     CK(ctx->d_cell_sub.ensure(cap));
+    CK(ctx->d_cell_kind.ensure(cap));
     CK(ctx->d_cell_info.ensure((size_t)9 * cap));
     CK(ctx->d_cell_w0.ensure(cap));
     CK(ctx->d_cell_w.ensure(cap));
@@ -551,13 +572,26 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
         LAUNCH(k_root, 1, 256, 0, ctx->d_world.p, N, ctx->d_linfo.p + l, bb, bb + 3 * nb, bb + 6 * nb, bb + 9 * nb);
     }
     }
-    CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int l = 0; l < 2; ++l)
-        if (ctx->levelOn[l] && ctx->h_linfo[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
-    // phase 2: sort, segment, accept, gather
+    // The radix sort needs the number of key bits (3 * octree depth + 1) on the host.  The depth of the previous build of
+    // this context is a safe guess (more bits than needed are harmless); it is verified after phase 2 and the phase is
+    // redone in the rare case the tree grew.  Without a guess: one synchronisation here.
     size_t cubBytes = ctx->d_cub.cap;
     int prev = -1;
+    int depthUsed[2] = {ctx->cachedDepth[0], ctx->cachedDepth[1]};
+    bool haveGuess = true;
+    for (int l = 0; l < 2; ++l)
+        if (ctx->levelOn[l] && depthUsed[l] <= 0) haveGuess = false;
+    if (!haveGuess) {
+        CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int l = 0; l < 2; ++l) {
+            if (ctx->levelOn[l] && ctx->h_linfo[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
+            depthUsed[l] = ctx->h_linfo[l].depth;
+        }
+    }
+phase2:
+    // phase 2: sort, segment, accept, gather
+    prev = -1;
     {
     ProfScope prof_(ctx, PROF_SETS_SORT);
     for (int l = 0; l < 2; ++l) {
@@ -566,7 +600,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
         int* keys = ctx->d_keys.p + (size_t)3 * N * l;
         int* sidx = ctx->d_sidx.p + (size_t)N * l;
         LAUNCH(k_morton, cdiv(N, 256), 256, 0, keys, N, li, ctx->d_code.p, ctx->d_idx.p);
-        const int end_bit = std::min(64, 3 * ctx->h_linfo[l].depth + 1);
+        const int end_bit = std::min(64, 3 * depthUsed[l] + 1);
         CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, cubBytes, ctx->d_code.p, ctx->d_scode.p, ctx->d_idx.p, sidx, N, 0, end_bit, ctx->stream));
         LAUNCH(k_heads, cdiv(N, 256), 256, 0, ctx->d_scode.p, N, li, ctx->d_flagA.p);
         CK(cub::DeviceScan::InclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_flagA.p, ctx->d_scanA.p, N, ctx->stream));
@@ -577,7 +611,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
         CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_acc_flag.p, ctx->d_acc_scan.p, N, ctx->stream));
         LAUNCH(k_emit_cells, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_acc_flag.p, ctx->d_acc_scan.p, sidx, keys, li,
                prev >= 0 ? ctx->d_linfo.p + prev : nullptr, l, l * N, cs, cap);
-        LAUNCH(k_gather, cdiv(N, 256), 256, 0, sidx, li, ctx->d_local.p, ctx->d_tid.p, ctx->d_world.p, ctx->d_rec.p + (size_t)N * l,
+        LAUNCH(k_gather, cdiv(N, 256), 256, 0, sidx, li, ctx->d_local.p, ctx->d_tid.p, numTableRows(ctx), ctx->d_world.p, ctx->d_rec.p + (size_t)N * l,
                ctx->d_wrec.p + (size_t)N * l);
         prev = l;
     }
@@ -585,6 +619,20 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
+    {
+        bool redo = false;
+        for (int l = 0; l < 2; ++l) {
+            if (!ctx->levelOn[l]) continue;
+            if (ctx->h_linfo[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
+            if (ctx->h_linfo[l].depth > depthUsed[l]) redo = true;
+            depthUsed[l] = ctx->h_linfo[l].depth;
+            ctx->cachedDepth[l] = ctx->h_linfo[l].depth;
+        }
+        if (redo) {
+            prev = -1;
+            goto phase2;
+        }
+    }
     int G = 0;
     for (int l = 0; l < 2; ++l)
         if (ctx->levelOn[l]) G += ctx->h_linfo[l].G;
@@ -595,11 +643,16 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     // phase 3: per-set statistics, weights, chunk list
     ProfScope prof_(ctx, PROF_SETS_STATS);
     LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G);
+    LAUNCH(k_gaussian_big, G, 256, 0, ctx->d_wrec.p, cs, G);
     LAUNCH(k_weights, 1, 1024, 0, cs, G);
-    LAUNCH(k_chunk_counts, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->rank, ctx->world, ctx->d_nchunk.p);
+    CK(ctx->d_okey.ensure((size_t)2 * cap));
+    CK(ctx->d_oval.ensure((size_t)2 * cap));
+    LAUNCH(k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, ctx->d_oval.p);
+    CK(cub::DeviceRadixSort::SortPairsDescending(ctx->d_cub.p, cubBytes, ctx->d_okey.p, ctx->d_okey.p + cap, ctx->d_oval.p, ctx->d_oval.p + cap, G, 0, 10,
+                                                 ctx->stream));
     CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), ctx->stream));
     CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, ctx->stream));
-    ctx->chunkBound = (size_t)2 * N / CHUNK + (size_t)G + 1;
+    ctx->chunkBound = (size_t)2 * N / CHUNK + (size_t)2 * N / FUSE_MAX + 2;  // big sets only
     CK(ctx->d_chunks.ensure(ctx->chunkBound));
     LAUNCH(k_chunk_fill, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
     CK(cudaGetLastError());
@@ -621,33 +674,53 @@ int runCost(dmsa_b200_ctx* ctx) {
     a.Mtab = reinterpret_cast<const float4*>(ctx->d_Mtab.p);
     a.V = V;
     a.Vld = Vld;
+    a.S = (V <= 16) ? 32 / V : 1;
+    a.order = nullptr;
     a.info = ctx->d_cell_info.p;
     a.w = ctx->d_cell_w.p;
+    a.cell_start = ctx->d_cell_start.p;
     a.cell_n = ctx->d_cell_n.p;
+    a.cell_kind = ctx->d_cell_kind.p;
     a.nchunk = ctx->d_nchunk.p;
     a.chunk_off = ctx->d_chunk_off.p;
-    a.S = ctx->d_S.p;
+    a.S_part = ctx->d_S.p;
     a.mu = ctx->d_mu.p;
     a.Q = ctx->d_Q.p;
     a.E = ctx->d_E.p;
+    a.order = ctx->d_oval.p + ctx->cellCap;
     const unsigned grid = (unsigned)ctx->chunkBound;
     const int ph = ctx->phase ? 1 : 0;
+    const bool packed = a.S > 1;
+    const int cls = packed ? 0 : (Vld <= 128 ? 1 : (Vld <= 256 ? 2 : (Vld <= 512 ? 3 : 4)));
+#define DISPATCH(KERN, GRID, ...)                                                          \
+    switch (cls) {                                                                         \
+        case 0: LAUNCH((KERN<true, 32, 24>), GRID, 32, 0, __VA_ARGS__); break;             \
+        case 1: LAUNCH((KERN<false, 128, 10>), GRID, Vld, 0, __VA_ARGS__); break;          \
+        case 2: LAUNCH((KERN<false, 256, 5>), GRID, Vld, 0, __VA_ARGS__); break;           \
+        case 3: LAUNCH((KERN<false, 512, 2>), GRID, Vld, 0, __VA_ARGS__); break;           \
+        default: LAUNCH((KERN<false, 1024, 1>), GRID, Vld, 0, __VA_ARGS__); break;         \
+    }
+    {
+        ProfScope p_(ctx, PROF_FUSED_FD + ph);
+        DISPATCH(k_cost_fused, G, a, G);
+    }
     {
         ProfScope p_(ctx, PROF_SUM_FD + ph);
-        LAUNCH(k_cost_sum, grid, Vld, 0, a);
+        DISPATCH(k_cost_sum, grid, a);
     }
     {
         ProfScope p_(ctx, PROF_MEAN_FD + ph);
-        LAUNCH(k_cost_mean, G, Vld, 0, a, G);
+        LAUNCH(k_cost_mean, G, dim3(32, COST_RED_Y), 0, a, G);
     }
     {
         ProfScope p_(ctx, PROF_QUAD_FD + ph);
-        LAUNCH(k_cost_quad, grid, Vld, 0, a);
+        DISPATCH(k_cost_quad, grid, a);
     }
     {
         ProfScope p_(ctx, PROF_FIN_FD + ph);
-        LAUNCH(k_cost_fin, G, Vld, 0, a, G);
+        LAUNCH(k_cost_fin, G, dim3(32, COST_RED_Y), 0, a, G);
     }
+#undef DISPATCH
     if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaGetLastError());
     return 0;
@@ -844,7 +917,8 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
 // ============================================================================================
 extern "C" {
 
-int dmsa_b200_version(void) { return 100; }
+int dmsa_b200_version(void) { return 101; }
+int32_t dmsa_b200_fuse_threshold(void) { return FUSE_MAX; }
 
 int dmsa_b200_create(dmsa_b200_ctx** out, int device, void* cuda_stream) {
     if (!out) return DMSA_B200_ERR_ARG;
@@ -882,7 +956,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_relO); REL(d_extra); REL(d_Mtab);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
-    REL(d_cell_key); REL(d_cell_sub); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
+    REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
     REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_mu);
 #undef REL
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

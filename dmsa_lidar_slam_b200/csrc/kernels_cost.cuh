@@ -8,7 +8,7 @@
 // consecutive members.  Float arithmetic is the reference's, operation for operation, with explicit
 // round-to-nearest intrinsics (no FMA contraction: the reference is built without FMA):
 //   world  = ((m0*x + m1*y) + m2*z) + m3            Matrix4f * Vector4f, w == 1 (checked at upload)
-//   mean   = float(sum_j world_j) / float(n)        exactly-rounded sum (see DESIGN.md "mean")
+//   mean   = float(sum_j world_j) / float(n)        exactly-rounded sum (double accumulation; see DESIGN.md "mean")
 //   d      = world - mean
 //   term   = ((w*d)^T * info) * d                   row-vector * Matrix3f * vector, 3-element redux a0 + (a1 + a2)
 //   e      = sqrt(|sum_j double(term_j)|)
@@ -19,142 +19,280 @@
 
 namespace dmsa {
 
+#define COST_CHUNK 512  // members per block-sized work unit: == CHUNK == FUSE_MAX of dmsa_b200.cu (shared-memory staging buffer)
+
 struct CostArgs {
     const Chunk* chunks;
-    const int* n_chunks;     // device scalar: total chunks (grid is an upper bound)
-    const float4* rec;       // member records, sorted order
-    const float4* Mtab;      // [(row * Vld + v) * 3 + r]
+    const int* n_chunks;     // device scalar: total chunks of the big sets (grid is an upper bound)
+    const float4* rec;       // member records, sorted order: local xyz + transform-table row (int bits)
+    const float4* Mtab;      // [(row * Vld + v) * 3 + r]; the last row is the identity (static points)
     int V, Vld;
+    int S;                   // member sub-streams per warp: 1 when V > 16 (one thread per vector), else 32 / V lane groups
     const float* info;       // [g][9]
     const float* w;          // [g]
+    const int* cell_start;   // [g]
     const int* cell_n;       // [g]
+    const int* cell_kind;    // [g] 0: owned by another rank, 1: small (fused kernel), 2: big (chunked kernels)
+    const int* order;        // small sets in descending-size order (longest blocks first)
     const int* nchunk;       // [g]
     const int* chunk_off;    // [g]
-    double* S;               // partial sums   [(c*3 + a) * Vld + v]
+    double* S_part;          // partial sums   [(c*3 + a) * Vld + v]
     float* mu;               // means          [(g*3 + a) * Vld + v]
     double* Q;               // partial quadratic forms [c * Vld + v]
     double* E;               // residuals      [g * Vld + v]
 };
 
-__device__ __forceinline__ void load_tform(const float4* __restrict__ Mtab, int row, int Vld, int v, float4& m0, float4& m1, float4& m2) {
-    const float4* M = Mtab + ((size_t)row * Vld + v) * 3;
-    m0 = __ldg(M);
-    m1 = __ldg(M + 1);
-    m2 = __ldg(M + 2);
-}
 __device__ __forceinline__ void xform(const float4& m0, const float4& m1, const float4& m2, const float4& r, float& X, float& Y, float& Z) {
     X = fadd_(fadd_(fadd_(fmul_(m0.x, r.x), fmul_(m0.y, r.y)), fmul_(m0.z, r.z)), m0.w);
     Y = fadd_(fadd_(fadd_(fmul_(m1.x, r.x), fmul_(m1.y, r.y)), fmul_(m1.z, r.z)), m1.w);
     Z = fadd_(fadd_(fadd_(fmul_(m2.x, r.x), fmul_(m2.y, r.y)), fmul_(m2.z, r.z)), m2.w);
 }
 
-// pass 1: per-chunk coordinate sums (double)
-__global__ void __launch_bounds__(1024) k_cost_sum(CostArgs a) {
-    const int c = blockIdx.x;
-    if (c >= *a.n_chunks) return;
-    const int v = threadIdx.x;
-    if (v >= a.V) return;
-    const Chunk ch = a.chunks[c];
-    const float4* __restrict__ rec = a.rec + ch.start;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    int tprev = -2;
+// Lane mapping.  PACKED = false (V > 16): blockDim = Vld, thread = vector, every thread walks all members.
+// PACKED = true (V <= 16, the 9 line-search vectors): blockDim = 32, lane = sub * V + v; the S = 32 / V sub-streams walk
+// interleaved members and are combined in fixed order (sub 0 + sub 1 + ...) with warp shuffles.
+struct LaneMap {
+    int v, sub, stride;
+    bool active;
+};
+template <bool PACKED>
+__device__ __forceinline__ LaneMap lane_map(const CostArgs& a) {
+    LaneMap m;
+    if (!PACKED) {
+        m.v = threadIdx.x;
+        m.sub = 0;
+        m.stride = 1;
+        m.active = m.v < a.V;
+        if (!m.active) m.v = a.V - 1;
+    } else {
+        m.sub = threadIdx.x / a.V;
+        m.v = threadIdx.x - m.sub * a.V;
+        m.stride = a.S;
+        m.active = m.sub < a.S;
+    }
+    return m;
+}
+template <bool PACKED>
+__device__ __forceinline__ double combine_subs(const CostArgs& a, const LaneMap& lm, double val) {
+    if (!PACKED) return val;
+    double tot = 0.0;
+    for (int s = 0; s < a.S; ++s) tot += __shfl_sync(0xffffffffu, val, lm.v + s * a.V);
+    return tot;
+}
+
+// cooperative, coalesced staging of `count` member records into shared memory
+__device__ __forceinline__ void stage_records(float4* __restrict__ srec, const float4* __restrict__ rec, int count) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) srec[i] = __ldg(rec + i);
+    __syncthreads();
+}
+
+// The transform of row t for this thread's vector; fetched only when the row changes between consecutive members
+// (predicated loads, no branch: the loop stays straight-line so the compiler can pipeline it).
+#define DMSA_ROW_UPDATE(t)                                                                                              \
+    if ((t) != tprev) {                                                                                                \
+        const float4* Mp = reinterpret_cast<const float4*>(Mv + (size_t)(unsigned)(t) * (size_t)rowbytes);             \
+        m0 = __ldg(Mp);                                                                                                \
+        m1 = __ldg(Mp + 1);                                                                                            \
+        m2 = __ldg(Mp + 2);                                                                                            \
+        tprev = (t);                                                                                                   \
+    }
+
+// sum of the transformed coordinates of the staged members, sub-stream lm.sub
+template <bool PACKED>
+__device__ __forceinline__ void pass_sum(const CostArgs& a, const float4* __restrict__ srec, int count, const LaneMap& lm, double& sx, double& sy,
+                                         double& sz) {
+    sx = sy = sz = 0.0;
+    int tprev = -1;
     float4 m0, m1, m2;
     m0 = m1 = m2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int j = 0; j < ch.count; ++j) {
-        const float4 r = __ldg(rec + j);
-        const int t = __float_as_int(r.w);
-        float X = r.x, Y = r.y, Z = r.z;
-        if (t >= 0) {
-            if (t != tprev) {
-                load_tform(a.Mtab, t, a.Vld, v, m0, m1, m2);
-                tprev = t;
-            }
-            xform(m0, m1, m2, r, X, Y, Z);
-        }
-        sx += (double)X;
-        sy += (double)Y;
-        sz += (double)Z;
+    const char* __restrict__ Mv = reinterpret_cast<const char*>(a.Mtab) + (size_t)lm.v * 48u;  // this vector's column of the table
+    const unsigned rowbytes = (unsigned)a.Vld * 48u;
+    const int stride = PACKED ? lm.stride : 1;
+    const int nmine = (count - lm.sub + stride - 1) / stride;  // members of this sub-stream
+#define DMSA_SUM_BODY(jj)                          \
+    {                                              \
+        const float4 r = srec[(jj)];               \
+        const int t = __float_as_int(r.w);         \
+        DMSA_ROW_UPDATE(t)                         \
+        float X, Y, Z;                             \
+        xform(m0, m1, m2, r, X, Y, Z);             \
+        sx += (double)X;                           \
+        sy += (double)Y;                           \
+        sz += (double)Z;                           \
     }
-    a.S[((size_t)c * 3 + 0) * a.Vld + v] = sx;
-    a.S[((size_t)c * 3 + 1) * a.Vld + v] = sy;
-    a.S[((size_t)c * 3 + 2) * a.Vld + v] = sz;
-}
-
-// per (set, v): mean = float(sum over the set's chunks, in chunk order) / float(n)        DmsaOptimizer.h:254
-__global__ void k_cost_mean(CostArgs a, int G) {
-    const int g = blockIdx.x;
-    const int v = threadIdx.x;
-    if (g >= G || v >= a.V) return;
-    const int nc = a.nchunk[g];
-    if (nc == 0) return;
-    const int o = a.chunk_off[g];
-    double sx = 0.0, sy = 0.0, sz = 0.0;
-    for (int c = 0; c < nc; ++c) {
-        sx += a.S[((size_t)(o + c) * 3 + 0) * a.Vld + v];
-        sy += a.S[((size_t)(o + c) * 3 + 1) * a.Vld + v];
-        sz += a.S[((size_t)(o + c) * 3 + 2) * a.Vld + v];
+    int k = 0, j = lm.sub;
+    for (; k + 4 <= nmine; k += 4, j += 4 * stride) {  // no exit test inside a group of four
+        DMSA_SUM_BODY(j)
+        DMSA_SUM_BODY(j + stride)
+        DMSA_SUM_BODY(j + 2 * stride)
+        DMSA_SUM_BODY(j + 3 * stride)
     }
-    const float nf = (float)a.cell_n[g];
-    a.mu[((size_t)g * 3 + 0) * a.Vld + v] = fdiv_((float)sx, nf);
-    a.mu[((size_t)g * 3 + 1) * a.Vld + v] = fdiv_((float)sy, nf);
-    a.mu[((size_t)g * 3 + 2) * a.Vld + v] = fdiv_((float)sz, nf);
+    for (; k < nmine; ++k, j += stride) DMSA_SUM_BODY(j)
+#undef DMSA_SUM_BODY
 }
-
-// pass 2: per-chunk sums of the Mahalanobis terms                                        DmsaOptimizer.h:259-264
-__global__ void __launch_bounds__(1024) k_cost_quad(CostArgs a) {
-    const int c = blockIdx.x;
-    if (c >= *a.n_chunks) return;
-    const int v = threadIdx.x;
-    if (v >= a.V) return;
-    const Chunk ch = a.chunks[c];
-    const int g = ch.cell;
-    const float4* __restrict__ rec = a.rec + ch.start;
-    const float mx = a.mu[((size_t)g * 3 + 0) * a.Vld + v];
-    const float my = a.mu[((size_t)g * 3 + 1) * a.Vld + v];
-    const float mz = a.mu[((size_t)g * 3 + 2) * a.Vld + v];
+// sum of the Mahalanobis terms  ((w d)^T info) d                                   DmsaOptimizer.h:259-264
+template <bool PACKED>
+__device__ __forceinline__ double pass_quad(const CostArgs& a, const float4* __restrict__ srec, int count, const LaneMap& lm, int g, float mx, float my,
+                                            float mz) {
     const float* __restrict__ I = a.info + 9 * (size_t)g;
     const float i0 = __ldg(I + 0), i1 = __ldg(I + 1), i2 = __ldg(I + 2), i3 = __ldg(I + 3), i4 = __ldg(I + 4), i5 = __ldg(I + 5), i6 = __ldg(I + 6),
                 i7 = __ldg(I + 7), i8 = __ldg(I + 8);
     const float wk = __ldg(a.w + g);
     double acc = 0.0;
-    int tprev = -2;
+    int tprev = -1;
     float4 m0, m1, m2;
     m0 = m1 = m2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int j = 0; j < ch.count; ++j) {
-        const float4 r = __ldg(rec + j);
-        const int t = __float_as_int(r.w);
-        float X = r.x, Y = r.y, Z = r.z;
-        if (t >= 0) {
-            if (t != tprev) {
-                load_tform(a.Mtab, t, a.Vld, v, m0, m1, m2);
-                tprev = t;
-            }
-            xform(m0, m1, m2, r, X, Y, Z);
-        }
-        const float d0 = fsub_(X, mx), d1 = fsub_(Y, my), d2 = fsub_(Z, mz);
-        const float t0 = fmul_(wk, d0), t1 = fmul_(wk, d1), t2 = fmul_(wk, d2);
-        const float r0 = fadd_(fmul_(t0, i0), fadd_(fmul_(t1, i3), fmul_(t2, i6)));
-        const float r1 = fadd_(fmul_(t0, i1), fadd_(fmul_(t1, i4), fmul_(t2, i7)));
-        const float r2 = fadd_(fmul_(t0, i2), fadd_(fmul_(t1, i5), fmul_(t2, i8)));
-        const float s = fadd_(fmul_(r0, d0), fadd_(fmul_(r1, d1), fmul_(r2, d2)));
-        acc += (double)s;
+    const char* __restrict__ Mv = reinterpret_cast<const char*>(a.Mtab) + (size_t)lm.v * 48u;  // this vector's column of the table
+    const unsigned rowbytes = (unsigned)a.Vld * 48u;
+    const int stride = PACKED ? lm.stride : 1;
+    const int nmine = (count - lm.sub + stride - 1) / stride;
+#define DMSA_QUAD_BODY(jj)                                                                   \
+    {                                                                                        \
+        const float4 r = srec[(jj)];                                                         \
+        const int t = __float_as_int(r.w);                                                   \
+        DMSA_ROW_UPDATE(t)                                                                   \
+        float X, Y, Z;                                                                       \
+        xform(m0, m1, m2, r, X, Y, Z);                                                       \
+        const float d0 = fsub_(X, mx), d1 = fsub_(Y, my), d2 = fsub_(Z, mz);                 \
+        const float t0 = fmul_(wk, d0), t1 = fmul_(wk, d1), t2 = fmul_(wk, d2);              \
+        const float r0 = fadd_(fmul_(t0, i0), fadd_(fmul_(t1, i3), fmul_(t2, i6)));          \
+        const float r1 = fadd_(fmul_(t0, i1), fadd_(fmul_(t1, i4), fmul_(t2, i7)));          \
+        const float r2 = fadd_(fmul_(t0, i2), fadd_(fmul_(t1, i5), fmul_(t2, i8)));          \
+        const float s_ = fadd_(fmul_(r0, d0), fadd_(fmul_(r1, d1), fmul_(r2, d2)));          \
+        acc += (double)s_;                                                                   \
     }
-    a.Q[(size_t)c * a.Vld + v] = acc;
+    int k = 0, j = lm.sub;
+    for (; k + 4 <= nmine; k += 4, j += 4 * stride) {
+        DMSA_QUAD_BODY(j)
+        DMSA_QUAD_BODY(j + stride)
+        DMSA_QUAD_BODY(j + 2 * stride)
+        DMSA_QUAD_BODY(j + 3 * stride)
+    }
+    for (; k < nmine; ++k, j += stride) DMSA_QUAD_BODY(j)
+#undef DMSA_QUAD_BODY
+    return acc;
 }
 
-// per (set, v): e = sqrt(|sum of chunk partials|); rows of sets owned by other ranks are zero   DmsaOptimizer.h:267
-__global__ void k_cost_fin(CostArgs a, int G) {
-    const int g = blockIdx.x;
-    const int v = threadIdx.x;
-    if (g >= G || v >= a.Vld) return;
-    double q = 0.0;
-    if (v < a.V) {
-        const int nc = a.nchunk[g], o = a.chunk_off[g];
-        for (int c = 0; c < nc; ++c) q += a.Q[(size_t)(o + c) * a.Vld + v];
+// Small sets (n <= COST_CHUNK): one block stages the set's member records in shared memory once and runs both passes
+// on them.  Blocks are issued longest-set-first (a.order) so that the kernel does not end on a long block.
+// Also zero-fills the rows of sets owned by other ranks.
+template <bool PACKED, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
+    __shared__ float4 srec[COST_CHUNK];
+    if ((int)blockIdx.x >= G) return;
+    const int g = a.order[blockIdx.x];
+    const int kind = a.cell_kind[g];
+    if (kind == 2) return;
+    const LaneMap lm = lane_map<PACKED>(a);
+    if (kind == 0) {
+        if (lm.active && lm.sub == 0) a.E[(size_t)g * a.Vld + lm.v] = 0.0;
+        return;
     }
-    a.E[(size_t)g * a.Vld + v] = sqrt(fabs(q));
+    const int n = a.cell_n[g];
+    stage_records(srec, a.rec + a.cell_start[g], n);
+    const int cnt = lm.active ? n : 0;
+    double sx, sy, sz;
+    pass_sum<PACKED>(a, srec, cnt, lm, sx, sy, sz);
+    sx = combine_subs<PACKED>(a, lm, sx);
+    sy = combine_subs<PACKED>(a, lm, sy);
+    sz = combine_subs<PACKED>(a, lm, sz);
+    const float nf = (float)n;
+    const float mx = fdiv_((float)sx, nf), my = fdiv_((float)sy, nf), mz = fdiv_((float)sz, nf);  // DmsaOptimizer.h:254
+    double q = pass_quad<PACKED>(a, srec, cnt, lm, g, mx, my, mz);
+    q = combine_subs<PACKED>(a, lm, q);
+    if (lm.active && lm.sub == 0) a.E[(size_t)g * a.Vld + lm.v] = sqrt(fabs(q));  // :267
+}
+
+// Big sets, pass 1: per-chunk coordinate sums (double)
+template <bool PACKED, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
+    __shared__ float4 srec[COST_CHUNK];
+    const int c = blockIdx.x;
+    if (c >= *a.n_chunks) return;
+    const LaneMap lm = lane_map<PACKED>(a);
+    const Chunk ch = a.chunks[c];
+    stage_records(srec, a.rec + ch.start, ch.count);
+    double sx, sy, sz;
+    pass_sum<PACKED>(a, srec, lm.active ? ch.count : 0, lm, sx, sy, sz);
+    sx = combine_subs<PACKED>(a, lm, sx);
+    sy = combine_subs<PACKED>(a, lm, sy);
+    sz = combine_subs<PACKED>(a, lm, sz);
+    if (lm.active && lm.sub == 0) {
+        a.S_part[((size_t)c * 3 + 0) * a.Vld + lm.v] = sx;
+        a.S_part[((size_t)c * 3 + 1) * a.Vld + lm.v] = sy;
+        a.S_part[((size_t)c * 3 + 2) * a.Vld + lm.v] = sz;
+    }
+}
+
+#define COST_RED_Y 8
+// Big sets: mean = float(sum over the set's chunks) / float(n).  blockDim = (32, COST_RED_Y): lane = vector, the
+// COST_RED_Y rows take interleaved chunks and are combined in fixed order.                         DmsaOptimizer.h:254
+__global__ void k_cost_mean(CostArgs a, int G) {
+    __shared__ double red[COST_RED_Y][3][33];
+    const int g = blockIdx.x;
+    if (g >= G || a.cell_kind[g] != 2) return;
+    const int nc = a.nchunk[g], o = a.chunk_off[g];
+    const float nf = (float)a.cell_n[g];
+    for (int v0 = 0; v0 < a.V; v0 += 32) {
+        const int v = v0 + threadIdx.x;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        if (v < a.V)
+            for (int c = threadIdx.y; c < nc; c += COST_RED_Y) {
+                sx += a.S_part[((size_t)(o + c) * 3 + 0) * a.Vld + v];
+                sy += a.S_part[((size_t)(o + c) * 3 + 1) * a.Vld + v];
+                sz += a.S_part[((size_t)(o + c) * 3 + 2) * a.Vld + v];
+            }
+        red[threadIdx.y][0][threadIdx.x] = sx;
+        red[threadIdx.y][1][threadIdx.x] = sy;
+        red[threadIdx.y][2][threadIdx.x] = sz;
+        __syncthreads();
+        if (threadIdx.y < 3 && v < a.V) {
+            double t = 0.0;
+            for (int y = 0; y < COST_RED_Y; ++y) t += red[y][threadIdx.y][threadIdx.x];
+            a.mu[((size_t)g * 3 + threadIdx.y) * a.Vld + v] = fdiv_((float)t, nf);
+        }
+        __syncthreads();
+    }
+}
+
+// Big sets, pass 2: per-chunk sums of the Mahalanobis terms
+template <bool PACKED, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
+    __shared__ float4 srec[COST_CHUNK];
+    const int c = blockIdx.x;
+    if (c >= *a.n_chunks) return;
+    const LaneMap lm = lane_map<PACKED>(a);
+    const Chunk ch = a.chunks[c];
+    const int g = ch.cell;
+    stage_records(srec, a.rec + ch.start, ch.count);
+    const float mx = a.mu[((size_t)g * 3 + 0) * a.Vld + lm.v];
+    const float my = a.mu[((size_t)g * 3 + 1) * a.Vld + lm.v];
+    const float mz = a.mu[((size_t)g * 3 + 2) * a.Vld + lm.v];
+    double acc = pass_quad<PACKED>(a, srec, lm.active ? ch.count : 0, lm, g, mx, my, mz);
+    acc = combine_subs<PACKED>(a, lm, acc);
+    if (lm.active && lm.sub == 0) a.Q[(size_t)c * a.Vld + lm.v] = acc;
+}
+
+// Big sets: e = sqrt(|sum of chunk partials|), same thread layout as k_cost_mean                   DmsaOptimizer.h:267
+__global__ void k_cost_fin(CostArgs a, int G) {
+    __shared__ double red[COST_RED_Y][33];
+    const int g = blockIdx.x;
+    if (g >= G || a.cell_kind[g] != 2) return;
+    const int nc = a.nchunk[g], o = a.chunk_off[g];
+    for (int v0 = 0; v0 < a.V; v0 += 32) {
+        const int v = v0 + threadIdx.x;
+        double q = 0.0;
+        if (v < a.V)
+            for (int c = threadIdx.y; c < nc; c += COST_RED_Y) q += a.Q[(size_t)(o + c) * a.Vld + v];
+        red[threadIdx.y][threadIdx.x] = q;
+        __syncthreads();
+        if (threadIdx.y == 0 && v < a.V) {
+            double t = 0.0;
+            for (int y = 0; y < COST_RED_Y; ++y) t += red[y][threadIdx.x];
+            a.E[(size_t)g * a.Vld + v] = sqrt(fabs(t));
+        }
+        __syncthreads();
+    }
 }
 
 // per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): one block per v, fixed reduction order
@@ -268,8 +406,8 @@ __global__ void k_transform_points(const float4* __restrict__ local, const int* 
         world[i] = p;
         return;
     }
-    float4 m0, m1, m2;
-    load_tform(Mtab, t, Vld, v, m0, m1, m2);
+    const float4* Mp = Mtab + ((size_t)t * Vld + v) * 3;
+    const float4 m0 = __ldg(Mp), m1 = __ldg(Mp + 1), m2 = __ldg(Mp + 2);
     float4 o;
     xform(m0, m1, m2, p, o.x, o.y, o.z);
     o.w = p.w;

@@ -147,6 +147,12 @@ __global__ void k_pose_chain(PoseBatch pb, float* __restrict__ Mtab, ImuFactors 
             }
         }
     }
+    if (MODEL == 1 && threadIdx.x == 0) {  // identity row (unused by keyframe points, kept for uniformity)
+        float4* M = reinterpret_cast<float4*>(Mtab + ((size_t)n * Vld + v) * 12);
+        M[0] = make_float4(1.f, 0.f, 0.f, 0.f);
+        M[1] = make_float4(0.f, 1.f, 0.f, 0.f);
+        M[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+    }
     if (pb.extra == nullptr) return;
     __syncthreads();
     // D: additional residual rows
@@ -248,8 +254,15 @@ __global__ void k_pose_chain(PoseBatch pb, float* __restrict__ Mtab, ImuFactors 
 __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ Mtab) {
     const int v = blockIdx.x * 32 + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (v >= pb.V || j >= tt.n_total) return;
+    if (v >= pb.V || j > tt.n_total) return;
     const int n = pb.n, Vld = pb.Vld;
+    if (j == tt.n_total) {  // identity row: static points (already in the world frame) go through the same code path
+        float4* M = reinterpret_cast<float4*>(Mtab + ((size_t)j * Vld + v) * 12);
+        M[0] = make_float4(1.f, 0.f, 0.f, 0.f);
+        M[1] = make_float4(0.f, 1.f, 0.f, 0.f);
+        M[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+        return;
+    }
     // orientation (:194-198, :570-591)
     const int r = tt.seg[j];
     Vec3 aa;

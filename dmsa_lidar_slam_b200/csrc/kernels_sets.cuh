@@ -368,15 +368,17 @@ __global__ void k_emit_cells(const int* __restrict__ raw_start, const int* __res
     cs.key[3 * g + 2] = keys[3 * (size_t)p + 2];
 }
 
-// Member records in sorted order: rec = (local xyz, transform-row index as int bits; -1 = static point, no transform),
+// Member records in sorted order: rec = (local xyz, transform-table row as int bits; static points -> identity row),
 // wrec = world xyz at the base pose (input of the covariance).
 __global__ void k_gather(const int* __restrict__ idx, const LevelInfo* __restrict__ info, const float4* __restrict__ local,
-                         const int* __restrict__ tid, const float4* __restrict__ world, float4* __restrict__ rec, float4* __restrict__ wrec) {
+                         const int* __restrict__ tid, int identity_row, const float4* __restrict__ world, float4* __restrict__ rec,
+                         float4* __restrict__ wrec) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= info->n_valid) return;
     const int p = idx[i];
     float4 l = local[p];
-    l.w = __int_as_float(tid[p]);
+    const int t = tid[p];
+    l.w = __int_as_float(t < 0 ? identity_row : t);  // static points: the table's identity row reproduces them exactly
     rec[i] = l;
     wrec[i] = world[p];
 }
@@ -434,46 +436,12 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// One warp per accepted set.  Gaussians.h:146-154, 181-201 (covariance, eigenvalue clamp, information matrix).
-__global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (g >= G) return;
-    const int s = cs.start[g], n = cs.n[g];
-    // colwise().mean(): exactly-rounded sum, float division
-    double sx = 0, sy = 0, sz = 0;
-    for (int j = lane; j < n; j += 32) {
-        float4 p = wrec[s + j];
-        sx += (double)p.x;
-        sy += (double)p.y;
-        sz += (double)p.z;
-    }
-    sx = warp_sum(sx);
-    sy = warp_sum(sy);
-    sz = warp_sum(sz);
+// Gaussians.h:146-154, 181-201 given the exactly-rounded coordinate sums (s) and centred second moments (acc)
+__device__ inline void gaussian_finish(CellStore cs, int g, int n, const double acc[6]) {
     const float nf = (float)n;
-    const float mx = fdiv_((float)sx, nf), my = fdiv_((float)sy, nf), mz = fdiv_((float)sz, nf);
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0;
-    for (int j = lane; j < n; j += 32) {
-        float4 p = wrec[s + j];
-        double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
-        a0 += cx * cx;
-        a1 += cx * cy;
-        a2 += cx * cz;
-        a3 += cy * cy;
-        a4 += cy * cz;
-        a5 += cz * cz;
-    }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    a2 = warp_sum(a2);
-    a3 = warp_sum(a3);
-    a4 = warp_sum(a4);
-    a5 = warp_sum(a5);
-    if (lane != 0) return;
     const float den = (float)(n - 1);
-    const float cxx = fdiv_((float)a0, den), cxy = fdiv_((float)a1, den), cxz = fdiv_((float)a2, den);
-    const float cyy = fdiv_((float)a3, den), cyz = fdiv_((float)a4, den), czz = fdiv_((float)a5, den);
+    const float cxx = fdiv_((float)acc[0], den), cxy = fdiv_((float)acc[1], den), cxz = fdiv_((float)acc[2], den);
+    const float cyy = fdiv_((float)acc[3], den), cyz = fdiv_((float)acc[4], den), czz = fdiv_((float)acc[5], den);
     double A[9] = {cxx, cxy, cxz, cxy, cyy, cyz, cxz, cyz, czz};
     double l[3], V[9];
     jacobi3(A, l, V);
@@ -506,6 +474,101 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G)
     cs.w0[g] = fmul_(fdiv_(1.0f, nf), 1.0f);  // Gaussians.h:172-175, observation weight 1 (OptimizablePointSet.h:52)
 }
 
+#define GAUSS_WARP_MAX 1024
+// One warp per accepted set with n <= GAUSS_WARP_MAX members.
+__global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= G) return;
+    const int s = cs.start[g], n = cs.n[g];
+    if (n > GAUSS_WARP_MAX) return;
+    // colwise().mean(): exactly-rounded sum, float division
+    double sx = 0, sy = 0, sz = 0;
+    for (int j = lane; j < n; j += 32) {
+        float4 p = wrec[s + j];
+        sx += (double)p.x;
+        sy += (double)p.y;
+        sz += (double)p.z;
+    }
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    sz = warp_sum(sz);
+    const float nf = (float)n;
+    const float mx = fdiv_((float)sx, nf), my = fdiv_((float)sy, nf), mz = fdiv_((float)sz, nf);
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = lane; j < n; j += 32) {
+        float4 p = wrec[s + j];
+        double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
+        a[0] += cx * cx;
+        a[1] += cx * cy;
+        a[2] += cx * cz;
+        a[3] += cy * cy;
+        a[4] += cy * cz;
+        a[5] += cz * cz;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = warp_sum(a[k]);
+    if (lane == 0) gaussian_finish(cs, g, n, a);
+}
+// One 256-thread block per accepted set with n > GAUSS_WARP_MAX members (grid = G, other blocks exit at once).
+__global__ void __launch_bounds__(256) k_gaussian_big(const float4* __restrict__ wrec, CellStore cs, int G) {
+    __shared__ double red[8][6];
+    __shared__ float smean[3];
+    const int g = blockIdx.x;
+    if (g >= G) return;
+    const int s = cs.start[g], n = cs.n[g];
+    if (n <= GAUSS_WARP_MAX) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double sx = 0, sy = 0, sz = 0;
+    for (int j = threadIdx.x; j < n; j += 256) {
+        float4 p = wrec[s + j];
+        sx += (double)p.x;
+        sy += (double)p.y;
+        sz += (double)p.z;
+    }
+    sx = warp_sum(sx);
+    sy = warp_sum(sy);
+    sz = warp_sum(sz);
+    if (lane == 0) {
+        red[wid][0] = sx;
+        red[wid][1] = sy;
+        red[wid][2] = sz;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        smean[threadIdx.x] = fdiv_((float)t, (float)n);
+    }
+    __syncthreads();
+    const float mx = smean[0], my = smean[1], mz = smean[2];
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = threadIdx.x; j < n; j += 256) {
+        float4 p = wrec[s + j];
+        double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
+        a[0] += cx * cx;
+        a[1] += cx * cy;
+        a[2] += cx * cz;
+        a[3] += cy * cy;
+        a[4] += cy * cz;
+        a[5] += cz * cz;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = warp_sum(a[k]);
+    __syncthreads();
+    if (lane == 0)
+        for (int k = 0; k < 6; ++k) red[wid][k] = a[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[6];
+        for (int k = 0; k < 6; ++k) {
+            t[k] = 0;
+            for (int w = 0; w < 8; ++w) t[k] += red[w][k];
+        }
+        gaussian_finish(cs, g, n, t);
+    }
+}
+
 // Gaussians.h:177: w / w.mean()   (one block; deterministic double reduction, one rounding)
 __global__ void k_weights(CellStore cs, int G) {
     __shared__ double part[1024];
@@ -521,14 +584,22 @@ __global__ void k_weights(CellStore cs, int G) {
     for (int g = threadIdx.x; g < G; g += blockDim.x) cs.w[g] = fdiv_(cs.w0[g], mean);
 }
 
-// ---- work decomposition for the cost kernels: fixed-size chunks of members ----------------------------------------
+// ---- work decomposition for the cost kernels ------------------------------------------------------------------------
+// Sets with at most FUSE_MAX members are evaluated by one block (fused kernel); larger sets are cut into chunks of CH
+// members so that no block runs long and the per-set reductions stay parallel.
 struct Chunk {
     int cell, start, count, first;  // first: index of the set's first chunk
 };
-__global__ void k_chunk_counts(CellStore cs, int G, int CH, int rank, int world, int* __restrict__ nchunk) {
+__global__ void k_cell_plan(CellStore cs, int G, int CH, int fuse_max, int rank, int world, int* __restrict__ kind, int* __restrict__ nchunk,
+                            int* __restrict__ okey, int* __restrict__ oval) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
-    nchunk[g] = (g % world == rank) ? (cs.n[g] + CH - 1) / CH : 0;
+    const int n = cs.n[g];
+    const int k = (g % world == rank) ? (n <= fuse_max ? 1 : 2) : 0;
+    kind[g] = k;
+    nchunk[g] = (k == 2) ? (n + CH - 1) / CH : 0;
+    okey[g] = (k == 1) ? n : 0;  // sort key of the fused kernel's longest-first order (n <= fuse_max < 1024: 10 bits)
+    oval[g] = g;
 }
 // chunk_off = exclusive scan of nchunk (G+1 entries, last = total)
 __global__ void k_chunk_fill(CellStore cs, int G, int CH, const int* __restrict__ nchunk, const int* __restrict__ chunk_off, Chunk* __restrict__ chunks) {

@@ -95,6 +95,8 @@ int dmsa_b200_create(dmsa_b200_ctx** out, int device, void* cuda_stream);
 void dmsa_b200_destroy(dmsa_b200_ctx* ctx);
 const char* dmsa_b200_last_error(const dmsa_b200_ctx* ctx);
 int dmsa_b200_version(void);
+/* sets with at most this many members are evaluated by the fused cost kernel (the rest by the chunked kernels) */
+int32_t dmsa_b200_fuse_threshold(void);
 /* number of kernels this library has launched on the context's stream since creation */
 int64_t dmsa_b200_launch_count(const dmsa_b200_ctx* ctx);
 int dmsa_b200_synchronize(dmsa_b200_ctx* ctx);
