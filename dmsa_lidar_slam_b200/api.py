@@ -116,6 +116,7 @@ def load_library():
         "dmsa_b200_set_shard": (i32, [vp, i32, i32]),
         "dmsa_b200_cost_jacobian_dev": (i32, [vp, vp]),
         "dmsa_b200_line_search_costs_dev": (i32, [vp, vp, vp]),
+        "dmsa_b200_lm_solve": (i32, [P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -135,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_num_points", "dmsa_b200_get_global_points", "dmsa_b200_traj_get_dense_tforms", "dmsa_b200_build_sets", "dmsa_b200_get_sets",
     "dmsa_b200_get_voxel_keys", "dmsa_b200_eval_cost", "dmsa_b200_cost_jacobian", "dmsa_b200_iteration", "dmsa_b200_optimize",
     "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
-    "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev",
+    "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
 ]
 
 
@@ -318,6 +319,15 @@ class OptimizablePointSet:
             out[self.L.dmsa_b200_profile_name(i).decode()] = (ms.value, cnt.value)
         return out
 
+    def costJacobianDev(self, hg_dev_ptr):
+        """Partial [H | g | err0] of this context's sets into caller-owned DEVICE memory (P*P + P + 1 doubles)."""
+        self.ctx._ck(self.L.dmsa_b200_cost_jacobian_dev(self.h, C.c_void_p(hg_dev_ptr)))
+
+    def lineSearchCostsDev(self, step, ls_dev_ptr):
+        """Partial costs of the 9 trial points p + 0.1 k step into caller-owned DEVICE memory (9 doubles)."""
+        st = _c64(step)
+        self.ctx._ck(self.L.dmsa_b200_line_search_costs_dev(self.h, _p(st), C.c_void_p(ls_dev_ptr)))
+
     def setShard(self, rank, world):
         self.ctx._ck(self.L.dmsa_b200_set_shard(self.h, int(rank), int(world)))
 
@@ -441,3 +451,15 @@ class DmsaOptimizer:
         self.last_report = rep.asdict()
         s._G = rep.num_gaussians
         return self.last_report
+
+
+def lm_solve(settings, hg, n_params):
+    """step = -alpha (H + lambda I)^-1 g with the library's own LU inverse and clamp (DmsaOptimizer.h:107-128)."""
+    L = load_library()
+    hg = _c64(hg)
+    step = np.zeros(n_params)
+    nan = C.c_int32()
+    rc = L.dmsa_b200_lm_solve(C.byref(settings), _p(hg), int(n_params), _p(step), C.byref(nan))
+    if rc != 0:
+        raise DmsaError(f"dmsa_b200_lm_solve failed ({rc})")
+    return step, bool(nan.value)

@@ -1511,6 +1511,17 @@ int dmsa_b200_profile_read(dmsa_b200_ctx* ctx, int32_t id, double* total_ms, int
     return 0;
 }
 
+// Host-side LM step of DmsaOptimizer.h:107-128 on an (all-reduced) [H | g | err0] buffer: H.diag += lambda,
+// step = -alpha * H^-1 * g (explicit LU inverse like Eigen's inverse()), NaN guard, infinity-norm clamp.
+int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step, int32_t* has_nan) {
+    if (!settings || !hg || !step || n_params <= 0) return DMSA_B200_ERR_ARG;
+    std::vector<double> st;
+    int nan = solveStep(settings, hg, n_params, st);
+    std::copy(st.begin(), st.end(), step);
+    if (has_nan) *has_nan = nan;
+    return 0;
+}
+
 // ---- multi-GPU row sharding -----------------------------------------------------------------------------
 int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world) {
     if (world < 1 || rank < 0 || rank >= world) ARGFAIL("set_shard: bad rank/world");

@@ -190,6 +190,10 @@ int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev);
 /* 9 partial line-search costs for step (host P doubles) into ls_dev[9] (device) */
 int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, double* ls_dev);
 
+/* Host-side LM step (DmsaOptimizer.h:107-128) on a host copy of the (all-reduced) [H | g | err0] buffer; no context needed.
+ * step: n_params doubles (clamped); *has_nan = 1 if the step contains NaN (the caller restores the parameters and stops). */
+int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step, int32_t* has_nan);
+
 #ifdef __cplusplus
 }
 #endif
