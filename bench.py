@@ -193,7 +193,9 @@ def run_sliding(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     win = synth.make_config(args.config, seed=None if world == 1 else 100 + rank)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))  # a real (non-default) stream: the library launches on it, torch events see it
     stream = torch.cuda.current_stream().cuda_stream
+    assert stream != 0
     s = DmsaOptimSettings(**SETTINGS)
     traj = ContinuousTrajectory.from_window(win, device=local, stream=stream)
     traj.centralize()

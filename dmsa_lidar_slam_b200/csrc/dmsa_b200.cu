@@ -215,7 +215,10 @@ struct dmsa_b200_ctx {
     // set construction
     DBuf<LevelInfo> d_linfo;
     LevelInfo h_linfo[2];
-    DBuf<int> d_keys, d_bb, d_idx, d_sidx, d_flagA, d_scanA, d_raw_start, d_raw_diff, d_acc_flag, d_acc_scan;
+    DBuf<int> d_keys, d_bb, d_idx, d_sidx, d_flagA, d_scanA, d_raw_start, d_raw_diff, d_acc_flag, d_acc_scan, d_out_cnt, d_sub, d_ntile, d_tile_off,
+        d_best_ij, d_scratch;
+    DBuf<SplitTile> d_tiles;
+    DBuf<float> d_best_v;
     DBuf<unsigned long long> d_code, d_scode;
     DBuf<unsigned char> d_cub;
     DBuf<float4> d_rec, d_wrec;
@@ -509,11 +512,8 @@ int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
 int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     const int64_t N64 = numPoints(ctx);
     if (N64 <= 0 || N64 > 0x3fffffff) ARGFAIL("build_sets: no points staged (or more than 2^30)");
-    if (st->gauss_split && ctx->model == MODEL_KF) {
-        // Gaussians.h:27-85 splitSet<PointNormal> is restated in the oracle only so far; refuse loudly
-        ctx->err = "gauss_split on the keyframe model is not implemented on the GPU yet";
-        return DMSA_B200_ERR_UNSUPPORTED;
-    }
+    // splitSet is specialised for PointCloud<PointNormal> only (Gaussians.h:19-28): the trajectory model never splits
+    const bool split = st->gauss_split && ctx->model == MODEL_KF;
     const int N = (int)N64;
     const int nb = (N + DMSA_KEYS_BLOCK - 1) / DMSA_KEYS_BLOCK;
     const int minPts = st->min_num_points_per_set;
@@ -532,6 +532,17 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     CK(ctx->d_raw_diff.ensure((size_t)N + 2));
     CK(ctx->d_acc_flag.ensure((size_t)N + 2));
     CK(ctx->d_acc_scan.ensure((size_t)N + 2));
+    CK(ctx->d_out_cnt.ensure((size_t)N + 2));
+    CK(ctx->d_sub.ensure((size_t)6 * ((size_t)N + 2)));
+    const size_t tileBound = (size_t)N / 256 + (size_t)N / std::max(1, minPts) + 2;
+    if (split) {
+        CK(ctx->d_ntile.ensure((size_t)N + 2));
+        CK(ctx->d_tile_off.ensure((size_t)N + 2));
+        CK(ctx->d_tiles.ensure(tileBound));
+        CK(ctx->d_best_v.ensure(tileBound));
+        CK(ctx->d_best_ij.ensure(2 * tileBound));
+        CK(ctx->d_scratch.ensure(N));
+    }
     CK(ctx->d_rec.ensure((size_t)2 * N));
     CK(ctx->d_wrec.ensure((size_t)2 * N));
     CK(ctx->d_cell_start.ensure(cap));
@@ -607,9 +618,23 @@ phase2:
         CK(cudaMemsetAsync(ctx->d_raw_diff.p, 0, ((size_t)N + 2) * sizeof(int), ctx->stream));
         LAUNCH(k_raw_starts, cdiv(N, 256), 256, 0, ctx->d_scode.p, ctx->d_flagA.p, ctx->d_scanA.p, N, li, ctx->d_raw_start.p);
         LAUNCH(k_ring_diff, cdiv(N, 256), 256, 0, sidx, ctx->d_scanA.p, ctx->d_raw_start.p, ctx->d_ring.p, li, ctx->d_raw_diff.p);
-        LAUNCH(k_accept, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_raw_diff.p, li, minPts, ctx->d_acc_flag.p);
-        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_acc_flag.p, ctx->d_acc_scan.p, N, ctx->stream));
-        LAUNCH(k_emit_cells, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_acc_flag.p, ctx->d_acc_scan.p, sidx, keys, li,
+        int* sub_start = ctx->d_sub.p;
+        int* sub_n = sub_start + 2 * ((size_t)N + 2);
+        int* sub_code = sub_n + 2 * ((size_t)N + 2);
+        LAUNCH(k_accept, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_raw_diff.p, li, minPts, ctx->d_acc_flag.p, ctx->d_out_cnt.p, sub_start, sub_n,
+               sub_code);
+        if (split) {  // Gaussians.h:27-85 on every accepted leaf
+            LAUNCH(k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, ctx->d_raw_start.p, ctx->d_acc_flag.p, li, ctx->d_ntile.p);
+            CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_ntile.p, ctx->d_tile_off.p, N + 1, ctx->stream));
+            LAUNCH(k_split_tile_fill, cdiv(N, 256), 256, 0, ctx->d_ntile.p, ctx->d_tile_off.p, li, ctx->d_tiles.p);
+            LAUNCH(k_split_pairs, (unsigned)tileBound, 256, 0, ctx->d_tiles.p, ctx->d_tile_off.p, li, ctx->d_raw_start.p, sidx, ctx->d_normal_w.p,
+                   ctx->d_best_v.p, ctx->d_best_ij.p, ctx->d_best_ij.p + tileBound);
+            LAUNCH(k_split_decide, 148 * 8, 256, 0, ctx->d_acc_flag.p, ctx->d_ntile.p, ctx->d_tile_off.p, li, ctx->d_raw_start.p, sidx, ctx->d_scratch.p,
+                   ctx->d_normal_w.p, ctx->d_ring.p, ctx->d_best_v.p, ctx->d_best_ij.p, ctx->d_best_ij.p + tileBound, minPts, ctx->d_out_cnt.p, sub_start, sub_n,
+                   sub_code);
+        }
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_out_cnt.p, ctx->d_acc_scan.p, N, ctx->stream));
+        LAUNCH(k_emit_cells, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_out_cnt.p, ctx->d_acc_scan.p, sub_start, sub_n, sub_code, sidx, keys, li,
                prev >= 0 ? ctx->d_linfo.p + prev : nullptr, l, l * N, cs, cap);
         LAUNCH(k_gather, cdiv(N, 256), 256, 0, sidx, li, ctx->d_local.p, ctx->d_tid.p, numTableRows(ctx), ctx->d_world.p, ctx->d_rec.p + (size_t)N * l,
                ctx->d_wrec.p + (size_t)N * l);
@@ -955,7 +980,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
     REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_relO); REL(d_extra); REL(d_Mtab);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
-    REL(d_acc_scan); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
+    REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
     REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_mu);
 #undef REL

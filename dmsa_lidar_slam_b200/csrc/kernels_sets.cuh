@@ -324,12 +324,212 @@ __global__ void k_ring_diff(const int* __restrict__ idx, const int* __restrict__
     if (ring[idx[i]] != ring[idx[raw_start[c]]]) raw_diff[c] = 1;
 }
 
+// Acceptance of a leaf (DmsaOptimizer.h:307) and its default emission plan: one unsplit set.
+// out_cnt[c] in {0,1,2} sets are emitted for leaf c; sub_* describe them (2 slots per leaf).
 __global__ void k_accept(const int* __restrict__ raw_start, const int* __restrict__ raw_diff, const LevelInfo* __restrict__ info, int minPts,
-                         int* __restrict__ acc_flag) {
+                         int* __restrict__ acc_flag, int* __restrict__ out_cnt, int* __restrict__ sub_start, int* __restrict__ sub_n,
+                         int* __restrict__ sub_code) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= info->R) return;
-    int n = raw_start[c + 1] - raw_start[c];
-    acc_flag[c] = (n >= minPts && raw_diff[c]) ? 1 : 0;
+    const int s = raw_start[c];
+    const int n = raw_start[c + 1] - s;
+    const int acc = (n >= minPts && raw_diff[c]) ? 1 : 0;
+    acc_flag[c] = acc;
+    out_cnt[c] = acc;
+    sub_start[2 * c] = s;
+    sub_n[2 * c] = n;
+    sub_code[2 * c] = 0;
+}
+
+// ---- splitSet<PointCloud<PointNormal>> (Gaussians.h:27-85; keyframe pass with gauss_split) --------------------------------
+// Pair search: over ordered pairs (a != b) of a leaf's members the minimum of ||n_a + n_b|| (float, first minimum in loop
+// order wins == lexicographic minimum of (value, position a, position b)).  256 first members per block x all second members.
+struct SplitTile {
+    int cell, i1_start;
+};
+__global__ void k_split_tile_counts(const int* __restrict__ raw_start, const int* __restrict__ acc_flag, const LevelInfo* __restrict__ info,
+                                    int* __restrict__ ntile) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int R = info->R;
+    if (c > R) return;
+    ntile[c] = (c < R && acc_flag[c]) ? (raw_start[c + 1] - raw_start[c] + 255) / 256 : 0;
+}
+__global__ void k_split_tile_fill(const int* __restrict__ ntile, const int* __restrict__ tile_off, const LevelInfo* __restrict__ info,
+                                  SplitTile* __restrict__ tiles) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= info->R) return;
+    const int nt = ntile[c], o = tile_off[c];
+    for (int t = 0; t < nt; ++t) {
+        SplitTile st;
+        st.cell = c;
+        st.i1_start = t * 256;
+        tiles[o + t] = st;
+    }
+}
+__device__ __forceinline__ bool pair_less(float v, int i, int j, float v2, int i2, int j2) {
+    return v < v2 || (v == v2 && (i < i2 || (i == i2 && j < j2)));
+}
+__global__ void __launch_bounds__(256) k_split_pairs(const SplitTile* __restrict__ tiles, const int* __restrict__ tile_off, const LevelInfo* __restrict__ info,
+                                                     const int* __restrict__ raw_start, const int* __restrict__ sidx,
+                                                     const float4* __restrict__ normal_w, float* __restrict__ best_v, int* __restrict__ best_i,
+                                                     int* __restrict__ best_j) {
+    __shared__ float sx[256], sy[256], sz[256];
+    __shared__ float rv[256];
+    __shared__ int ri[256], rj[256];
+    const int total = tile_off[info->R];
+    const int t = blockIdx.x;
+    if (t >= total) return;
+    const SplitTile tl = tiles[t];
+    const int s = raw_start[tl.cell], n = raw_start[tl.cell + 1] - s;
+    const int i1 = tl.i1_start + threadIdx.x;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (i1 < n) {
+        const float4 a = normal_w[sidx[s + i1]];
+        ax = a.x;
+        ay = a.y;
+        az = a.z;
+    }
+    float bv = 3.402823466e+38f;  // std::numeric_limits<float>::max(), Gaussians.h:31
+    int bj = 0x7fffffff;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int jj = j0 + threadIdx.x;
+        if (jj < n) {
+            const float4 b = normal_w[sidx[s + jj]];
+            sx[threadIdx.x] = b.x;
+            sy[threadIdx.x] = b.y;
+            sz[threadIdx.x] = b.z;
+        }
+        __syncthreads();
+        const int lim = min(256, n - j0);
+        if (i1 < n) {
+            for (int q = 0; q < lim; ++q) {
+                const int j = j0 + q;
+                if (j == i1) continue;  // id1 == id2
+                const float ux = fadd_(ax, sx[q]), uy = fadd_(ay, sy[q]), uz = fadd_(az, sz[q]);
+                const float v = __fsqrt_rn(fadd_(fmul_(ux, ux), fadd_(fmul_(uy, uy), fmul_(uz, uz))));  // (n1 + n2).norm()
+                if (v < bv) {
+                    bv = v;
+                    bj = j;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    rv[threadIdx.x] = bv;
+    ri[threadIdx.x] = (i1 < n) ? i1 : 0x7fffffff;
+    rj[threadIdx.x] = bj;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            if (pair_less(rv[threadIdx.x + o], ri[threadIdx.x + o], rj[threadIdx.x + o], rv[threadIdx.x], ri[threadIdx.x], rj[threadIdx.x])) {
+                rv[threadIdx.x] = rv[threadIdx.x + o];
+                ri[threadIdx.x] = ri[threadIdx.x + o];
+                rj[threadIdx.x] = rj[threadIdx.x + o];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        best_v[t] = rv[0];
+        best_i[t] = ri[0];
+        best_j[t] = rj[0];
+    }
+}
+// One block per accepted leaf: reduce the tiles' winners; if min <= 0.5 split the members by the nearer reference normal
+// (stable partition of the leaf's range of sidx through `scratch`), ring test of the first half, the reference's two
+// acceptance tests (DmsaOptimizer.h:319 and the :327-331 quirk: the second half re-tests the FIRST half's rings).
+__global__ void __launch_bounds__(256) k_split_decide(const int* __restrict__ acc_flag, const int* __restrict__ ntile, const int* __restrict__ tile_off,
+                                                      const LevelInfo* __restrict__ info, const int* __restrict__ raw_start, int* __restrict__ sidx,
+                                                      int* __restrict__ scratch, const float4* __restrict__ normal_w, const int* __restrict__ ring,
+                                                      const float* __restrict__ best_v, const int* __restrict__ best_i, const int* __restrict__ best_j,
+                                                      int minPts, int* __restrict__ out_cnt, int* __restrict__ sub_start, int* __restrict__ sub_n,
+                                                      int* __restrict__ sub_code) {
+    __shared__ int scan[256];
+    __shared__ int s_rmin, s_rmax;
+    __shared__ float s_bv;
+    __shared__ int s_bi, s_bj;
+  for (int c = blockIdx.x; c < info->R; c += gridDim.x) {  // block-uniform loop over leaves
+    __syncthreads();
+    if (!acc_flag[c]) continue;
+    const int s = raw_start[c], n = raw_start[c + 1] - s;
+    if (threadIdx.x == 0) {
+        float bv = 3.402823466e+38f;
+        int bi = 0x7fffffff, bj = 0x7fffffff;
+        const int o = tile_off[c], nt = ntile[c];
+        for (int t = 0; t < nt; ++t)
+            if (pair_less(best_v[o + t], best_i[o + t], best_j[o + t], bv, bi, bj)) {
+                bv = best_v[o + t];
+                bi = best_i[o + t];
+                bj = best_j[o + t];
+            }
+        s_bv = bv;
+        s_bi = bi;
+        s_bj = bj;
+        s_rmin = 2147483647;
+        s_rmax = -2147483647 - 1;
+    }
+    __syncthreads();
+    if (s_bv > 0.5f) continue;  // Gaussians.h:54: no opposite normals -> the default plan (one unsplit set) stands
+    const float4 ra = normal_w[sidx[s + s_bi]], rb = normal_w[sidx[s + s_bj]];
+    __syncthreads();
+    // stable partition: first-half members to the front of scratch in order, second-half members (reversed) to the back
+    int base1 = 0;
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        int f = 0, id = 0;
+        if (j < n) {
+            id = sidx[s + j];
+            const float4 m = normal_w[id];
+            const float ax = fsub_(ra.x, m.x), ay = fsub_(ra.y, m.y), az = fsub_(ra.z, m.z);
+            const float bx = fsub_(rb.x, m.x), by = fsub_(rb.y, m.y), bz = fsub_(rb.z, m.z);
+            const float d1 = __fsqrt_rn(fadd_(fmul_(ax, ax), fadd_(fmul_(ay, ay), fmul_(az, az))));
+            const float d2 = __fsqrt_rn(fadd_(fmul_(bx, bx), fadd_(fmul_(by, by), fmul_(bz, bz))));
+            f = d1 < d2 ? 1 : 0;  // Gaussians.h:75
+        }
+        scan[threadIdx.x] = f;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {  // inclusive Hillis-Steele scan
+            int v = threadIdx.x >= o ? scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const int incl = scan[threadIdx.x], tot = scan[255];
+        if (j < n) {
+            if (f) {
+                scratch[s + base1 + incl - 1] = id;
+                atomicMin(&s_rmin, ring[id]);
+                atomicMax(&s_rmax, ring[id]);
+            } else {
+                const int k2 = j - (base1 + incl);  // rank among the second-half members
+                scratch[s + n - 1 - k2] = id;
+            }
+        }
+        base1 += tot;
+        __syncthreads();
+    }
+    const int n1 = base1, n2 = n - n1;
+    for (int j = threadIdx.x; j < n1; j += 256) sidx[s + j] = scratch[s + j];
+    for (int j = threadIdx.x; j < n2; j += 256) sidx[s + n1 + j] = scratch[s + n - 1 - j];
+    if (threadIdx.x == 0) {
+        const bool ring1 = s_rmax != s_rmin;
+        const int ok1 = (n1 > minPts && ring1) ? 1 : 0;
+        const int ok2 = (n2 > minPts && ring1) ? 1 : 0;  // quirk: the FIRST half's ring test again
+        out_cnt[c] = ok1 + ok2;
+        int e = 0;
+        if (ok1) {
+            sub_start[2 * c + e] = s;
+            sub_n[2 * c + e] = n1;
+            sub_code[2 * c + e] = 1;
+            ++e;
+        }
+        if (ok2) {
+            sub_start[2 * c + e] = s + n1;
+            sub_n[2 * c + e] = n2;
+            sub_code[2 * c + e] = 2;
+        }
+    }
+  }
 }
 
 struct CellStore {
@@ -343,8 +543,9 @@ struct CellStore {
     float* w;     // rebalancing weight
 };
 
-// acc_scan = exclusive scan of acc_flag.  gbase_src: LevelInfo of the previous level (or null).
-__global__ void k_emit_cells(const int* __restrict__ raw_start, const int* __restrict__ acc_flag, const int* __restrict__ acc_scan,
+// out_scan = exclusive scan of out_cnt.  prev: LevelInfo of the previous level (or null).
+__global__ void k_emit_cells(const int* __restrict__ raw_start, const int* __restrict__ out_cnt, const int* __restrict__ out_scan,
+                             const int* __restrict__ sub_start, const int* __restrict__ sub_n, const int* __restrict__ sub_code,
                              const int* __restrict__ idx, const int* __restrict__ keys, LevelInfo* __restrict__ info,
                              const LevelInfo* __restrict__ prev, int level, int mbase, CellStore cs, int cap) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,20 +553,23 @@ __global__ void k_emit_cells(const int* __restrict__ raw_start, const int* __res
     const int gbase = prev ? prev->gbase + prev->G : 0;
     if (c == 0) {
         info->gbase = gbase;
-        info->G = R > 0 ? acc_scan[R - 1] + acc_flag[R - 1] : 0;
+        info->G = R > 0 ? out_scan[R - 1] + out_cnt[R - 1] : 0;
     }
-    if (c >= R || !acc_flag[c]) return;
-    const int g = gbase + acc_scan[c];
-    if (g >= cap) return;
-    const int s = raw_start[c];
-    cs.start[g] = mbase + s;
-    cs.n[g] = raw_start[c + 1] - s;
-    cs.level[g] = level;
-    cs.sub[g] = 0;
-    const int p = idx[s];
-    cs.key[3 * g] = keys[3 * (size_t)p];
-    cs.key[3 * g + 1] = keys[3 * (size_t)p + 1];
-    cs.key[3 * g + 2] = keys[3 * (size_t)p + 2];
+    if (c >= R) return;
+    const int cnt = out_cnt[c];
+    if (cnt == 0) return;
+    const int p = idx[raw_start[c]];
+    for (int e = 0; e < cnt; ++e) {
+        const int g = gbase + out_scan[c] + e;
+        if (g >= cap) return;
+        cs.start[g] = mbase + sub_start[2 * c + e];
+        cs.n[g] = sub_n[2 * c + e];
+        cs.level[g] = level;
+        cs.sub[g] = sub_code[2 * c + e];
+        cs.key[3 * g] = keys[3 * (size_t)p];
+        cs.key[3 * g + 1] = keys[3 * (size_t)p + 1];
+        cs.key[3 * g + 2] = keys[3 * (size_t)p + 2];
+    }
 }
 
 // Member records in sorted order: rec = (local xyz, transform-table row as int bits; static points -> identity row),

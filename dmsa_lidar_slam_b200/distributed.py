@@ -118,6 +118,10 @@ class KeyframeBundleOptimizer:
         self.ranges = bundle_ranges(self.n, min(bundle_size, self.n), overlap)
         self.mine = [b for i, b in enumerate(self.ranges) if i % world == rank]
         self.dev = torch.device("cuda", device)
+        # one CUDA stream for everything: the library's kernels (contexts are created on it) and torch's index_add_/all_reduce,
+        # so that the partial buffers are ordered without host synchronisation.  (Handle 0 == "create an own stream" in the C-ABI.)
+        self.stream = torch.cuda.Stream(self.dev) if not stream else torch.cuda.ExternalStream(stream, self.dev)
+        stream = self.stream.cuda_stream
         self.ex = Exchange(world)
         self.ctx, self.idx, self.scatter = [], [], []
         for (f, l) in self.mine:
@@ -145,6 +149,10 @@ class KeyframeBundleOptimizer:
 
     def iteration(self):
         """One DMSA iteration over all bundles.  Returns dict(stop, error0, best_step, step_norm, num_sets)."""
+        with self.torch.cuda.stream(self.stream):
+            return self._iteration()
+
+    def _iteration(self):
         torch = self.torch
         s = self.settings
         self._push_poses()
@@ -211,8 +219,8 @@ def bench_keyframe(args):
     sm = synth.make_keyframe_submap(n_keyframes=n_kf, n_points=n_pts, seed=4)
     st = dict(num_iter=1, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=10, min_num_gaussians=30, gauss_split=0, epsilon=1e-4)
     s = DmsaOptimSettings(**st)
-    stream = torch.cuda.current_stream().cuda_stream
-    opt = KeyframeBundleOptimizer(sm, s, 15, 8, rank, world, local, stream)
+    opt = KeyframeBundleOptimizer(sm, s, 15, 8, rank, world, local, None)
+    torch.cuda.set_stream(opt.stream)  # events / barriers below are recorded on the stream the kernels run on
     p0 = opt.p.copy()
 
     def barrier():

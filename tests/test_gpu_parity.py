@@ -426,3 +426,29 @@ def test_imu_factor_rows():
     assert rel(cj["e0"][G:], e0[G:]) < 1e-10  # ContinuousTrajectory.h:603-663
     assert rel(cj["J"][G:], J[G:]) < 1e-5
     assert rel(cj["H"], J.T @ J) < 1e-6
+
+
+def test_keyframe_gauss_split_matches_oracle():
+    """splitSet<PointNormal> (Gaussians.h:27-85) + the split acceptance quirks (DmsaOptimizer.h:310-337) — the production
+    keyframe settings use gauss_split = true (DmsaSlam.h:93)."""
+    sm = synth.make_keyframe_submap(n_keyframes=5, n_points=6000, seed=9)
+    st = dict(num_iter=2, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=6, min_num_gaussians=10, gauss_split=1, epsilon=1e-4)
+    kf = MapManagement.from_submap(sm)
+    om = ob.OracleModel.from_submap(sm)
+    om.set_mode(2)
+    s, so = DmsaOptimSettings(**st), ob.settings(**st)
+    kf.updateGlobalPoints()
+    om.update_global_points()
+    G, M = kf.buildSets(s)
+    assert G == om.build_sets(so)
+    sg, so_ = kf.getSets(), om.sets()
+    assert (so_["sub"] > 0).sum() > 10, "the fixture must exercise the split path"
+    assert (sg["sub"] == so_["sub"]).all() and (sg["offs"] == so_["offs"]).all() and (sg["members"] == so_["members"]).all()
+    assert (sg["key"] == so_["key"]).all() and rel(sg["info"], so_["info"]) < 1e-6
+    cj = kf.costJacobian(with_rows=True)
+    e0, J = om.jacobian()
+    assert rel(cj["e0"], e0) < TOL_SAME_ARITH and rel(cj["H"], J.T @ J) < 1e-7
+    for it in range(2):
+        d = kf.iteration(s)
+        assert d["stop_reason"] == om.iteration(so) and d["best_step"] == om.last_trace()["best_k"]
+    assert rel(kf.getPoseParameters(), om.get_params()) < 1e-6
