@@ -25,6 +25,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout otherwise; stdout carries exactly one JSON line
 
 SETTINGS = dict(num_iter=1, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10, min_num_gaussians=30)
 METRIC = "DMSA iterations/sec"

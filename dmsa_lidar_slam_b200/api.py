@@ -116,7 +116,7 @@ def load_library():
         "dmsa_b200_set_shard": (i32, [vp, i32, i32]),
         "dmsa_b200_cost_jacobian_dev": (i32, [vp, vp]),
         "dmsa_b200_line_search_costs_dev": (i32, [vp, vp, vp]),
-        "dmsa_b200_lm_solve": (i32, [P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
+        "dmsa_b200_lm_solve": (i32, [P(DmsaOptimSettings), vp, i32, i32, vp, P(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -453,13 +453,13 @@ class DmsaOptimizer:
         return self.last_report
 
 
-def lm_solve(settings, hg, n_params):
-    """step = -alpha (H + lambda I)^-1 g with the library's own LU inverse and clamp (DmsaOptimizer.h:107-128)."""
+def lm_solve(settings, hg, n_params, explicit_inverse=True):
+    """step = -alpha (H + lambda I)^-1 g and clamp (DmsaOptimizer.h:107-128); explicit_inverse=True is the reference's arithmetic."""
     L = load_library()
     hg = _c64(hg)
     step = np.zeros(n_params)
     nan = C.c_int32()
-    rc = L.dmsa_b200_lm_solve(C.byref(settings), _p(hg), int(n_params), _p(step), C.byref(nan))
+    rc = L.dmsa_b200_lm_solve(C.byref(settings), _p(hg), int(n_params), int(bool(explicit_inverse)), _p(step), C.byref(nan))
     if rc != 0:
         raise DmsaError(f"dmsa_b200_lm_solve failed ({rc})")
     return step, bool(nan.value)

@@ -162,6 +162,78 @@ bool lu_solve_inverse(const std::vector<double>& A, int n, std::vector<double>& 
     return true;
 }
 
+// LU with partial pivoting and ONE right-hand side (no explicit inverse): used by the keyframe-bundle extension, where no
+// reference arithmetic exists to mirror and the P x P system is large (P = 378: 3x less work than forming H^-1).
+bool lu_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) {
+    std::vector<double> a(A);
+    x.assign(b, b + n);
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        double best = std::fabs(a[(size_t)k * n + k]);
+        for (int i = k + 1; i < n; ++i) {
+            double v = std::fabs(a[(size_t)i * n + k]);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        if (p != k) {
+            for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)p * n + j]);
+            std::swap(x[k], x[p]);
+        }
+        const double d = a[(size_t)k * n + k];
+        const double* __restrict__ ak = &a[(size_t)k * n];
+        for (int i = k + 1; i < n; ++i) {
+            double* __restrict__ ai = &a[(size_t)i * n];
+            const double f = ai[k] / d;
+            for (int j = k + 1; j < n; ++j) ai[j] -= f * ak[j];
+            x[i] -= f * x[k];
+        }
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double s = x[i];
+        const double* ai = &a[(size_t)i * n];
+        for (int j = i + 1; j < n; ++j) s -= ai[j] * x[j];
+        x[i] = s / ai[i];
+    }
+    return true;
+}
+
+// Cholesky (right-looking, row-major lower triangle) solve of the SPD system (J^T J + lambda I) x = b; false if a pivot
+// is not positive (then the caller falls back to LU).  Used by the keyframe-bundle extension only.
+bool chol_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) {
+    std::vector<double> a(A), col(n);
+    for (int k = 0; k < n; ++k) {
+        const double d = a[(size_t)k * n + k];
+        if (!(d > 0.0)) return false;
+        const double lkk = std::sqrt(d);
+        a[(size_t)k * n + k] = lkk;
+        for (int i = k + 1; i < n; ++i) {
+            a[(size_t)i * n + k] /= lkk;
+            col[i] = a[(size_t)i * n + k];
+        }
+        for (int i = k + 1; i < n; ++i) {
+            double* __restrict__ ai = &a[(size_t)i * n];
+            const double lik = col[i];
+            const double* __restrict__ c = col.data();
+            for (int j = k + 1; j <= i; ++j) ai[j] -= lik * c[j];
+        }
+    }
+    x.assign(b, b + n);
+    for (int i = 0; i < n; ++i) {  // L y = b
+        double s = x[i];
+        const double* ai = &a[(size_t)i * n];
+        for (int j = 0; j < i; ++j) s -= ai[j] * x[j];
+        x[i] = s / ai[i];
+    }
+    for (int i = n - 1; i >= 0; --i) {  // L^T x = y
+        double s = x[i];
+        for (int j = i + 1; j < n; ++j) s -= a[(size_t)j * n + i] * x[j];
+        x[i] = s / a[(size_t)i * n + i];
+    }
+    return true;
+}
+
 inline int pad32(int v) { return (v + 31) / 32 * 32; }
 
 }  // namespace
@@ -236,8 +308,12 @@ struct dmsa_b200_ctx {
     DBuf<float> d_mu;
     size_t chunkBound = 0;
 
-    // host mirrors
+    // host mirrors; the small per-iteration read-backs / uploads go through one pinned block so that
+    // cudaMemcpyAsync is a true async DMA (pageable memory costs a staging copy and an implicit synchronisation)
     std::vector<double> h_hg, h_p;
+    double* pin = nullptr;  // [P*P+P+1 hg | 16 ls | P params | P step] doubles, then 2 LevelInfo
+    size_t pinCap = 0;
+    cudaEvent_t evUpload = nullptr;  // last H2D out of the pinned block (waited on before the block is rewritten)
     double lastErr0 = 0;
 
     // optional per-kernel timing with CUDA events on the launching stream (bench.py roofline)
@@ -470,13 +546,37 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
     return 0;
 }
 
+int ensurePinned(dmsa_b200_ctx* ctx, int P) {
+    if (!ctx->evUpload) CK(cudaEventCreateWithFlags(&ctx->evUpload, cudaEventDisableTiming));
+    const size_t need = ((size_t)P * P + P + 1 + 16 + 2 * (size_t)P) * sizeof(double) + 2 * sizeof(LevelInfo) + 64;
+    if (need <= ctx->pinCap) return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr;
+    ctx->pinCap = 0;
+    CK(cudaHostAlloc((void**)&ctx->pin, need, cudaHostAllocDefault));
+    ctx->pinCap = need;
+    return 0;
+}
+inline double* pinHg(dmsa_b200_ctx* ctx) { return ctx->pin; }
+inline double* pinLs(dmsa_b200_ctx* ctx, int P) { return ctx->pin + (size_t)P * P + P + 1; }
+inline double* pinParams(dmsa_b200_ctx* ctx, int P) { return pinLs(ctx, P) + 16; }
+inline double* pinStep(dmsa_b200_ctx* ctx, int P) { return pinParams(ctx, P) + P; }
+inline LevelInfo* pinLinfo(dmsa_b200_ctx* ctx, int P) { return reinterpret_cast<LevelInfo*>(pinStep(ctx, P) + P); }
+
 int uploadParams(dmsa_b200_ctx* ctx) {
     ctx->poses.getParams(ctx->h_p);
     const int P = (int)ctx->h_p.size();
+    CKRC(ensurePinned(ctx, P));
     CK(ctx->d_p.ensure(std::max(P, 1)));
     CK(ctx->d_step.ensure(std::max(P, 1)));
     CK(ctx->d_batch.ensure((size_t)(P + 1) * std::max(P, 1)));
-    if (P > 0) CK(cudaMemcpyAsync(ctx->d_p.p, ctx->h_p.data(), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (P > 0) {
+        CK(cudaEventSynchronize(ctx->evUpload));
+        std::copy(ctx->h_p.begin(), ctx->h_p.end(), pinParams(ctx, P));
+        CK(cudaMemcpyAsync(ctx->d_p.p, pinParams(ctx, P), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->evUpload, ctx->stream));
+    }
     return 0;
 }
 
@@ -515,6 +615,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     // splitSet is specialised for PointCloud<PointNormal> only (Gaussians.h:19-28): the trajectory model never splits
     const bool split = st->gauss_split && ctx->model == MODEL_KF;
     const int N = (int)N64;
+    const int Ppin = std::max(0, 6 * (ctx->poses.n - 1));
     const int nb = (N + DMSA_KEYS_BLOCK - 1) / DMSA_KEYS_BLOCK;
     const int minPts = st->min_num_points_per_set;
     const int cap = (int)std::min<int64_t>(2 * N64 / std::max(1, minPts) + 16, 2 * N64 + 16);
@@ -573,14 +674,18 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     // phase 1: anchors, keys, octree roots
     {
     ProfScope prof_(ctx, PROF_SETS_KEYS);
+    LevelPlan plan;
+    plan.n = 0;
     for (int l = 0; l < 2; ++l) {
         if (!ctx->levelOn[l]) continue;
-        const float res = factors[l] * ctx->minGridSize;  // float product, DmsaOptimizer.h:82,86
-        int* keys = ctx->d_keys.p + (size_t)3 * N * l;
-        int* bb = ctx->d_bb.p + (size_t)12 * nb * l;
-        LAUNCH(k_anchor, 1, 32, 0, ctx->d_world.p, N, res, ctx->d_linfo.p + l);
-        LAUNCH(k_keys, nb, DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, ctx->d_linfo.p + l, keys, bb, bb + 3 * nb, bb + 6 * nb, bb + 9 * nb);
-        LAUNCH(k_root, 1, 256, 0, ctx->d_world.p, N, ctx->d_linfo.p + l, bb, bb + 3 * nb, bb + 6 * nb, bb + 9 * nb);
+        plan.level[plan.n] = l;
+        plan.res[plan.n] = factors[l] * ctx->minGridSize;  // float product, DmsaOptimizer.h:82,86
+        plan.n++;
+    }
+    if (plan.n > 0) {
+        LAUNCH(k_anchor, 1, 32, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p);
+        LAUNCH(k_keys, dim3(nb, plan.n), DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_keys.p, ctx->d_bb.p, nb);
+        LAUNCH(k_root, plan.n, 256, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_bb.p, nb);
     }
     }
     // The radix sort needs the number of key bits (3 * octree depth + 1) on the host.  The depth of the previous build of
@@ -593,8 +698,10 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     for (int l = 0; l < 2; ++l)
         if (ctx->levelOn[l] && depthUsed[l] <= 0) haveGuess = false;
     if (!haveGuess) {
-        CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+        CKRC(ensurePinned(ctx, Ppin));
+        CK(cudaMemcpyAsync(pinLinfo(ctx, Ppin), ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(ctx->h_linfo, pinLinfo(ctx, Ppin), 2 * sizeof(LevelInfo));
         for (int l = 0; l < 2; ++l) {
             if (ctx->levelOn[l] && ctx->h_linfo[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
             depthUsed[l] = ctx->h_linfo[l].depth;
@@ -641,8 +748,10 @@ phase2:
         prev = l;
     }
     }
-    CK(cudaMemcpyAsync(ctx->h_linfo, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CKRC(ensurePinned(ctx, Ppin));
+    CK(cudaMemcpyAsync(pinLinfo(ctx, Ppin), ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_linfo, pinLinfo(ctx, Ppin), 2 * sizeof(LevelInfo));
     CK(cudaGetLastError());
     {
         bool redo = false;
@@ -780,7 +889,11 @@ int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
 
 int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) {
     const int P = 6 * (ctx->poses.n - 1);
-    CK(cudaMemcpyAsync(ctx->d_step.p, step_host, P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CKRC(ensurePinned(ctx, P));
+    CK(cudaEventSynchronize(ctx->evUpload));
+    std::copy(step_host, step_host + P, pinStep(ctx, P));
+    CK(cudaMemcpyAsync(ctx->d_step.p, pinStep(ctx, P), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->evUpload, ctx->stream));
     LAUNCH(k_make_ls_batch, cdiv((size_t)9 * P, 256), 256, 0, ctx->d_p.p, ctx->d_step.p, P, ctx->d_batch.p);
     ctx->phase = 1;
     int rc = runPoseTables(ctx, 9);
@@ -795,18 +908,27 @@ int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) 
 
 // H.diag += lambda; step = -alpha * H^-1 * (J^T e0); NaN guard; infinity-norm clamp      DmsaOptimizer.h:107-128
 // returns 1 if the step contains NaN
-int solveStep(const dmsa_b200_settings* st, const double* hg, int P, std::vector<double>& step) {
+int solveStep(const dmsa_b200_settings* st, const double* hg, int P, std::vector<double>& step, bool explicit_inverse = true) {
     std::vector<double> H(hg, hg + (size_t)P * P), Hinv;
     const double* g = hg + (size_t)P * P;
     for (int i = 0; i < P; ++i) H[(size_t)i * P + i] += (double)st->lambda_diag;
-    lu_solve_inverse(H, P, Hinv);
     step.assign(P, 0.0);
     bool nan = false;
-    for (int a = 0; a < P; ++a) {
-        double s = 0;
-        for (int b = 0; b < P; ++b) s += (-st->step_length_optim * Hinv[(size_t)a * P + b]) * g[b];
-        step[a] = s;
-        if (std::isnan(s)) nan = true;
+    if (explicit_inverse) {  // the reference's expression: (-alpha * H.inverse()) * (J^T e)
+        lu_solve_inverse(H, P, Hinv);
+        for (int a = 0; a < P; ++a) {
+            double s = 0;
+            for (int b = 0; b < P; ++b) s += (-st->step_length_optim * Hinv[(size_t)a * P + b]) * g[b];
+            step[a] = s;
+            if (std::isnan(s)) nan = true;
+        }
+    } else {
+        std::vector<double> x;
+        if (!chol_solve_vec(H, P, g, x)) lu_solve_vec(H, P, g, x);
+        for (int a = 0; a < P; ++a) {
+            step[a] = -st->step_length_optim * x[a];
+            if (std::isnan(step[a])) nan = true;
+        }
     }
     if (nan) return 1;
     double mx = -std::numeric_limits<double>::infinity(), mn = std::numeric_limits<double>::infinity();
@@ -882,8 +1004,9 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     CK(ctx->d_ls.ensure(16));
     CKRC(jtjInto(ctx, ctx->d_hg.p));  // :107
     ctx->h_hg.resize((size_t)P * P + P + 1);
-    CK(cudaMemcpyAsync(ctx->h_hg.data(), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    std::copy(pinHg(ctx), pinHg(ctx) + ctx->h_hg.size(), ctx->h_hg.begin());
     const double error0 = ctx->h_hg[(size_t)P * P + P];
     ctx->lastErr0 = error0;
     std::vector<double> step;
@@ -903,8 +1026,9 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     // adaptiveStepSize :152-182 — the 9 trial costs in one batch
     CKRC(lineSearchInto(ctx, step.data(), ctx->d_ls.p));
     double ls[9];
-    CK(cudaMemcpyAsync(ls, ctx->d_ls.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pinLs(ctx, P), ctx->d_ls.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    std::copy(pinLs(ctx, P), pinLs(ctx, P) + 9, ls);
     if (ctx->profiling) profCollect(ctx);
     double minError = error0;
     int best = 0;
@@ -984,6 +1108,8 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
     REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_mu);
 #undef REL
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1538,10 +1664,11 @@ int dmsa_b200_profile_read(dmsa_b200_ctx* ctx, int32_t id, double* total_ms, int
 
 // Host-side LM step of DmsaOptimizer.h:107-128 on an (all-reduced) [H | g | err0] buffer: H.diag += lambda,
 // step = -alpha * H^-1 * g (explicit LU inverse like Eigen's inverse()), NaN guard, infinity-norm clamp.
-int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step, int32_t* has_nan) {
+int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, int32_t explicit_inverse, double* step,
+                       int32_t* has_nan) {
     if (!settings || !hg || !step || n_params <= 0) return DMSA_B200_ERR_ARG;
     std::vector<double> st;
-    int nan = solveStep(settings, hg, n_params, st);
+    int nan = solveStep(settings, hg, n_params, st, explicit_inverse != 0);
     std::copy(st.begin(), st.end(), step);
     if (has_nan) *has_nan = nan;
     return 0;

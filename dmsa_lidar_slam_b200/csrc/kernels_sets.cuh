@@ -41,9 +41,15 @@ struct LevelInfo {
 };
 
 // ---- anchor (one thread) ---------------------------------------------------------------------
-__global__ void k_anchor(const float4* __restrict__ world, int N, float res_f, LevelInfo* info) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double res = (double)res_f;  // OctreePointCloud(const double resolution)
+struct LevelPlan {  // the resolution levels built in this pass (DmsaOptimizer.h:81-86: a factor <= FLT_MIN disables a level)
+    int n;
+    int level[2];
+    float res[2];
+};
+__global__ void k_anchor(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* infos) {
+    if (blockIdx.x != 0 || (int)threadIdx.x >= plan.n) return;
+    LevelInfo* info = infos + plan.level[threadIdx.x];
+    const double res = (double)plan.res[threadIdx.x];  // OctreePointCloud(const double resolution)
     const double minValue = 1.1920928955078125e-07;  // std::numeric_limits<float>::epsilon()
     int i = 0;
     while (i < N) {
@@ -88,8 +94,16 @@ __global__ void k_anchor(const float4* __restrict__ world, int N, float res_f, L
 // Per 256-point block it also records the key box (bbmin/bbmax) and the key box of "edge" points (ebmin/ebmax):
 // points closer to a voxel face than PCL's bounding-box fudge (float eps on the upper side) or than the rounding
 // noise of the lattice arithmetic; only those can make the exact double test of k_root disagree with the integer test.
-__global__ void k_keys(const float4* __restrict__ world, int N, LevelInfo* __restrict__ info, int* __restrict__ keys, int* __restrict__ bbmin,
-                       int* __restrict__ bbmax, int* __restrict__ ebmin, int* __restrict__ ebmax) {
+// grid = (blocks of 256 points, levels): both resolution levels in one launch.
+__global__ void k_keys(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* __restrict__ infos, int* __restrict__ keys_all,
+                       int* __restrict__ bb_all, int nb) {
+    const int lvl = plan.level[blockIdx.y];
+    LevelInfo* __restrict__ info = infos + lvl;
+    int* __restrict__ keys = keys_all + (size_t)3 * N * lvl;
+    int* __restrict__ bbmin = bb_all + (size_t)12 * nb * lvl;
+    int* __restrict__ bbmax = bbmin + 3 * nb;
+    int* __restrict__ ebmin = bbmin + 6 * nb;
+    int* __restrict__ ebmax = bbmin + 9 * nb;
     __shared__ int smin[3][DMSA_KEYS_BLOCK / 32], smax[3][DMSA_KEYS_BLOCK / 32];
     __shared__ int semin[3][DMSA_KEYS_BLOCK / 32], semax[3][DMSA_KEYS_BLOCK / 32];
     int ek[3] = {2147483647, 2147483647, 2147483647};
@@ -163,8 +177,14 @@ __global__ void k_keys(const float4* __restrict__ world, int N, LevelInfo* __res
 // ---- octree root growth replay (adoptBoundingBoxToPoint for every later point, in index order) -----------------
 // One block.  The box only grows, so violators are found in increasing index order; per-block key boxes skip
 // blocks that cannot contain a violator (conservative integer test), candidates are re-tested exactly in double.
-__global__ void k_root(const float4* __restrict__ world, int N, LevelInfo* __restrict__ info, const int* __restrict__ bbmin,
-                       const int* __restrict__ bbmax, const int* __restrict__ ebmin, const int* __restrict__ ebmax) {
+__global__ void k_root(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* __restrict__ infos, const int* __restrict__ bb_all,
+                       int nb_) {
+    const int lvl = plan.level[blockIdx.x];  // one block per level
+    LevelInfo* __restrict__ info = infos + lvl;
+    const int* __restrict__ bbmin = bb_all + (size_t)12 * nb_ * lvl;
+    const int* __restrict__ bbmax = bbmin + 3 * nb_;
+    const int* __restrict__ ebmin = bbmin + 6 * nb_;
+    const int* __restrict__ ebmax = bbmin + 9 * nb_;
     __shared__ double mn[3], mx[3];
     __shared__ long long lo[3];
     __shared__ int depth, found, cand;

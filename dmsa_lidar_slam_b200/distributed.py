@@ -175,7 +175,9 @@ class KeyframeBundleOptimizer:
         error0 = float(hg[-1])
         from .api import lm_solve
 
-        step, nan = lm_solve(s, hg, self.P)  # every rank solves the same system (deterministic: no broadcast needed)
+        # every rank solves the same system (deterministic: no broadcast needed); with a single bundle keep the reference's
+        # explicit inverse so that the result equals dmsa_b200_iteration bit for bit
+        step, nan = lm_solve(s, hg, self.P, explicit_inverse=(len(self.ranges) == 1))
         if nan:
             return dict(stop="nan", error0=error0, best_step=0, step_norm=0.0, num_sets=self.num_sets)
         self.ls.zero_()

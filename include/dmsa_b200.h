@@ -191,8 +191,11 @@ int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev);
 int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, double* ls_dev);
 
 /* Host-side LM step (DmsaOptimizer.h:107-128) on a host copy of the (all-reduced) [H | g | err0] buffer; no context needed.
+ * explicit_inverse = 1: the reference's arithmetic, (-alpha * H.inverse()) * g with an LU inverse (what dmsa_b200_iteration uses);
+ * explicit_inverse = 0: LU solve of one right-hand side (3x cheaper; used by the keyframe-bundle extension).
  * step: n_params doubles (clamped); *has_nan = 1 if the step contains NaN (the caller restores the parameters and stops). */
-int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step, int32_t* has_nan);
+int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, int32_t explicit_inverse, double* step,
+                       int32_t* has_nan);
 
 #ifdef __cplusplus
 }
