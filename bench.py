@@ -53,8 +53,11 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
+            t0 = time.time()  # nvidia-smi needs a moment to attach: wait for its first sample so the timed region is covered
+            while time.time() - t0 < 5.0 and os.path.getsize(self.f.name) == 0:
+                time.sleep(0.05)
         except Exception:
             self.p = None
 
@@ -305,6 +308,12 @@ def run_sliding(args):
         flop_alg = 25.0 * units_M * V
     avg_ms = dom_ms / max(dom_n, 1)
     ach = alg_bytes / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tf = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tf) and args.config == "cfg2":
+        tj = json.load(open(tf))
+        if dom in tj:
+            traffic, traffic_src = tj[dom], tj["_source"]
     breakdown = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items() if v[1]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -321,7 +330,8 @@ def run_sliding(args):
                 "what": "traj_init + register_scans + add_static_points (pinned host AoS PointStampId) + set poses + centralize + 1 iteration + pose read-back"},
         "gpu_launches": int(launches),
         "gpu_launches_note": "hand-written kernels only (CUB radix-sort/scan launches inside the set build are not counted)",
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "memberships_per_launch": units_M, "sets_per_launch": units_G,
                      "vectors_per_launch": V, "peak_source": peak_src,
                      "fp32": {"algorithmic_flop_per_launch": flop_alg, "achieved_tflops": flop_alg / (avg_ms * 1e-3) / 1e12,
