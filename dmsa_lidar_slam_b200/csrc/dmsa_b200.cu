@@ -873,7 +873,7 @@ int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
     const int P = 6 * (ctx->poses.n - 1), R = ctx->G + numExtra(ctx), Vld = ctx->curVld;
     const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
     const double inv_h = 1.0 / h;  // one_div_incr, DmsaOptimizer.h:210
-    int nsplit = std::max(1, std::min(64, (R + 511) / 512));
+    int nsplit = std::max(1, std::min(64, (R + 127) / 128));  // enough blocks to fill the chip: the product is only ~0.2 GFLOP
     int rps = ((R + nsplit - 1) / nsplit + JTJ_T - 1) / JTJ_T * JTJ_T;
     nsplit = (R + rps - 1) / rps;
     const int n1 = P + 1, nt = (n1 + JTJ_T - 1) / JTJ_T;

@@ -80,10 +80,33 @@ __device__ __forceinline__ double combine_subs(const CostArgs& a, const LaneMap&
     return tot;
 }
 
-// cooperative, coalesced staging of `count` member records into shared memory
-__device__ __forceinline__ void stage_records(float4* __restrict__ srec, const float4* __restrict__ rec, int count) {
-    for (int i = threadIdx.x; i < count; i += blockDim.x) srec[i] = __ldg(rec + i);
+// Staging of `count` member records (16 B each, contiguous in HBM) into shared memory with ONE bulk asynchronous copy
+// (TMA 1-D bulk copy: cp.async.bulk.shared::cluster.global + mbarrier complete_tx; SASS: UBLKCP / SYNCS): a single
+// elected thread issues the copy, every thread waits on the mbarrier's phase 0.  The barrier is used once per block.
+__device__ __forceinline__ void stage_records(float4* __restrict__ srec, const float4* __restrict__ rec, int count, unsigned long long* bar) {
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned dst_s = (unsigned)__cvta_generic_to_shared(srec);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned bytes = (unsigned)count * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(rec), "r"(bytes), "r"(bar_s)
+                     : "memory");
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DMSA_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+        "@p bra DMSA_DONE;\n"
+        "bra DMSA_WAIT;\n"
+        "DMSA_DONE:\n"
+        "}\n" ::"r"(bar_s)
+        : "memory");
 }
 
 // The transform of row t for this thread's vector; fetched only when the row changes between consecutive members
@@ -178,7 +201,8 @@ __device__ __forceinline__ double pass_quad(const CostArgs& a, const float4* __r
 // Also zero-fills the rows of sets owned by other ranks.
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
-    __shared__ float4 srec[COST_CHUNK];
+    __shared__ __align__(128) float4 srec[COST_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
     if ((int)blockIdx.x >= G) return;
     const int g = a.order[blockIdx.x];
     const int kind = a.cell_kind[g];
@@ -189,7 +213,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
         return;
     }
     const int n = a.cell_n[g];
-    stage_records(srec, a.rec + a.cell_start[g], n);
+    stage_records(srec, a.rec + a.cell_start[g], n, &bar);
     const int cnt = lm.active ? n : 0;
     double sx, sy, sz;
     pass_sum<PACKED>(a, srec, cnt, lm, sx, sy, sz);
@@ -206,12 +230,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
 // Big sets, pass 1: per-chunk coordinate sums (double)
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
-    __shared__ float4 srec[COST_CHUNK];
+    __shared__ __align__(128) float4 srec[COST_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
     const int c = blockIdx.x;
     if (c >= *a.n_chunks) return;
     const LaneMap lm = lane_map<PACKED>(a);
     const Chunk ch = a.chunks[c];
-    stage_records(srec, a.rec + ch.start, ch.count);
+    stage_records(srec, a.rec + ch.start, ch.count, &bar);
     double sx, sy, sz;
     pass_sum<PACKED>(a, srec, lm.active ? ch.count : 0, lm, sx, sy, sz);
     sx = combine_subs<PACKED>(a, lm, sx);
@@ -258,13 +283,14 @@ __global__ void k_cost_mean(CostArgs a, int G) {
 // Big sets, pass 2: per-chunk sums of the Mahalanobis terms
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
-    __shared__ float4 srec[COST_CHUNK];
+    __shared__ __align__(128) float4 srec[COST_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
     const int c = blockIdx.x;
     if (c >= *a.n_chunks) return;
     const LaneMap lm = lane_map<PACKED>(a);
     const Chunk ch = a.chunks[c];
     const int g = ch.cell;
-    stage_records(srec, a.rec + ch.start, ch.count);
+    stage_records(srec, a.rec + ch.start, ch.count, &bar);
     const float mx = a.mu[((size_t)g * 3 + 0) * a.Vld + lm.v];
     const float my = a.mu[((size_t)g * 3 + 1) * a.Vld + lm.v];
     const float mz = a.mu[((size_t)g * 3 + 2) * a.Vld + lm.v];
