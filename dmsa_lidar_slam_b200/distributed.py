@@ -50,16 +50,19 @@ def hg_scatter_index(idx, P):
 
 
 def relative2global(rel_o, rel_t):
-    """ConsecutivePoses.h:26-43 on 3 x n arrays (host, double)."""
+    """ConsecutivePoses.h:26-43 on 3 x n arrays (host, double); rotations converted in two batched scipy calls."""
     n = rel_o.shape[1]
-    go, gt = np.zeros_like(rel_o), np.zeros_like(rel_t)
+    E = Rot.from_rotvec(rel_o.T).as_matrix()  # exp of every relative orientation
+    Rg = np.empty((n, 3, 3))
+    gt = np.zeros_like(rel_t)
     R, T = np.eye(3), np.zeros(3)
     for k in range(n):
         T = T + R @ rel_t[:, k]
         gt[:, k] = T
-        R = R @ Rot.from_rotvec(rel_o[:, k]).as_matrix()
-        go[:, k] = Rot.from_matrix(R).as_rotvec()
-    return go, gt
+        R = R @ E[k]
+        Rg[k] = R
+    go = Rot.from_matrix(Rg).as_rotvec().T
+    return np.ascontiguousarray(go), gt
 
 
 def params_to_rel(p, rel_o0, rel_t0, n):
