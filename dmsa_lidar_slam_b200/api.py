@@ -109,6 +109,7 @@ def load_library():
         "dmsa_b200_cost_jacobian": (i32, [vp, vp, vp, P(f64), vp, vp]),
         "dmsa_b200_iteration": (i32, [vp, P(DmsaOptimSettings), P(i32), P(Report), vp, vp]),
         "dmsa_b200_optimize": (i32, [vp, P(DmsaOptimSettings), P(Report)]),
+        "dmsa_b200_set_mean_mode": (i32, [vp, i32]),
         "dmsa_b200_profile_enable": (i32, [vp, i32]),
         "dmsa_b200_profile_num": (i32, []),
         "dmsa_b200_profile_name": (C.c_char_p, [i32]),
@@ -135,7 +136,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_pose_parameters", "dmsa_b200_centralize", "dmsa_b200_decentralize", "dmsa_b200_update_global_points",
     "dmsa_b200_num_points", "dmsa_b200_get_global_points", "dmsa_b200_traj_get_dense_tforms", "dmsa_b200_build_sets", "dmsa_b200_get_sets",
     "dmsa_b200_get_voxel_keys", "dmsa_b200_eval_cost", "dmsa_b200_cost_jacobian", "dmsa_b200_iteration", "dmsa_b200_optimize",
-    "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
+    "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
 ]
 
@@ -306,6 +307,10 @@ class OptimizablePointSet:
         d.update(step=step, ls_cost=ls, stop_reason=stop.value, stop=STOP_REASONS[stop.value])
         self._G = rep.num_gaussians
         return d
+
+    def setMeanMode(self, mode):
+        """0: order-free exactly-rounded per-set mean (default, fast); 1: the reference's sequential float accumulation."""
+        self.ctx._ck(self.L.dmsa_b200_set_mean_mode(self.h, int(mode)))
 
     def profileEnable(self, on=True):
         self.ctx._ck(self.L.dmsa_b200_profile_enable(self.h, int(bool(on))))

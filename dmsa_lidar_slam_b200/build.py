@@ -7,7 +7,9 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "dmsa_b200.cu")
-DEPS = [os.path.join(_HERE, "csrc", f) for f in ("dmsa_b200.cu", "kernels_cost.cuh", "kernels_pose.cuh", "kernels_sets.cuh", "se3_math.cuh")] + [
+HOST_SRC = os.path.join(_HERE, "csrc", "host_solve.cpp")
+HOST_OBJ = os.path.join(_HERE, "lib", "host_solve.o")
+DEPS = [os.path.join(_HERE, "csrc", f) for f in ("host_solve.cpp", "dmsa_b200.cu", "kernels_cost.cuh", "kernels_pose.cuh", "kernels_sets.cuh", "se3_math.cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", "dmsa_b200.h")]
 OUT = os.path.join(_HERE, "lib", "libdmsa_b200.so")
 
@@ -36,7 +38,9 @@ def build_library(force=False, verbose=False):
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     if not force and not is_stale():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O3", "-mavx2", "-ffp-contract=off", "-fPIC", "-c", "-o", HOST_OBJ, HOST_SRC])
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, HOST_OBJ]
     env = dict(os.environ)
     # the image exports CC/CXX=/opt/gcc/bin/*; nvcc must use the distro host compiler
     if os.path.exists("/usr/bin/g++"):

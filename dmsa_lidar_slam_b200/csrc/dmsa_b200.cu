@@ -102,137 +102,16 @@ struct HostPoses {
     }
 };
 
-// Eigen dynamic inverse() == PartialPivLU: explicit inverse by LU with partial pivoting (DmsaOptimizer.h:113).
-// All n right-hand sides are substituted together, row by row (contiguous axpy loops the host compiler vectorises);
-// every element still sees exactly the operation sequence of a column-by-column substitution (j ascending).
-bool lu_solve_inverse(const std::vector<double>& A, int n, std::vector<double>& inv) {
-    std::vector<double> a(A);
-    std::vector<int> piv(n);
-    for (int i = 0; i < n; ++i) piv[i] = i;
-    for (int k = 0; k < n; ++k) {
-        int p = k;
-        double best = std::fabs(a[(size_t)k * n + k]);
-        for (int i = k + 1; i < n; ++i) {
-            double v = std::fabs(a[(size_t)i * n + k]);
-            if (v > best) {
-                best = v;
-                p = i;
-            }
-        }
-        if (p != k) {
-            for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)p * n + j]);
-            std::swap(piv[k], piv[p]);
-        }
-        const double d = a[(size_t)k * n + k];
-        const double* __restrict__ ak = &a[(size_t)k * n];
-        for (int i = k + 1; i < n; ++i) {
-            double* __restrict__ ai = &a[(size_t)i * n];
-            const double f = ai[k] / d;
-            ai[k] = f;
-            for (int j = k + 1; j < n; ++j) ai[j] -= f * ak[j];
-        }
-    }
-    inv.assign((size_t)n * n, 0.0);
-    for (int i = 0; i < n; ++i) inv[(size_t)i * n + piv[i]] = 1.0;  // P * I
-    // (measured: an OpenMP team costs more than it saves at P = 114; the blocks stay a plain loop)
-    const int nblk = 1;
-    for (int blk = 0; blk < nblk; ++blk) {
-        const int c0 = (int)((long long)n * blk / nblk), c1 = (int)((long long)n * (blk + 1) / nblk);
-        for (int i = 0; i < n; ++i) {  // forward substitution, unit lower triangle
-            double* __restrict__ xi = &inv[(size_t)i * n];
-            const double* ai = &a[(size_t)i * n];
-            for (int j = 0; j < i; ++j) {
-                const double l = ai[j];
-                const double* __restrict__ xj = &inv[(size_t)j * n];
-                for (int c = c0; c < c1; ++c) xi[c] -= l * xj[c];
-            }
-        }
-        for (int i = n - 1; i >= 0; --i) {  // back substitution
-            double* __restrict__ xi = &inv[(size_t)i * n];
-            const double* ai = &a[(size_t)i * n];
-            for (int j = i + 1; j < n; ++j) {
-                const double u = ai[j];
-                const double* __restrict__ xj = &inv[(size_t)j * n];
-                for (int c = c0; c < c1; ++c) xi[c] -= u * xj[c];
-            }
-            const double dinv = ai[i];
-            for (int c = c0; c < c1; ++c) xi[c] = xi[c] / dinv;
-        }
-    }
-    return true;
-}
-
-// LU with partial pivoting and ONE right-hand side (no explicit inverse): used by the keyframe-bundle extension, where no
-// reference arithmetic exists to mirror and the P x P system is large (P = 378: 3x less work than forming H^-1).
-bool lu_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) {
-    std::vector<double> a(A);
-    x.assign(b, b + n);
-    for (int k = 0; k < n; ++k) {
-        int p = k;
-        double best = std::fabs(a[(size_t)k * n + k]);
-        for (int i = k + 1; i < n; ++i) {
-            double v = std::fabs(a[(size_t)i * n + k]);
-            if (v > best) {
-                best = v;
-                p = i;
-            }
-        }
-        if (p != k) {
-            for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)p * n + j]);
-            std::swap(x[k], x[p]);
-        }
-        const double d = a[(size_t)k * n + k];
-        const double* __restrict__ ak = &a[(size_t)k * n];
-        for (int i = k + 1; i < n; ++i) {
-            double* __restrict__ ai = &a[(size_t)i * n];
-            const double f = ai[k] / d;
-            for (int j = k + 1; j < n; ++j) ai[j] -= f * ak[j];
-            x[i] -= f * x[k];
-        }
-    }
-    for (int i = n - 1; i >= 0; --i) {
-        double s = x[i];
-        const double* ai = &a[(size_t)i * n];
-        for (int j = i + 1; j < n; ++j) s -= ai[j] * x[j];
-        x[i] = s / ai[i];
-    }
-    return true;
-}
-
-// Cholesky (right-looking, row-major lower triangle) solve of the SPD system (J^T J + lambda I) x = b; false if a pivot
-// is not positive (then the caller falls back to LU).  Used by the keyframe-bundle extension only.
-bool chol_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) {
-    std::vector<double> a(A), col(n);
-    for (int k = 0; k < n; ++k) {
-        const double d = a[(size_t)k * n + k];
-        if (!(d > 0.0)) return false;
-        const double lkk = std::sqrt(d);
-        a[(size_t)k * n + k] = lkk;
-        for (int i = k + 1; i < n; ++i) {
-            a[(size_t)i * n + k] /= lkk;
-            col[i] = a[(size_t)i * n + k];
-        }
-        for (int i = k + 1; i < n; ++i) {
-            double* __restrict__ ai = &a[(size_t)i * n];
-            const double lik = col[i];
-            const double* __restrict__ c = col.data();
-            for (int j = k + 1; j <= i; ++j) ai[j] -= lik * c[j];
-        }
-    }
-    x.assign(b, b + n);
-    for (int i = 0; i < n; ++i) {  // L y = b
-        double s = x[i];
-        const double* ai = &a[(size_t)i * n];
-        for (int j = 0; j < i; ++j) s -= ai[j] * x[j];
-        x[i] = s / ai[i];
-    }
-    for (int i = n - 1; i >= 0; --i) {  // L^T x = y
-        double s = x[i];
-        for (int j = i + 1; j < n; ++j) s -= a[(size_t)j * n + i] * x[j];
-        x[i] = s / a[(size_t)i * n + i];
-    }
-    return true;
-}
+// dense P x P solvers of the LM step live in host_solve.cpp (plain C++, compiled by the host compiler with
+// per-ISA clones: AVX-512 / AVX2 / baseline — element-wise IEEE arithmetic, identical results on every path)
+}  // namespace
+bool dmsa_host_lu_inverse(const std::vector<double>& A, int n, std::vector<double>& inv);
+bool dmsa_host_lu_solve(const std::vector<double>& A, int n, const double* b, std::vector<double>& x);
+bool dmsa_host_chol_solve(const std::vector<double>& A, int n, const double* b, std::vector<double>& x);
+namespace {
+inline bool lu_solve_inverse(const std::vector<double>& A, int n, std::vector<double>& inv) { return dmsa_host_lu_inverse(A, n, inv); }
+inline bool lu_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) { return dmsa_host_lu_solve(A, n, b, x); }
+inline bool chol_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) { return dmsa_host_chol_solve(A, n, b, x); }
 
 inline int pad32(int v) { return (v + 31) / 32 * 32; }
 
@@ -248,6 +127,7 @@ struct dmsa_b200_ctx {
     int64_t launches = 0;
     int model = MODEL_NONE;
     int rank = 0, world = 1;
+    int meanMode = 0;  // 0: order-free exactly-rounded mean (default), 1: the reference's sequential float accumulation
 
     HostPoses poses;
     double origin[3] = {0, 0, 0};
@@ -304,7 +184,7 @@ struct dmsa_b200_ctx {
     int cellCap = 0;
 
     // cost
-    DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls;
+    DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart;
     DBuf<float> d_mu;
     size_t chunkBound = 0;
 
@@ -777,13 +657,14 @@ phase2:
     // phase 3: per-set statistics, weights, chunk list
     ProfScope prof_(ctx, PROF_SETS_STATS);
     LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G);
-    LAUNCH(k_gaussian_big, G, 256, 0, ctx->d_wrec.p, cs, G);
+    LAUNCH(k_gaussian_big, G, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, G);
     LAUNCH(k_weights, 1, 1024, 0, cs, G);
-    CK(ctx->d_okey.ensure((size_t)2 * cap));
-    CK(ctx->d_oval.ensure((size_t)2 * cap));
-    LAUNCH(k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, ctx->d_oval.p);
-    CK(cub::DeviceRadixSort::SortPairsDescending(ctx->d_cub.p, cubBytes, ctx->d_okey.p, ctx->d_okey.p + cap, ctx->d_oval.p, ctx->d_oval.p + cap, G, 0, 10,
-                                                 ctx->stream));
+    CK(ctx->d_okey.ensure((size_t)cap));
+    CK(ctx->d_oval.ensure((size_t)2 * cap + 4 * ORDER_CLASSES));
+    int* hist = ctx->d_oval.p;  // [ORDER_CLASSES histogram | ORDER_CLASSES cursors], then the order at + cellCap
+    CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
+    LAUNCH(k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
+    LAUNCH(k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
     CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), ctx->stream));
     CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, ctx->stream));
     ctx->chunkBound = (size_t)2 * N / CHUNK + (size_t)2 * N / FUSE_MAX + 2;  // big sets only
@@ -821,9 +702,16 @@ int runCost(dmsa_b200_ctx* ctx) {
     a.mu = ctx->d_mu.p;
     a.Q = ctx->d_Q.p;
     a.E = ctx->d_E.p;
-    a.order = ctx->d_oval.p + ctx->cellCap;
+    a.order = ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES;
     const unsigned grid = (unsigned)ctx->chunkBound;
     const int ph = ctx->phase ? 1 : 0;
+    if (ctx->meanMode == 1) {
+        ProfScope p_(ctx, PROF_FUSED_FD + ph);
+        LAUNCH(k_cost_seq, G, Vld, 0, a, G);
+        if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaGetLastError());
+        return 0;
+    }
     const bool packed = a.S > 1;
     const int cls = packed ? 0 : (Vld <= 128 ? 1 : (Vld <= 256 ? 2 : (Vld <= 512 ? 3 : 4)));
 #define DISPATCH(KERN, GRID, ...)                                                          \
@@ -901,7 +789,9 @@ int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) 
     ctx->phase = 0;
     if (rc) return rc;
     ProfScope prof_(ctx, PROF_COLSUM);
-    LAUNCH(k_col_sumsq, 9, 256, 0, ctx->d_E.p, ctx->G + numExtra(ctx), ctx->curVld, ls_dev);
+    CK(ctx->d_lspart.ensure(9 * COLSUM_PARTS));
+    LAUNCH(k_col_sumsq, dim3(9, COLSUM_PARTS), 256, 0, ctx->d_E.p, ctx->G + numExtra(ctx), ctx->curVld, ctx->d_lspart.p);
+    LAUNCH(k_col_sumsq_fin, 1, 32, 0, ctx->d_lspart.p, ls_dev);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1106,7 +996,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_mu);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_mu);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
@@ -1639,6 +1529,12 @@ int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, d
     rep.iterations = it;
     rep.stop_reason = stop;
     if (report) *report = rep;
+    return 0;
+}
+
+int dmsa_b200_set_mean_mode(dmsa_b200_ctx* ctx, int32_t mode) {
+    if (mode != 0 && mode != 1) ARGFAIL("set_mean_mode: 0 (order-free, default) or 1 (reference-sequential)");
+    ctx->meanMode = mode;
     return 0;
 }
 

@@ -227,6 +227,75 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
     if (lm.active && lm.sub == 0) a.E[(size_t)g * a.Vld + lm.v] = sqrt(fabs(q));  // :267
 }
 
+// Reference-order validation kernel: the per-set mean accumulated SEQUENTIALLY IN FLOAT in member order, exactly like
+// DmsaOptimizer.h:249-254 (`mean = mean + x_j`), for every set regardless of size (one block per set, members staged
+// in tiles).  Slow on the big sets of un-downsampled clouds (a dependent float-add chain as long as the set) and
+// therefore not the default; it exists to show that the only arithmetic difference between the fast path and the
+// reference's operation order is that one reduction (DESIGN.md §3 "mean").
+__global__ void __launch_bounds__(1024) k_cost_seq(CostArgs a, int G) {
+    __shared__ __align__(16) float4 srec[COST_CHUNK];
+    const int g = blockIdx.x;
+    if (g >= G) return;
+    const int kind = a.cell_kind[g];
+    const int v = min((int)threadIdx.x, a.V - 1);
+    const bool active = (int)threadIdx.x < a.V;
+    if (kind == 0) {
+        if (active) a.E[(size_t)g * a.Vld + v] = 0.0;
+        return;
+    }
+    const int n = a.cell_n[g];
+    const float4* __restrict__ rec = a.rec + a.cell_start[g];
+    const char* __restrict__ Mv = reinterpret_cast<const char*>(a.Mtab) + (size_t)v * 48u;
+    const unsigned rowbytes = (unsigned)a.Vld * 48u;
+    int tprev = -1;
+    float4 m0, m1, m2;
+    m0 = m1 = m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int base = 0; base < n; base += COST_CHUNK) {
+        const int cnt = min(COST_CHUNK, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) srec[i] = __ldg(rec + base + i);
+        __syncthreads();
+        for (int j = 0; j < cnt; ++j) {
+            const float4 r = srec[j];
+            const int t = __float_as_int(r.w);
+            DMSA_ROW_UPDATE(t)
+            float X, Y, Z;
+            xform(m0, m1, m2, r, X, Y, Z);
+            sx = fadd_(sx, X);  // :251 sequential float accumulation
+            sy = fadd_(sy, Y);
+            sz = fadd_(sz, Z);
+        }
+    }
+    const float nf = (float)n;
+    const float mx = fdiv_(sx, nf), my = fdiv_(sy, nf), mz = fdiv_(sz, nf);  // :254
+    const float* __restrict__ I = a.info + 9 * (size_t)g;
+    const float i0 = I[0], i1 = I[1], i2 = I[2], i3 = I[3], i4 = I[4], i5 = I[5], i6 = I[6], i7 = I[7], i8 = I[8];
+    const float wk = a.w[g];
+    double acc = 0.0;
+    for (int base = 0; base < n; base += COST_CHUNK) {
+        const int cnt = min(COST_CHUNK, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) srec[i] = __ldg(rec + base + i);
+        __syncthreads();
+        for (int j = 0; j < cnt; ++j) {
+            const float4 r = srec[j];
+            const int t = __float_as_int(r.w);
+            DMSA_ROW_UPDATE(t)
+            float X, Y, Z;
+            xform(m0, m1, m2, r, X, Y, Z);
+            const float d0 = fsub_(X, mx), d1 = fsub_(Y, my), d2 = fsub_(Z, mz);
+            const float t0 = fmul_(wk, d0), t1 = fmul_(wk, d1), t2 = fmul_(wk, d2);
+            const float r0 = fadd_(fmul_(t0, i0), fadd_(fmul_(t1, i3), fmul_(t2, i6)));
+            const float r1 = fadd_(fmul_(t0, i1), fadd_(fmul_(t1, i4), fmul_(t2, i7)));
+            const float r2 = fadd_(fmul_(t0, i2), fadd_(fmul_(t1, i5), fmul_(t2, i8)));
+            const float s_ = fadd_(fmul_(r0, d0), fadd_(fmul_(r1, d1), fmul_(r2, d2)));
+            acc += (double)s_;  // :263 errorVec(k) += float term, in member order
+        }
+    }
+    if (active) a.E[(size_t)g * a.Vld + v] = sqrt(fabs(acc));
+}
+
 // Big sets, pass 1: per-chunk coordinate sums (double)
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
@@ -321,22 +390,32 @@ __global__ void k_cost_fin(CostArgs a, int G) {
     }
 }
 
-// per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): one block per v, fixed reduction order
-__global__ void k_col_sumsq(const double* __restrict__ E, int R, int Vld, double* __restrict__ out) {
-    __shared__ double part[256];
-    const int v = blockIdx.x;
+// per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): COLSUM_PARTS row slices per vector, fixed reduction order
+#define COLSUM_PARTS 16
+__global__ void k_col_sumsq(const double* __restrict__ E, int R, int Vld, double* __restrict__ part /*[9][COLSUM_PARTS]*/) {
+    __shared__ double red[256];
+    const int v = blockIdx.x, y = blockIdx.y;
+    const int per = (R + COLSUM_PARTS - 1) / COLSUM_PARTS;
+    const int r0 = y * per, r1 = min(R, r0 + per);
     double s = 0.0;
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
         double e = E[(size_t)r * Vld + v];
         s += e * e;
     }
-    part[threadIdx.x] = s;
+    red[threadIdx.x] = s;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[v] = part[0];
+    if (threadIdx.x == 0) part[v * COLSUM_PARTS + y] = red[0];
+}
+__global__ void k_col_sumsq_fin(const double* __restrict__ part, double* __restrict__ out) {
+    const int v = threadIdx.x;
+    if (v >= 9) return;
+    double s = 0.0;
+    for (int y = 0; y < COLSUM_PARTS; ++y) s += part[v * COLSUM_PARTS + y];
+    out[v] = s;
 }
 
 // ---- [J e0]^T [J e0] : H = J^T J, g = J^T e0, err0 = e0^T e0 in one symmetric product ---------------------------

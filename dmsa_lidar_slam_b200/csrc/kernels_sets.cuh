@@ -734,9 +734,10 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G)
     for (int k = 0; k < 6; ++k) a[k] = warp_sum(a[k]);
     if (lane == 0) gaussian_finish(cs, g, n, a);
 }
-// One 256-thread block per accepted set with n > GAUSS_WARP_MAX members (grid = G, other blocks exit at once).
-__global__ void __launch_bounds__(256) k_gaussian_big(const float4* __restrict__ wrec, CellStore cs, int G) {
-    __shared__ double red[8][6];
+#define GAUSS_BIG_T 1024
+// One 1024-thread block per accepted set with n > GAUSS_WARP_MAX members (grid = G, other blocks exit at once).
+__global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __restrict__ wrec, CellStore cs, int G) {
+    __shared__ double red[GAUSS_BIG_T / 32][6];
     __shared__ float smean[3];
     const int g = blockIdx.x;
     if (g >= G) return;
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(256) k_gaussian_big(const float4* __restrict__
     if (n <= GAUSS_WARP_MAX) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double sx = 0, sy = 0, sz = 0;
-    for (int j = threadIdx.x; j < n; j += 256) {
+    for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
         float4 p = wrec[s + j];
         sx += (double)p.x;
         sy += (double)p.y;
@@ -761,13 +762,13 @@ __global__ void __launch_bounds__(256) k_gaussian_big(const float4* __restrict__
     __syncthreads();
     if (threadIdx.x < 3) {
         double t = 0;
-        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        for (int w = 0; w < GAUSS_BIG_T / 32; ++w) t += red[w][threadIdx.x];
         smean[threadIdx.x] = fdiv_((float)t, (float)n);
     }
     __syncthreads();
     const float mx = smean[0], my = smean[1], mz = smean[2];
     double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int j = threadIdx.x; j < n; j += 256) {
+    for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
         float4 p = wrec[s + j];
         double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
         a[0] += cx * cx;
@@ -787,7 +788,7 @@ __global__ void __launch_bounds__(256) k_gaussian_big(const float4* __restrict__
         double t[6];
         for (int k = 0; k < 6; ++k) {
             t[k] = 0;
-            for (int w = 0; w < 8; ++w) t[k] += red[w][k];
+            for (int w = 0; w < GAUSS_BIG_T / 32; ++w) t[k] += red[w][k];
         }
         gaussian_finish(cs, g, n, t);
     }
@@ -811,6 +812,7 @@ __global__ void k_weights(CellStore cs, int G) {
 // ---- work decomposition for the cost kernels ------------------------------------------------------------------------
 // Sets with at most FUSE_MAX members are evaluated by one block (fused kernel); larger sets are cut into chunks of CH
 // members so that no block runs long and the per-set reductions stay parallel.
+#define ORDER_CLASSES 32
 struct Chunk {
     int cell, start, count, first;  // first: index of the set's first chunk
 };
@@ -822,8 +824,28 @@ __global__ void k_cell_plan(CellStore cs, int G, int CH, int fuse_max, int rank,
     const int k = (g % world == rank) ? (n <= fuse_max ? 1 : 2) : 0;
     kind[g] = k;
     nchunk[g] = (k == 2) ? (n + CH - 1) / CH : 0;
-    okey[g] = (k == 1) ? n : 0;  // sort key of the fused kernel's longest-first order (n <= fuse_max < 1024: 10 bits)
-    oval[g] = g;
+    // size class of the fused kernel's longest-first issue order (class 0 = longest; other ranks' / big sets last)
+    const int cls = (k == 1) ? min(ORDER_CLASSES - 2, (fuse_max - n) * (ORDER_CLASSES - 1) / (fuse_max + 1)) : ORDER_CLASSES - 1;
+    okey[g] = cls;
+    atomicAdd(&oval[cls], 1);  // class histogram (oval[0..ORDER_CLASSES) must be zeroed before the launch)
+}
+// order[] = set indices grouped by size class, longest class first.  The position inside a class comes from an atomic
+// cursor: the order is a scheduling hint only and does not influence any result.
+__global__ void k_cell_order(int G, const int* __restrict__ okey, int* __restrict__ hist_cursor, int* __restrict__ order) {
+    __shared__ int base[ORDER_CLASSES];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 0; c < ORDER_CLASSES; ++c) {
+            base[c] = acc;
+            acc += hist_cursor[c];
+        }
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int c = okey[g];
+    const int pos = atomicAdd(&hist_cursor[ORDER_CLASSES + c], 1);
+    order[base[c] + pos] = g;
 }
 // chunk_off = exclusive scan of nchunk (G+1 entries, last = total)
 __global__ void k_chunk_fill(CellStore cs, int G, int CH, const int* __restrict__ nchunk, const int* __restrict__ chunk_off, Chunk* __restrict__ chunks) {

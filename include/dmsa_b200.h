@@ -176,6 +176,11 @@ int dmsa_b200_iteration(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, 
 /* the whole optimizeSet: centralize, loop, decentralize, final updateGlobalPoints   DmsaOptimizer.h:54-150 */
 int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, dmsa_b200_report* report);
 
+/* Per-set mean of the cost evaluation (DmsaOptimizer.h:249-254).  0 (default): order-free, exactly-rounded sum — what the
+ * fast kernels compute; 1: the reference's sequential float accumulation in member order (validation mode: one block per
+ * set, slow on sets with tens of thousands of members).  See DESIGN.md §3 "mean". */
+int dmsa_b200_set_mean_mode(dmsa_b200_ctx* ctx, int32_t mode);
+
 /* ---- per-kernel device timing (CUDA events on the context's stream; used by bench.py for the roofline) ---- */
 int dmsa_b200_profile_enable(dmsa_b200_ctx* ctx, int32_t on); /* also resets the accumulators */
 int32_t dmsa_b200_profile_num(void);

@@ -452,3 +452,24 @@ def test_keyframe_gauss_split_matches_oracle():
         d = kf.iteration(s)
         assert d["stop_reason"] == om.iteration(so) and d["best_step"] == om.last_trace()["best_k"]
     assert rel(kf.getPoseParameters(), om.get_params()) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])
+def test_reference_order_mean_mode_equals_faithful_oracle(name):
+    """With the per-set mean accumulated sequentially in float (dmsa_b200_set_mean_mode 1) the CUDA path runs the
+    reference's operation order end to end: e and J equal the FAITHFUL oracle to double-summation noise."""
+    win, traj, om, s, so = make_pair(name, mode=0)
+    traj.setMeanMode(1)
+    traj.centralize(); om.centralize()
+    traj.updateGlobalPoints(); om.update_global_points()
+    G, _ = traj.buildSets(s)
+    assert G == om.build_sets(so)
+    cj = traj.costJacobian(with_rows=True)
+    e0, J = om.jacobian()
+    assert rel(cj["e0"], e0) < 1e-12
+    assert rel(cj["J"], J) < 1e-9
+    assert rel(cj["H"], J.T @ J) < 1e-9 and rel(cj["g"], J.T @ e0) < 1e-9
+    d = traj.iteration(s)
+    assert d["stop_reason"] == om.iteration(so)
+    tr = om.last_trace()
+    assert d["best_step"] == tr["best_k"] and rel(d["ls_cost"], tr["ls_cost"]) < 1e-9
