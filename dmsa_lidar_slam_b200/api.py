@@ -464,7 +464,7 @@ def lm_solve(settings, hg, n_params, explicit_inverse=True):
     hg = _c64(hg)
     step = np.zeros(n_params)
     nan = C.c_int32()
-    rc = L.dmsa_b200_lm_solve(C.byref(settings), _p(hg), int(n_params), int(bool(explicit_inverse)), _p(step), C.byref(nan))
+    rc = L.dmsa_b200_lm_solve(C.byref(settings), _p(hg), int(n_params), int(explicit_inverse), _p(step), C.byref(nan))
     if rc != 0:
         raise DmsaError(f"dmsa_b200_lm_solve failed ({rc})")
     return step, bool(nan.value)

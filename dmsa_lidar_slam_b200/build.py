@@ -39,7 +39,7 @@ def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return OUT
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.check_call([cxx, "-std=c++17", "-O3", "-mavx2", "-ffp-contract=off", "-fPIC", "-c", "-o", HOST_OBJ, HOST_SRC])
+    subprocess.check_call([cxx, "-std=c++17", "-O3", "-mavx2", "-ffp-contract=off", "-fPIC", "-pthread", "-c", "-o", HOST_OBJ, HOST_SRC])
     cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, HOST_OBJ]
     env = dict(os.environ)
     # the image exports CC/CXX=/opt/gcc/bin/*; nvcc must use the distro host compiler

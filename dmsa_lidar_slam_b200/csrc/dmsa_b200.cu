@@ -106,6 +106,8 @@ struct HostPoses {
 // per-ISA clones: AVX-512 / AVX2 / baseline — element-wise IEEE arithmetic, identical results on every path)
 }  // namespace
 bool dmsa_host_lu_inverse(const std::vector<double>& A, int n, std::vector<double>& inv);
+void dmsa_host_solver_arm();
+void dmsa_host_solver_disarm();
 bool dmsa_host_lu_solve(const std::vector<double>& A, int n, const double* b, std::vector<double>& x);
 bool dmsa_host_chol_solve(const std::vector<double>& A, int n, const double* b, std::vector<double>& x);
 namespace {
@@ -895,7 +897,12 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     CKRC(jtjInto(ctx, ctx->d_hg.p));  // :107
     ctx->h_hg.resize((size_t)P * P + P + 1);
     CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    dmsa_host_solver_arm();  // the solve follows this read-back immediately: helper threads spin up while the host waits
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        dmsa_host_solver_disarm();
+        ctx->err = "cudaStreamSynchronize failed before the LM solve";
+        return DMSA_B200_ERR_CUDA;
+    }
     std::copy(pinHg(ctx), pinHg(ctx) + ctx->h_hg.size(), ctx->h_hg.begin());
     const double error0 = ctx->h_hg[(size_t)P * P + P];
     ctx->lastErr0 = error0;
@@ -905,6 +912,7 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
         WallTimer ws{ctx, PROF_HOST_SOLVE};
         nanStep = solveStep(st, ctx->h_hg.data(), P, step);
     }
+    dmsa_host_solver_disarm();
     if (nanStep) {  // :113-122
         // the last cost evaluation of calcNumericJacobian was p + h e_{P-1}: its global poses stay behind (see staleGlobal)
         std::vector<double> plast = paramVec;
@@ -1564,7 +1572,9 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
                        int32_t* has_nan) {
     if (!settings || !hg || !step || n_params <= 0) return DMSA_B200_ERR_ARG;
     std::vector<double> st;
+    if (explicit_inverse == 2) dmsa_host_solver_arm();  // same arithmetic, substitution columns spread over the helper threads
     int nan = solveStep(settings, hg, n_params, st, explicit_inverse != 0);
+    if (explicit_inverse == 2) dmsa_host_solver_disarm();
     std::copy(st.begin(), st.end(), step);
     if (has_nan) *has_nan = nan;
     return 0;

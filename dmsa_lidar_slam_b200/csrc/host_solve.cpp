@@ -2,8 +2,13 @@
 // Compiled by the host C++ compiler (not nvcc) so that GCC function multi-versioning can emit AVX-512 / AVX2 / baseline
 // clones of the same loops; all arithmetic is element-wise IEEE double without FMA contraction (-ffp-contract=off),
 // so every clone produces bit-identical results.
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstddef>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -16,9 +21,7 @@
 // Eigen dynamic inverse() == PartialPivLU: explicit inverse by LU with partial pivoting (DmsaOptimizer.h:113).
 // All n right-hand sides are substituted together, row by row (contiguous axpy loops the host compiler vectorises);
 // every element still sees exactly the operation sequence of a column-by-column substitution (j ascending).
-DMSA_CLONES bool lu_solve_inverse_impl(const std::vector<double>& A, int n, std::vector<double>& inv) {
-    std::vector<double> a(A);
-    std::vector<int> piv(n);
+DMSA_CLONES static void lu_factor_impl(std::vector<double>& a, std::vector<int>& piv, int n) {
     for (int i = 0; i < n; ++i) piv[i] = i;
     for (int k = 0; k < n; ++k) {
         int p = k;
@@ -43,38 +46,124 @@ DMSA_CLONES bool lu_solve_inverse_impl(const std::vector<double>& A, int n, std:
             for (int j = k + 1; j < n; ++j) ai[j] -= f * ak[j];
         }
     }
+}
+// forward + back substitution of the right-hand-side columns [c0, c1) (independent of every other column)
+DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n, int c0, int c1) {
+    for (int i = 0; i < n; ++i) {  // forward substitution, unit lower triangle
+        double* __restrict__ xi = &inv[(size_t)i * n];
+        const double* ai = &a[(size_t)i * n];
+        for (int j = 0; j < i; ++j) {
+            const double l = ai[j];
+            const double* __restrict__ xj = &inv[(size_t)j * n];
+            for (int c = c0; c < c1; ++c) xi[c] -= l * xj[c];
+        }
+    }
+    for (int i = n - 1; i >= 0; --i) {  // back substitution
+        double* __restrict__ xi = &inv[(size_t)i * n];
+        const double* ai = &a[(size_t)i * n];
+        for (int j = i + 1; j < n; ++j) {
+            const double u = ai[j];
+            const double* __restrict__ xj = &inv[(size_t)j * n];
+            for (int c = c0; c < c1; ++c) xi[c] -= u * xj[c];
+        }
+        const double dinv = ai[i];
+        for (int c = c0; c < c1; ++c) xi[c] = xi[c] / dinv;
+    }
+}
+
+// A few helper threads for the substitution of the n independent right-hand sides.  The optimizer loop knows when the
+// solve is about to happen (right after the read-back of [H | g]), so it ARMS the pool before it blocks on the stream:
+// armed workers spin on the job counter and start without a wake-up latency; disarmed workers sleep on a condition
+// variable.  Each column is still computed by exactly one thread with the serial operation order: results are identical.
+namespace {
+struct SolvePool {
+    static constexpr int kWorkers = 3;
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::atomic<int> armed{0};
+    std::atomic<unsigned long long> gen{0};
+    std::atomic<int> remaining{0};
+    std::atomic_flag busy = ATOMIC_FLAG_INIT;  // one solve at a time uses the helpers; a concurrent one runs serially
+    const double* a = nullptr;
+    double* inv = nullptr;
+    int n = 0;
+    bool stop = false;
+    bool disabled = false;
+    void start() {
+        if (!th.empty() || disabled) return;
+        const char* e = std::getenv("DMSA_B200_SOLVER_THREADS");  // "0" keeps the solve on the calling thread
+        if (e && std::atoi(e) <= 0) {
+            disabled = true;
+            return;
+        }
+        for (int w = 0; w < kWorkers; ++w) th.emplace_back([this, w] { worker(w); });
+    }
+    void worker(int w) {
+        unsigned long long seen = 0;  // generations start at 0; a job published before this thread first runs must not be missed
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return stop || armed.load() > 0; });
+                if (stop) return;
+            }
+            while (armed.load(std::memory_order_acquire) > 0) {
+                const unsigned long long g = gen.load(std::memory_order_acquire);
+                if (g != seen) {
+                    seen = g;
+                    const int nb = kWorkers + 1, blk = w + 1;
+                    lu_subst_block_impl(a, inv, n, (int)((long long)n * blk / nb), (int)((long long)n * (blk + 1) / nb));
+                    remaining.fetch_sub(1, std::memory_order_acq_rel);
+                } else {
+                    __builtin_ia32_pause();
+                }
+            }
+        }
+    }
+    ~SolvePool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+            armed.store(0);
+        }
+        cv.notify_all();
+        for (auto& t : th) t.join();
+    }
+};
+SolvePool g_pool;
+}  // namespace
+
+void dmsa_host_solver_arm() {
+    g_pool.start();
+    {
+        std::lock_guard<std::mutex> lk(g_pool.m);
+        g_pool.armed.store(1, std::memory_order_release);
+    }
+    g_pool.cv.notify_all();
+}
+void dmsa_host_solver_disarm() { g_pool.armed.store(0, std::memory_order_release); }
+
+static bool lu_solve_inverse_impl(const std::vector<double>& A, int n, std::vector<double>& inv) {
+    std::vector<double> a(A);
+    std::vector<int> piv(n);
+    lu_factor_impl(a, piv, n);
     inv.assign((size_t)n * n, 0.0);
     for (int i = 0; i < n; ++i) inv[(size_t)i * n + piv[i]] = 1.0;  // P * I
-    // (measured: an OpenMP team costs more than it saves at P = 114; the blocks stay a plain loop)
-    const int nblk = 1;
-    for (int blk = 0; blk < nblk; ++blk) {
-        const int c0 = (int)((long long)n * blk / nblk), c1 = (int)((long long)n * (blk + 1) / nblk);
-        for (int i = 0; i < n; ++i) {  // forward substitution, unit lower triangle
-            double* __restrict__ xi = &inv[(size_t)i * n];
-            const double* ai = &a[(size_t)i * n];
-            for (int j = 0; j < i; ++j) {
-                const double l = ai[j];
-                const double* __restrict__ xj = &inv[(size_t)j * n];
-                for (int c = c0; c < c1; ++c) xi[c] -= l * xj[c];
-            }
-        }
-        for (int i = n - 1; i >= 0; --i) {  // back substitution
-            double* __restrict__ xi = &inv[(size_t)i * n];
-            const double* ai = &a[(size_t)i * n];
-            for (int j = i + 1; j < n; ++j) {
-                const double u = ai[j];
-                const double* __restrict__ xj = &inv[(size_t)j * n];
-                for (int c = c0; c < c1; ++c) xi[c] -= u * xj[c];
-            }
-            const double dinv = ai[i];
-            for (int c = c0; c < c1; ++c) xi[c] = xi[c] / dinv;
-        }
+    if (n >= 64 && g_pool.armed.load(std::memory_order_acquire) > 0 && !g_pool.th.empty() && !g_pool.busy.test_and_set(std::memory_order_acquire)) {
+        g_pool.a = a.data();
+        g_pool.inv = inv.data();
+        g_pool.n = n;
+        g_pool.remaining.store(SolvePool::kWorkers, std::memory_order_release);
+        g_pool.gen.fetch_add(1, std::memory_order_acq_rel);
+        lu_subst_block_impl(a.data(), inv.data(), n, 0, (int)((long long)n / (SolvePool::kWorkers + 1)));
+        while (g_pool.remaining.load(std::memory_order_acquire) > 0) __builtin_ia32_pause();
+        g_pool.busy.clear(std::memory_order_release);
+    } else {
+        lu_subst_block_impl(a.data(), inv.data(), n, 0, n);
     }
     return true;
 }
 
-// LU with partial pivoting and ONE right-hand side (no explicit inverse): used by the keyframe-bundle extension, where no
-// reference arithmetic exists to mirror and the P x P system is large (P = 378: 3x less work than forming H^-1).
 DMSA_CLONES bool lu_solve_vec_impl(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) {
     std::vector<double> a(A);
     x.assign(b, b + n);

@@ -197,7 +197,9 @@ int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, doub
 
 /* Host-side LM step (DmsaOptimizer.h:107-128) on a host copy of the (all-reduced) [H | g | err0] buffer; no context needed.
  * explicit_inverse = 1: the reference's arithmetic, (-alpha * H.inverse()) * g with an LU inverse (what dmsa_b200_iteration uses);
- * explicit_inverse = 0: LU solve of one right-hand side (3x cheaper; used by the keyframe-bundle extension).
+ * explicit_inverse = 2: the same arithmetic with the inverse's columns spread over a few helper threads (bit-identical; what
+ *                      dmsa_b200_iteration does while it waits for the read-back);
+ * explicit_inverse = 0: Cholesky (LU fallback) solve of one right-hand side (used by the keyframe-bundle extension).
  * step: n_params doubles (clamped); *has_nan = 1 if the step contains NaN (the caller restores the parameters and stops). */
 int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, int32_t explicit_inverse, double* step,
                        int32_t* has_nan);

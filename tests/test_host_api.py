@@ -101,3 +101,31 @@ def test_window_timing_matches_reference_formulas():
     assert t["param_indices"][0] == 0 and t["param_indices"][-1] == 1001
     ids = ob.tform_ids(np.array([0.0, 0.00049, 0.0005, 0.9999, 5.0]), 0.0, t["traj_time"])
     assert list(ids) == [0, 1, 1, 1000, 1001]
+
+
+def test_lm_solve_variants():
+    """Host LM step (DmsaOptimizer.h:107-128): the helper-thread variant is bit-identical to the serial explicit inverse; the
+    Cholesky variant agrees to conditioning; clamp and NaN guard behave like the reference."""
+    from dmsa_lidar_slam_b200.api import lm_solve
+
+    rng = np.random.default_rng(5)
+    for n in (18, 114, 234):
+        J = rng.normal(size=(3 * n, n))
+        H = J.T @ J
+        g = rng.normal(size=n)
+        hg = np.concatenate([H.ravel(), g, [1.0]])
+        s = api.DmsaOptimSettings(step_length_optim=0.2, max_step=1e9)
+        a, nan_a = lm_solve(s, hg, n, 1)
+        for _ in range(3):
+            b, nan_b = lm_solve(s, hg, n, 2)
+            assert (a == b).all() and not nan_a and not nan_b
+        c, _ = lm_solve(s, hg, n, 0)
+        ref = -0.2 * np.linalg.solve(H + np.eye(n) * float(np.float32(1e-5)), g)
+        np.testing.assert_allclose(a, ref, rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(c, ref, rtol=1e-8, atol=1e-12)
+        s2 = api.DmsaOptimSettings(step_length_optim=0.2, max_step=1e-6)  # infinity-norm clamp, DmsaOptimizer.h:125-128
+        d, _ = lm_solve(s2, hg, n, 1)
+        assert abs(np.abs(d).max() - 1e-6) < 1e-18 and np.allclose(d / np.abs(d).max(), a / np.abs(a).max())
+    hg[3] = np.nan
+    _, nan = lm_solve(api.DmsaOptimSettings(), hg, n, 1)
+    assert nan
