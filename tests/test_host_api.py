@@ -108,6 +108,7 @@ def test_lm_solve_variants():
     Cholesky variant agrees to conditioning; clamp and NaN guard behave like the reference."""
     from dmsa_lidar_slam_b200.api import lm_solve
 
+    os.environ["DMSA_B200_SOLVER_THREADS"] = "1"  # exercise the helper-thread path (off by default)
     rng = np.random.default_rng(5)
     for n in (18, 114, 234):
         J = rng.normal(size=(3 * n, n))
