@@ -129,6 +129,7 @@ struct dmsa_b200_ctx {
     int64_t launches = 0;
     int model = MODEL_NONE;
     int rank = 0, world = 1;
+    bool worldValid = false;  // globalPoints on the device correspond to the staged points (set by the base transform)
     int meanMode = 0;  // 0: order-free exactly-rounded mean (default), 1: the reference's sequential float accumulation
 
     HostPoses poses;
@@ -162,7 +163,7 @@ struct dmsa_b200_ctx {
     DBuf<int> d_tid, d_ring, d_flag;
 
     // pose batches
-    DBuf<double> d_p, d_step, d_batch, d_globO, d_globT, d_quat, d_relO, d_extra;
+    DBuf<double> d_p, d_step, d_batch, d_globO, d_globT, d_quat, d_extra;
     DBuf<float> d_Mtab;
     int curV = 0, curVld = 0;
 
@@ -380,7 +381,6 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
     pb.globO_t = ctx->d_globO.p;
     pb.globT_t = ctx->d_globT.p;
     pb.quat_t = ctx->d_quat.p;
-    pb.relO_t = nullptr;
     pb.extra = E > 0 ? ctx->d_extra.p : nullptr;
     TrajTiming tt;
     tt.n_total = ctx->n_total;
@@ -473,6 +473,7 @@ int transformBase(dmsa_b200_ctx* ctx) {
     LAUNCH(k_transform_points, cdiv(ctx->n_scan, 256), 256, 0, ctx->d_local.p, ctx->d_tid.p, (int)ctx->n_scan, reinterpret_cast<const float4*>(ctx->d_Mtab.p),
            ctx->curVld, 0, ctx->d_world.p, kfm ? ctx->d_normal_l.p : nullptr, kfm ? ctx->d_normal_w.p : nullptr);
     CK(cudaGetLastError());
+    ctx->worldValid = true;
     return 0;
 }
 
@@ -494,6 +495,8 @@ int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
 int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     const int64_t N64 = numPoints(ctx);
     if (N64 <= 0 || N64 > 0x3fffffff) ARGFAIL("build_sets: no points staged (or more than 2^30)");
+    if (!ctx->worldValid) ARGFAIL("build_sets: call update_global_points first (the sets are built on globalPoints)");
+    ctx->G = 0;
     // splitSet is specialised for PointCloud<PointNormal> only (Gaussians.h:19-28): the trajectory model never splits
     const bool split = st->gauss_split && ctx->model == MODEL_KF;
     const int N = (int)N64;
@@ -1000,7 +1003,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
 #define REL(b) ctx->b.release()
     REL(d_stamps); REL(d_trajTime); REL(d_urel); REL(d_fh); REL(d_seg); REL(d_hit); REL(d_paramIdx); REL(d_imu); REL(d_kfD); REL(d_plausible);
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
-    REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_relO); REL(d_extra); REL(d_Mtab);
+    REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_Mtab);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
@@ -1130,6 +1133,8 @@ int dmsa_b200_traj_register_scans(dmsa_b200_ctx* ctx, int32_t n_scans, const dms
         off += sizes[s];
     }
     ctx->n_scan = total;
+    ctx->worldValid = false;
+    ctx->G = 0;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1177,6 +1182,8 @@ int dmsa_b200_traj_add_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_s
     LAUNCH(k_unpack_psi, cdiv(n, 256), 256, 0, ctx->d_stage.p, (int)n, (int)(ctx->n_scan + ctx->n_static), ctx->d_trajTime.p, ctx->n_total, ctx->t0, 1,
            ctx->d_local.p, ctx->d_world.p, ctx->d_ring.p, ctx->d_tid.p, ctx->d_flag.p);
     ctx->n_static += n;
+    ctx->worldValid = false;
+    ctx->G = 0;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1190,6 +1197,7 @@ int dmsa_b200_traj_add_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_s
 
 int dmsa_b200_traj_remove_static_points(dmsa_b200_ctx* ctx) {
     ctx->n_static = 0;  // :174-187
+    ctx->G = 0;         // sets built with the static points are stale
     return 0;
 }
 
@@ -1287,6 +1295,8 @@ int dmsa_b200_kf_commit(dmsa_b200_ctx* ctx) {
     }
     ctx->n_scan = total;
     ctx->n_static = 0;
+    ctx->worldValid = false;
+    ctx->G = 0;
     int flag = 0;
     CK(cudaMemcpy(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaGetLastError());

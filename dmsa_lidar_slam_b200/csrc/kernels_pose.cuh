@@ -27,7 +27,6 @@ struct PoseBatch {
     double* globO_t;       // [(k*3+a)*Vld + v]
     double* globT_t;       // [(k*3+a)*Vld + v]
     double* quat_t;        // [(k*4+c)*Vld + v]
-    double* relO_t;        // [(k*3+a)*Vld + v]  relative orientations after global2relative (IMU / odometry rows)
     double* extra;         // [E][Vld] additional residual rows (may be null)
 };
 

@@ -135,7 +135,7 @@ class KeyframeBundleOptimizer:
             self.idx.append(idx)
             pos, _ = hg_scatter_index(idx, self.P)
             self.scatter.append(torch.from_numpy(pos).to(self.dev))
-        self.hg = torch.zeros(self.P * self.P + self.P + 1, dtype=torch.float64, device=self.dev)
+        self.hg = torch.zeros(self.P * self.P + self.P + 2, dtype=torch.float64, device=self.dev)  # [H | g | err0 | number of sets]
         self.ls = torch.zeros(9, dtype=torch.float64, device=self.dev)
         Pb = max([len(i) for i in self.idx] + [1])
         self.tmp = torch.zeros(Pb * Pb + Pb + 1, dtype=torch.float64, device=self.dev)
@@ -168,19 +168,36 @@ class KeyframeBundleOptimizer:
             n = len(idx) * len(idx) + len(idx) + 1
             c.costJacobianDev(self.tmp.data_ptr())
             self.hg.index_add_(0, pos, self.tmp[:n])
-        cnt = torch.tensor([float(G)], dtype=torch.float64, device=self.dev)
-        self.ex.all_reduce_sum(self.hg)  # exchange 1: P*P + P + 1 doubles
-        self.ex.all_reduce_sum(cnt)
-        self.num_sets = int(cnt.item())
-        if self.num_sets < s.min_num_gaussians:
-            return dict(stop="few_gaussians", error0=0.0, best_step=0, step_norm=0.0, num_sets=self.num_sets)
-        hg = self.hg.cpu().numpy()
-        error0 = float(hg[-1])
-        from .api import lm_solve
+        self.hg[-1] = float(G)
+        self.ex.all_reduce_sum(self.hg)  # exchange 1: P*P + P + 2 doubles ([H | g | err0 | set count])
+        P = self.P
+        if len(self.ranges) == 1:
+            # a single bundle is the reference's iteration: keep its arithmetic (host LU inverse), bit-equal to dmsa_b200_iteration
+            hg = self.hg.cpu().numpy()
+            error0, self.num_sets = float(hg[-2]), int(hg[-1])
+            from .api import lm_solve
 
-        # every rank solves the same system (deterministic: no broadcast needed); with a single bundle keep the reference's
-        # explicit inverse so that the result equals dmsa_b200_iteration bit for bit
-        step, nan = lm_solve(s, hg, self.P, explicit_inverse=(len(self.ranges) == 1))
+            step, nan = lm_solve(s, hg, P, explicit_inverse=1)
+        else:
+            # bundle extension (no reference arithmetic to mirror): solve the SPD system where it already lives — on the
+            # device, with the library Cholesky behind torch.linalg (cuSOLVER; a plain library factorisation) — and bring back
+            # only the step.  Every rank solves redundantly; identical inputs give identical steps (no broadcast needed).
+            H = self.hg[:P * P].view(P, P).clone()
+            H.diagonal().add_(float(np.float32(s.lambda_diag)))
+            L, info = torch.linalg.cholesky_ex(H)
+            x = torch.cholesky_solve(self.hg[P * P:P * P + P].unsqueeze(1), L).squeeze(1)
+            st_dev = (-s.step_length_optim) * x
+            m = st_dev.abs().max()
+            st_dev = torch.where(m > s.max_step, st_dev * (s.max_step / m), st_dev)  # infinity-norm clamp, DmsaOptimizer.h:125-128
+            out = torch.cat([st_dev, self.hg[-2:], info.to(torch.float64).view(1)]).cpu().numpy()
+            step, error0, self.num_sets = out[:P].copy(), float(out[P]), int(out[P + 1])
+            nan = bool(np.isnan(step).any()) or out[P + 2] != 0
+            if out[P + 2] != 0:  # not numerically SPD: fall back to the host LU solve
+                from .api import lm_solve
+
+                step, nan = lm_solve(s, self.hg.cpu().numpy(), P, explicit_inverse=0)
+        if self.num_sets < s.min_num_gaussians:  # DmsaOptimizer.h:89-93
+            return dict(stop="few_gaussians", error0=0.0, best_step=0, step_norm=0.0, num_sets=self.num_sets)
         if nan:
             return dict(stop="nan", error0=error0, best_step=0, step_norm=0.0, num_sets=self.num_sets)
         self.ls.zero_()
@@ -259,7 +276,7 @@ def bench_keyframe(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 point arithmetic / f64 pose chain, sums, J^T J", "data": "synthetic",
             "config": {"workload": f"cfg4: keyframe-graph DMSA iteration, {n_kf} keyframes x {n_pts} pts, {len(opt.ranges)} overlapping bundles (15 keyframes, overlap 8) "
-                                   f"round-robin over {world} rank(s), NCCL all-reduce of [J^T J | J^T r | e^T e] ({opt.P * opt.P + opt.P + 1} doubles) + 9 line-search costs per iteration",
+                                   f"round-robin over {world} rank(s), NCCL all-reduce of [J^T J | J^T r | e^T e | #sets] ({opt.P * opt.P + opt.P + 2} doubles) + 9 line-search costs per iteration",
                        "P": opt.P, "sets": last["num_sets"], "settings": st, "l2": "working set (>= 8 x 1.5M points x 64 B) exceeds L2"},
             "gpu_launches": int(launches), "last_step": {k: (v if not isinstance(v, np.ndarray) else v.tolist()) for k, v in last.items()},
         }

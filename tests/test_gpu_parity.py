@@ -473,3 +473,22 @@ def test_reference_order_mean_mode_equals_faithful_oracle(name):
     assert d["stop_reason"] == om.iteration(so)
     tr = om.last_trace()
     assert d["best_step"] == tr["best_k"] and rel(d["ls_cost"], tr["ls_cost"]) < 1e-9
+
+
+def test_call_order_is_checked():
+    """The C-ABI refuses out-of-order use instead of computing on stale device state."""
+    from dmsa_lidar_slam_b200 import DmsaError
+
+    win = synth.make_config("tiny")
+    traj = ContinuousTrajectory.from_window(win)
+    s = DmsaOptimSettings(min_num_points_per_set=6, min_num_gaussians=10)
+    with pytest.raises(DmsaError, match="update_global_points"):
+        traj.buildSets(s)
+    traj.updateGlobalPoints()
+    traj.buildSets(s)
+    traj.removeStaticPoints()  # the sets referenced the static points
+    traj._G = 1
+    with pytest.raises(DmsaError, match="build_sets"):
+        traj.evalCost(traj.getPoseParameters()[None, :])
+    with pytest.raises(DmsaError):
+        ContinuousTrajectory().initTraj(0.0, 1.0, 2)  # barycentric_rational of order 2 needs >= 3 poses
