@@ -220,13 +220,14 @@ __global__ void k_root(const float4* __restrict__ world, int N, LevelPlan plan, 
             }
             if (c) atomicMin(&cand, bi);
             __syncthreads();
-            const int cv = cand;
+            const int cv = *reinterpret_cast<volatile int*>(&cand);
             __syncthreads();
             if (cv < nb) break;
         }
         __syncthreads();
-        if (cand >= nb) break;
-        b = cand;
+        const int cnd = *reinterpret_cast<volatile int*>(&cand);
+        if (cnd >= nb) break;
+        b = cnd;
         // 2. exact test of the candidate block's points, repeatedly (each growth step may leave later violators)
         while (true) {
             if (threadIdx.x == 0) found = 2147483647;
@@ -245,9 +246,12 @@ __global__ void k_root(const float4* __restrict__ world, int N, LevelPlan plan, 
                 }
             }
             __syncthreads();
-            if (found == 2147483647) break;
+            // (volatile: keeps the compiler from fetching the neighbouring `depth` word in the same wide shared load, which
+            //  thread 0 rewrites below before the next barrier)
+            const int fnd = *reinterpret_cast<volatile int*>(&found);
+            if (fnd == 2147483647) break;
             if (threadIdx.x == 0) {
-                float4 p = world[found];
+                float4 p = world[fnd];
                 double c[3] = {(double)p.x, (double)p.y, (double)p.z};
                 while (true) {
                     bool up[3], any = false;
