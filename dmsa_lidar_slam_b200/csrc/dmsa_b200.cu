@@ -125,6 +125,9 @@ struct dmsa_b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // second stream: the two resolution levels of a set build run side by side (fork / join with events)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evLevel0 = nullptr;
     std::string err;
     int64_t launches = 0;
     int model = MODEL_NONE;
@@ -185,10 +188,11 @@ struct dmsa_b200_ctx {
     bool levelOn[2] = {false, false};
     int cachedDepth[2] = {0, 0};
     int cellCap = 0;
+    size_t cubPer = 0;  // bytes of CUB temporary storage per resolution level
 
     // cost
     DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart;
-    DBuf<float> d_mu;
+    DBuf<int> d_done;  // per-set completion counters of k_cost_quad (zeroed by the set build, self-resetting)
     size_t chunkBound = 0;
 
     // host mirrors; the small per-iteration read-backs / uploads go through one pinned block so that
@@ -277,6 +281,11 @@ static void profCollect(dmsa_b200_ctx* ctx) {  // call after a stream synchroniz
     do {                                                           \
         kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__); \
         ctx->launches++;                                           \
+    } while (0)
+#define LAUNCH_ON(strm, kern, grid, block, smem, ...)          \
+    do {                                                       \
+        kern<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__); \
+        ctx->launches++;                                       \
     } while (0)
 #define ARGFAIL(msg)               \
     do {                           \
@@ -487,7 +496,9 @@ int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
     need = std::max(need, b);
     cub::DeviceRadixSort::SortPairsDescending(nullptr, b, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, cells, 0, 10);
     need = std::max(need, b);
-    CK(ctx->d_cub.ensure(need + 256));
+    // one temporary area per resolution level: the two levels' sorts / scans run concurrently on two streams
+    ctx->cubPer = (need + 511) / 256 * 256;
+    CK(ctx->d_cub.ensure(2 * ctx->cubPer));
     return 0;
 }
 
@@ -508,26 +519,28 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     CK(ctx->d_linfo.ensure(2));
     CK(ctx->d_keys.ensure((size_t)6 * N));
     CK(ctx->d_bb.ensure((size_t)2 * 12 * nb));
-    CK(ctx->d_code.ensure(N));
-    CK(ctx->d_scode.ensure(N));
-    CK(ctx->d_idx.ensure(N));
+    // per-level scratch (x2: level 0 on the context's stream, level 1 on stream2, side by side)
+    const size_t N2 = (size_t)N + 2;
+    CK(ctx->d_code.ensure((size_t)2 * N));
+    CK(ctx->d_scode.ensure((size_t)2 * N));
+    CK(ctx->d_idx.ensure((size_t)2 * N));
     CK(ctx->d_sidx.ensure((size_t)2 * N));
-    CK(ctx->d_flagA.ensure(N));
-    CK(ctx->d_scanA.ensure(N));
-    CK(ctx->d_raw_start.ensure((size_t)N + 2));
-    CK(ctx->d_raw_diff.ensure((size_t)N + 2));
-    CK(ctx->d_acc_flag.ensure((size_t)N + 2));
-    CK(ctx->d_acc_scan.ensure((size_t)N + 2));
-    CK(ctx->d_out_cnt.ensure((size_t)N + 2));
-    CK(ctx->d_sub.ensure((size_t)6 * ((size_t)N + 2)));
+    CK(ctx->d_flagA.ensure((size_t)2 * N));
+    CK(ctx->d_scanA.ensure((size_t)2 * N));
+    CK(ctx->d_raw_start.ensure(2 * N2));
+    CK(ctx->d_raw_diff.ensure(2 * N2));
+    CK(ctx->d_acc_flag.ensure(2 * N2));
+    CK(ctx->d_acc_scan.ensure(2 * N2));
+    CK(ctx->d_out_cnt.ensure(2 * N2));
+    CK(ctx->d_sub.ensure(2 * 6 * N2));
     const size_t tileBound = (size_t)N / 256 + (size_t)N / std::max(1, minPts) + 2;
     if (split) {
-        CK(ctx->d_ntile.ensure((size_t)N + 2));
-        CK(ctx->d_tile_off.ensure((size_t)N + 2));
-        CK(ctx->d_tiles.ensure(tileBound));
-        CK(ctx->d_best_v.ensure(tileBound));
-        CK(ctx->d_best_ij.ensure(2 * tileBound));
-        CK(ctx->d_scratch.ensure(N));
+        CK(ctx->d_ntile.ensure(2 * N2));
+        CK(ctx->d_tile_off.ensure(2 * N2));
+        CK(ctx->d_tiles.ensure(2 * tileBound));
+        CK(ctx->d_best_v.ensure(2 * tileBound));
+        CK(ctx->d_best_ij.ensure(4 * tileBound));
+        CK(ctx->d_scratch.ensure((size_t)2 * N));
     }
     CK(ctx->d_rec.ensure((size_t)2 * N));
     CK(ctx->d_wrec.ensure((size_t)2 * N));
@@ -542,6 +555,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     CK(ctx->d_cell_w.ensure(cap));
     CK(ctx->d_nchunk.ensure((size_t)cap + 1));
     CK(ctx->d_chunk_off.ensure((size_t)cap + 1));
+    CK(ctx->d_done.ensure((size_t)cap + 1));
     CKRC(ensureCub(ctx, N, cap));
     CellStore cs;
     cs.start = ctx->d_cell_start.p;
@@ -576,7 +590,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     // The radix sort needs the number of key bits (3 * octree depth + 1) on the host.  The depth of the previous build of
     // this context is a safe guess (more bits than needed are harmless); it is verified after phase 2 and the phase is
     // redone in the rare case the tree grew.  Without a guess: one synchronisation here.
-    size_t cubBytes = ctx->d_cub.cap;
+    size_t cubBytes = ctx->cubPer;
     int prev = -1;
     int depthUsed[2] = {ctx->cachedDepth[0], ctx->cachedDepth[1]};
     bool haveGuess = true;
@@ -593,44 +607,72 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
         }
     }
 phase2:
-    // phase 2: sort, segment, accept, gather
+    // phase 2: sort, segment, accept, gather.  The two levels are independent up to the set numbering (level 1's sets
+    // follow level 0's): level 0 runs on the context's stream, level 1 on stream2; level 1's emission waits for level 0's.
     prev = -1;
     {
     ProfScope prof_(ctx, PROF_SETS_SORT);
+    const bool fork = ctx->levelOn[0] && ctx->levelOn[1];
+    if (fork) {
+        CK(cudaEventRecord(ctx->evFork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+    }
     for (int l = 0; l < 2; ++l) {
         if (!ctx->levelOn[l]) continue;
+        cudaStream_t strm = (fork && l == 1) ? ctx->stream2 : ctx->stream;
         LevelInfo* li = ctx->d_linfo.p + l;
         int* keys = ctx->d_keys.p + (size_t)3 * N * l;
         int* sidx = ctx->d_sidx.p + (size_t)N * l;
-        LAUNCH(k_morton, cdiv(N, 256), 256, 0, keys, N, li, ctx->d_code.p, ctx->d_idx.p);
+        unsigned long long* code = ctx->d_code.p + (size_t)N * l;
+        unsigned long long* scode = ctx->d_scode.p + (size_t)N * l;
+        int* idx = ctx->d_idx.p + (size_t)N * l;
+        int* flagA = ctx->d_flagA.p + (size_t)N * l;
+        int* scanA = ctx->d_scanA.p + (size_t)N * l;
+        int* raw_start = ctx->d_raw_start.p + N2 * l;
+        int* raw_diff = ctx->d_raw_diff.p + N2 * l;
+        int* acc_flag = ctx->d_acc_flag.p + N2 * l;
+        int* acc_scan = ctx->d_acc_scan.p + N2 * l;
+        int* out_cnt = ctx->d_out_cnt.p + N2 * l;
+        unsigned char* cubTmp = ctx->d_cub.p + ctx->cubPer * l;
+        LAUNCH_ON(strm, k_morton, cdiv(N, 256), 256, 0, keys, N, li, code, idx);
         const int end_bit = std::min(64, 3 * depthUsed[l] + 1);
-        CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, cubBytes, ctx->d_code.p, ctx->d_scode.p, ctx->d_idx.p, sidx, N, 0, end_bit, ctx->stream));
-        LAUNCH(k_heads, cdiv(N, 256), 256, 0, ctx->d_scode.p, N, li, ctx->d_flagA.p);
-        CK(cub::DeviceScan::InclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_flagA.p, ctx->d_scanA.p, N, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_raw_diff.p, 0, ((size_t)N + 2) * sizeof(int), ctx->stream));
-        LAUNCH(k_raw_starts, cdiv(N, 256), 256, 0, ctx->d_scode.p, ctx->d_flagA.p, ctx->d_scanA.p, N, li, ctx->d_raw_start.p);
-        LAUNCH(k_ring_diff, cdiv(N, 256), 256, 0, sidx, ctx->d_scanA.p, ctx->d_raw_start.p, ctx->d_ring.p, li, ctx->d_raw_diff.p);
-        int* sub_start = ctx->d_sub.p;
-        int* sub_n = sub_start + 2 * ((size_t)N + 2);
-        int* sub_code = sub_n + 2 * ((size_t)N + 2);
-        LAUNCH(k_accept, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_raw_diff.p, li, minPts, ctx->d_acc_flag.p, ctx->d_out_cnt.p, sub_start, sub_n,
-               sub_code);
+        CK(cub::DeviceRadixSort::SortPairs(cubTmp, cubBytes, code, scode, idx, sidx, N, 0, end_bit, strm));
+        LAUNCH_ON(strm, k_heads, cdiv(N, 256), 256, 0, scode, N, li, flagA);
+        CK(cub::DeviceScan::InclusiveSum(cubTmp, cubBytes, flagA, scanA, N, strm));
+        CK(cudaMemsetAsync(raw_diff, 0, N2 * sizeof(int), strm));
+        LAUNCH_ON(strm, k_raw_starts, cdiv(N, 256), 256, 0, scode, flagA, scanA, N, li, raw_start);
+        LAUNCH_ON(strm, k_ring_diff, cdiv(N, 256), 256, 0, sidx, scanA, raw_start, ctx->d_ring.p, li, raw_diff);
+        int* sub_start = ctx->d_sub.p + 6 * N2 * l;
+        int* sub_n = sub_start + 2 * N2;
+        int* sub_code = sub_n + 2 * N2;
+        LAUNCH_ON(strm, k_accept, cdiv(N, 256), 256, 0, raw_start, raw_diff, li, minPts, acc_flag, out_cnt, sub_start, sub_n, sub_code);
         if (split) {  // Gaussians.h:27-85 on every accepted leaf
-            LAUNCH(k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, ctx->d_raw_start.p, ctx->d_acc_flag.p, li, ctx->d_ntile.p);
-            CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_ntile.p, ctx->d_tile_off.p, N + 1, ctx->stream));
-            LAUNCH(k_split_tile_fill, cdiv(N, 256), 256, 0, ctx->d_ntile.p, ctx->d_tile_off.p, li, ctx->d_tiles.p);
-            LAUNCH(k_split_pairs, (unsigned)tileBound, 256, 0, ctx->d_tiles.p, ctx->d_tile_off.p, li, ctx->d_raw_start.p, sidx, ctx->d_normal_w.p,
-                   ctx->d_best_v.p, ctx->d_best_ij.p, ctx->d_best_ij.p + tileBound);
-            LAUNCH(k_split_decide, 148 * 8, 256, 0, ctx->d_acc_flag.p, ctx->d_ntile.p, ctx->d_tile_off.p, li, ctx->d_raw_start.p, sidx, ctx->d_scratch.p,
-                   ctx->d_normal_w.p, ctx->d_ring.p, ctx->d_best_v.p, ctx->d_best_ij.p, ctx->d_best_ij.p + tileBound, minPts, ctx->d_out_cnt.p, sub_start, sub_n,
-                   sub_code);
+            int* ntile = ctx->d_ntile.p + N2 * l;
+            int* tile_off = ctx->d_tile_off.p + N2 * l;
+            SplitTile* tiles = ctx->d_tiles.p + tileBound * l;
+            float* best_v = ctx->d_best_v.p + tileBound * l;
+            int* best_i = ctx->d_best_ij.p + 2 * tileBound * l;
+            int* best_j = best_i + tileBound;
+            int* scratch = ctx->d_scratch.p + (size_t)N * l;
+            LAUNCH_ON(strm, k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, raw_start, acc_flag, li, ntile);
+            CK(cub::DeviceScan::ExclusiveSum(cubTmp, cubBytes, ntile, tile_off, N + 1, strm));
+            LAUNCH_ON(strm, k_split_tile_fill, cdiv(N, 256), 256, 0, ntile, tile_off, li, tiles);
+            LAUNCH_ON(strm, k_split_pairs, (unsigned)tileBound, 256, 0, tiles, tile_off, li, raw_start, sidx, ctx->d_normal_w.p, best_v, best_i, best_j);
+            LAUNCH_ON(strm, k_split_decide, 148 * 8, 256, 0, acc_flag, ntile, tile_off, li, raw_start, sidx, scratch, ctx->d_normal_w.p, ctx->d_ring.p, best_v,
+                      best_i, best_j, minPts, out_cnt, sub_start, sub_n, sub_code);
         }
-        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_out_cnt.p, ctx->d_acc_scan.p, N, ctx->stream));
-        LAUNCH(k_emit_cells, cdiv(N, 256), 256, 0, ctx->d_raw_start.p, ctx->d_out_cnt.p, ctx->d_acc_scan.p, sub_start, sub_n, sub_code, sidx, keys, li,
-               prev >= 0 ? ctx->d_linfo.p + prev : nullptr, l, l * N, cs, cap);
-        LAUNCH(k_gather, cdiv(N, 256), 256, 0, sidx, li, ctx->d_local.p, ctx->d_tid.p, numTableRows(ctx), ctx->d_world.p, ctx->d_rec.p + (size_t)N * l,
-               ctx->d_wrec.p + (size_t)N * l);
+        CK(cub::DeviceScan::ExclusiveSum(cubTmp, cubBytes, out_cnt, acc_scan, N, strm));
+        if (fork && l == 1) CK(cudaStreamWaitEvent(strm, ctx->evLevel0, 0));  // gbase of level 1 = sets emitted by level 0
+        LAUNCH_ON(strm, k_emit_cells, cdiv(N, 256), 256, 0, raw_start, out_cnt, acc_scan, sub_start, sub_n, sub_code, sidx, keys, li,
+                  prev >= 0 ? ctx->d_linfo.p + prev : nullptr, l, l * N, cs, cap);
+        if (fork && l == 0) CK(cudaEventRecord(ctx->evLevel0, strm));
+        LAUNCH_ON(strm, k_gather, cdiv(N, 256), 256, 0, sidx, li, ctx->d_local.p, ctx->d_tid.p, numTableRows(ctx), ctx->d_world.p,
+                  ctx->d_rec.p + (size_t)N * l, ctx->d_wrec.p + (size_t)N * l);
         prev = l;
+    }
+    if (fork) {
+        CK(cudaEventRecord(ctx->evJoin, ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
     }
     }
     CKRC(ensurePinned(ctx, Ppin));
@@ -662,12 +704,13 @@ phase2:
     // phase 3: per-set statistics, weights, chunk list
     ProfScope prof_(ctx, PROF_SETS_STATS);
     LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G);
-    LAUNCH(k_gaussian_big, G, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, G);
+    LAUNCH(k_gaussian_big, std::min(G, 148 * 2), GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, G);
     LAUNCH(k_weights, 1, 1024, 0, cs, G);
     CK(ctx->d_okey.ensure((size_t)cap));
     CK(ctx->d_oval.ensure((size_t)2 * cap + 4 * ORDER_CLASSES));
     int* hist = ctx->d_oval.p;  // [ORDER_CLASSES histogram | ORDER_CLASSES cursors], then the order at + cellCap
     CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_done.p, 0, ((size_t)G + 1) * sizeof(int), ctx->stream));
     LAUNCH(k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
     LAUNCH(k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
     CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), ctx->stream));
@@ -685,7 +728,6 @@ int runCost(dmsa_b200_ctx* ctx) {
     if (Vld > 1024) ARGFAIL("more than 1023 pose parameters are not supported by the cost kernels");
     CK(ctx->d_S.ensure(ctx->chunkBound * 3 * Vld));
     CK(ctx->d_Q.ensure(ctx->chunkBound * Vld));
-    CK(ctx->d_mu.ensure((size_t)G * 3 * Vld));
     CK(ctx->d_E.ensure((size_t)(G + E) * Vld));
     CostArgs a;
     a.chunks = ctx->d_chunks.p;
@@ -704,7 +746,7 @@ int runCost(dmsa_b200_ctx* ctx) {
     a.nchunk = ctx->d_nchunk.p;
     a.chunk_off = ctx->d_chunk_off.p;
     a.S_part = ctx->d_S.p;
-    a.mu = ctx->d_mu.p;
+    a.done = ctx->d_done.p;
     a.Q = ctx->d_Q.p;
     a.E = ctx->d_E.p;
     a.order = ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES;
@@ -736,16 +778,8 @@ int runCost(dmsa_b200_ctx* ctx) {
         DISPATCH(k_cost_sum, grid, a);
     }
     {
-        ProfScope p_(ctx, PROF_MEAN_FD + ph);
-        LAUNCH(k_cost_mean, G, dim3(32, COST_RED_Y), 0, a, G);
-    }
-    {
-        ProfScope p_(ctx, PROF_QUAD_FD + ph);
+        ProfScope p_(ctx, PROF_QUAD_FD + ph);  // includes the per-set mean and the final chunk reduction (last block of a set)
         DISPATCH(k_cost_quad, grid, a);
-    }
-    {
-        ProfScope p_(ctx, PROF_FIN_FD + ph);
-        LAUNCH(k_cost_fin, G, dim3(32, COST_RED_Y), 0, a, G);
     }
 #undef DISPATCH
     if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -987,7 +1021,10 @@ int dmsa_b200_create(dmsa_b200_ctx** out, int device, void* cuda_stream) {
         }
         ctx->own_stream = true;
     }
-    if (ctx->d_flag.ensure(4) != cudaSuccess) {
+    if (ctx->d_flag.ensure(4) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->evLevel0, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return DMSA_B200_ERR_CUDA;
     }
@@ -1000,6 +1037,12 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) {
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamDestroy(ctx->stream2);
+    }
+    for (cudaEvent_t e : {ctx->evFork, ctx->evJoin, ctx->evLevel0})
+        if (e) cudaEventDestroy(e);
 #define REL(b) ctx->b.release()
     REL(d_stamps); REL(d_trajTime); REL(d_urel); REL(d_fh); REL(d_seg); REL(d_hit); REL(d_paramIdx); REL(d_imu); REL(d_kfD); REL(d_plausible);
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
@@ -1007,7 +1050,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_mu);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);

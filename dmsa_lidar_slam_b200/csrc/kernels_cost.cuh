@@ -37,7 +37,7 @@ struct CostArgs {
     const int* nchunk;       // [g]
     const int* chunk_off;    // [g]
     double* S_part;          // partial sums   [(c*3 + a) * Vld + v]
-    float* mu;               // means          [(g*3 + a) * Vld + v]
+    int* done;               // [g] chunk blocks of set g that finished pass 2 (self-resetting counter)
     double* Q;               // partial quadratic forms [c * Vld + v]
     double* E;               // residuals      [g * Vld + v]
 };
@@ -319,75 +319,53 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
 }
 
 #define COST_RED_Y 8
-// Big sets: mean = float(sum over the set's chunks) / float(n).  blockDim = (32, COST_RED_Y): lane = vector, the
-// COST_RED_Y rows take interleaved chunks and are combined in fixed order.                         DmsaOptimizer.h:254
-__global__ void k_cost_mean(CostArgs a, int G) {
-    __shared__ double red[COST_RED_Y][3][33];
-    const int g = blockIdx.x;
-    if (g >= G || a.cell_kind[g] != 2) return;
-    const int nc = a.nchunk[g], o = a.chunk_off[g];
-    const float nf = (float)a.cell_n[g];
-    for (int v0 = 0; v0 < a.V; v0 += 32) {
-        const int v = v0 + threadIdx.x;
-        double sx = 0.0, sy = 0.0, sz = 0.0;
-        if (v < a.V)
-            for (int c = threadIdx.y; c < nc; c += COST_RED_Y) {
-                sx += a.S_part[((size_t)(o + c) * 3 + 0) * a.Vld + v];
-                sy += a.S_part[((size_t)(o + c) * 3 + 1) * a.Vld + v];
-                sz += a.S_part[((size_t)(o + c) * 3 + 2) * a.Vld + v];
-            }
-        red[threadIdx.y][0][threadIdx.x] = sx;
-        red[threadIdx.y][1][threadIdx.x] = sy;
-        red[threadIdx.y][2][threadIdx.x] = sz;
-        __syncthreads();
-        if (threadIdx.y < 3 && v < a.V) {
-            double t = 0.0;
-            for (int y = 0; y < COST_RED_Y; ++y) t += red[y][threadIdx.y][threadIdx.x];
-            a.mu[((size_t)g * 3 + threadIdx.y) * a.Vld + v] = fdiv_((float)t, nf);
-        }
-        __syncthreads();
+// Fixed-order reduction of a big set's chunk partials, identical for every reader: COST_RED_Y interleaved partial sums
+// (chunk c goes to slot c % COST_RED_Y, ascending c), then the slots in ascending order.  Every block of the set
+// recomputes it from the same partials, so all of them see bit-identical means.
+__device__ __forceinline__ double reduce_chunks(const double* __restrict__ part, int nc, size_t stride) {
+    double t = 0.0;
+#pragma unroll 1
+    for (int y = 0; y < COST_RED_Y; ++y) {
+        double s = 0.0;
+        for (int c = y; c < nc; c += COST_RED_Y) s += __ldcg(part + (size_t)c * stride);
+        t += s;
     }
+    return t;
 }
 
-// Big sets, pass 2: per-chunk sums of the Mahalanobis terms
+// Big sets, pass 2: mean = float(sum over the set's chunks) / float(n) (DmsaOptimizer.h:254, recomputed by every chunk
+// block from the chunk partials of pass 1), per-chunk sums of the Mahalanobis terms, and - in the block that finishes
+// last for its set (fence + per-set counter) - e = sqrt(|sum of the chunk partials|) in fixed chunk order (:267).
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ int s_last;
     const int c = blockIdx.x;
     if (c >= *a.n_chunks) return;
     const LaneMap lm = lane_map<PACKED>(a);
     const Chunk ch = a.chunks[c];
     const int g = ch.cell;
     stage_records(srec, a.rec + ch.start, ch.count, &bar);
-    const float mx = a.mu[((size_t)g * 3 + 0) * a.Vld + lm.v];
-    const float my = a.mu[((size_t)g * 3 + 1) * a.Vld + lm.v];
-    const float mz = a.mu[((size_t)g * 3 + 2) * a.Vld + lm.v];
+    const int nc = a.nchunk[g], o = ch.first;
+    const float nf = (float)a.cell_n[g];
+    const size_t st3 = (size_t)3 * a.Vld;
+    const double* __restrict__ Sp = a.S_part + (size_t)o * st3 + lm.v;
+    const float mx = fdiv_((float)reduce_chunks(Sp, nc, st3), nf);
+    const float my = fdiv_((float)reduce_chunks(Sp + a.Vld, nc, st3), nf);
+    const float mz = fdiv_((float)reduce_chunks(Sp + 2 * (size_t)a.Vld, nc, st3), nf);
     double acc = pass_quad<PACKED>(a, srec, lm.active ? ch.count : 0, lm, g, mx, my, mz);
     acc = combine_subs<PACKED>(a, lm, acc);
-    if (lm.active && lm.sub == 0) a.Q[(size_t)c * a.Vld + lm.v] = acc;
-}
-
-// Big sets: e = sqrt(|sum of chunk partials|), same thread layout as k_cost_mean                   DmsaOptimizer.h:267
-__global__ void k_cost_fin(CostArgs a, int G) {
-    __shared__ double red[COST_RED_Y][33];
-    const int g = blockIdx.x;
-    if (g >= G || a.cell_kind[g] != 2) return;
-    const int nc = a.nchunk[g], o = a.chunk_off[g];
-    for (int v0 = 0; v0 < a.V; v0 += 32) {
-        const int v = v0 + threadIdx.x;
-        double q = 0.0;
-        if (v < a.V)
-            for (int c = threadIdx.y; c < nc; c += COST_RED_Y) q += a.Q[(size_t)(o + c) * a.Vld + v];
-        red[threadIdx.y][threadIdx.x] = q;
-        __syncthreads();
-        if (threadIdx.y == 0 && v < a.V) {
-            double t = 0.0;
-            for (int y = 0; y < COST_RED_Y; ++y) t += red[y][threadIdx.x];
-            a.E[(size_t)g * a.Vld + v] = sqrt(fabs(t));
-        }
-        __syncthreads();
-    }
+    const bool writer = lm.active && lm.sub == 0;
+    if (writer) a.Q[(size_t)c * a.Vld + lm.v] = acc;
+    __threadfence();  // the partials of this block are visible device-wide before the counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(a.done + g, 1) == nc - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (writer) a.E[(size_t)g * a.Vld + lm.v] = sqrt(fabs(reduce_chunks(a.Q + (size_t)o * a.Vld + lm.v, nc, (size_t)a.Vld)));
+    if (threadIdx.x == 0) a.done[g] = 0;  // ready for the next launch
 }
 
 // per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): COLSUM_PARTS row slices per vector, fixed reduction order

@@ -739,62 +739,64 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G)
     if (lane == 0) gaussian_finish(cs, g, n, a);
 }
 #define GAUSS_BIG_T 1024
-// One 1024-thread block per accepted set with n > GAUSS_WARP_MAX members (grid = G, other blocks exit at once).
+// Accepted sets with n > GAUSS_WARP_MAX members: one 1024-thread block per set, a persistent grid strides over the set
+// list (the big sets are few; a grid of G mostly-empty 1024-thread blocks costs more than the work itself).
 __global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __restrict__ wrec, CellStore cs, int G) {
     __shared__ double red[GAUSS_BIG_T / 32][6];
     __shared__ float smean[3];
-    const int g = blockIdx.x;
-    if (g >= G) return;
-    const int s = cs.start[g], n = cs.n[g];
-    if (n <= GAUSS_WARP_MAX) return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double sx = 0, sy = 0, sz = 0;
-    for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
-        float4 p = wrec[s + j];
-        sx += (double)p.x;
-        sy += (double)p.y;
-        sz += (double)p.z;
-    }
-    sx = warp_sum(sx);
-    sy = warp_sum(sy);
-    sz = warp_sum(sz);
-    if (lane == 0) {
-        red[wid][0] = sx;
-        red[wid][1] = sy;
-        red[wid][2] = sz;
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        double t = 0;
-        for (int w = 0; w < GAUSS_BIG_T / 32; ++w) t += red[w][threadIdx.x];
-        smean[threadIdx.x] = fdiv_((float)t, (float)n);
-    }
-    __syncthreads();
-    const float mx = smean[0], my = smean[1], mz = smean[2];
-    double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
-        float4 p = wrec[s + j];
-        double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
-        a[0] += cx * cx;
-        a[1] += cx * cy;
-        a[2] += cx * cz;
-        a[3] += cy * cy;
-        a[4] += cy * cz;
-        a[5] += cz * cz;
-    }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a[k] = warp_sum(a[k]);
-    __syncthreads();
-    if (lane == 0)
-        for (int k = 0; k < 6; ++k) red[wid][k] = a[k];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t[6];
-        for (int k = 0; k < 6; ++k) {
-            t[k] = 0;
-            for (int w = 0; w < GAUSS_BIG_T / 32; ++w) t[k] += red[w][k];
+    for (int g = blockIdx.x; g < G; g += gridDim.x) {  // block-uniform
+        const int s = cs.start[g], n = cs.n[g];
+        if (n <= GAUSS_WARP_MAX) continue;
+        __syncthreads();  // shared scratch of the previous set is free
+        double sx = 0, sy = 0, sz = 0;
+        for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
+            float4 p = wrec[s + j];
+            sx += (double)p.x;
+            sy += (double)p.y;
+            sz += (double)p.z;
         }
-        gaussian_finish(cs, g, n, t);
+        sx = warp_sum(sx);
+        sy = warp_sum(sy);
+        sz = warp_sum(sz);
+        if (lane == 0) {
+            red[wid][0] = sx;
+            red[wid][1] = sy;
+            red[wid][2] = sz;
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double t = 0;
+            for (int w = 0; w < GAUSS_BIG_T / 32; ++w) t += red[w][threadIdx.x];
+            smean[threadIdx.x] = fdiv_((float)t, (float)n);
+        }
+        __syncthreads();
+        const float mx = smean[0], my = smean[1], mz = smean[2];
+        double a[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
+            float4 p = wrec[s + j];
+            double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
+            a[0] += cx * cx;
+            a[1] += cx * cy;
+            a[2] += cx * cz;
+            a[3] += cy * cy;
+            a[4] += cy * cz;
+            a[5] += cz * cz;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a[k] = warp_sum(a[k]);
+        __syncthreads();
+        if (lane == 0)
+            for (int k = 0; k < 6; ++k) red[wid][k] = a[k];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t[6];
+            for (int k = 0; k < 6; ++k) {
+                t[k] = 0;
+                for (int w = 0; w < GAUSS_BIG_T / 32; ++w) t[k] += red[w][k];
+            }
+            gaussian_finish(cs, g, n, t);
+        }
     }
 }
 
