@@ -118,6 +118,8 @@ def load_library():
         "dmsa_b200_cost_jacobian_dev": (i32, [vp, vp]),
         "dmsa_b200_line_search_costs_dev": (i32, [vp, vp, vp]),
         "dmsa_b200_lm_solve": (i32, [P(DmsaOptimSettings), vp, i32, i32, vp, P(i32)]),
+        "dmsa_b200_set_lm_solver": (i32, [vp, i32]),
+        "dmsa_b200_lm_solve_device": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -138,6 +140,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_get_voxel_keys", "dmsa_b200_eval_cost", "dmsa_b200_cost_jacobian", "dmsa_b200_iteration", "dmsa_b200_optimize",
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
+    "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device",
 ]
 
 
@@ -311,6 +314,18 @@ class OptimizablePointSet:
     def setMeanMode(self, mode):
         """0: order-free exactly-rounded per-set mean (default, fast); 1: the reference's sequential float accumulation."""
         self.ctx._ck(self.L.dmsa_b200_set_mean_mode(self.h, int(mode)))
+
+    def setLmSolver(self, mode):
+        """0: LM step on the device (default; no host round trip inside an iteration); 1: host solver (bit-identical)."""
+        self.ctx._ck(self.L.dmsa_b200_set_lm_solver(self.h, int(mode)))
+
+    def lmSolveDevice(self, settings, hg, n_params):
+        """Device twin of api.lm_solve(.., explicit_inverse=1): (step, has_nan) for a host [H | g | err0] buffer."""
+        hg = np.ascontiguousarray(hg, dtype=np.float64)
+        step = np.zeros(int(n_params))
+        nan = C.c_int32(0)
+        self.ctx._ck(self.L.dmsa_b200_lm_solve_device(self.h, C.byref(settings), _p(hg), int(n_params), _p(step), C.byref(nan)))
+        return step, int(nan.value)
 
     def profileEnable(self, on=True):
         self.ctx._ck(self.L.dmsa_b200_profile_enable(self.h, int(bool(on))))

@@ -18,6 +18,7 @@
 
 #include "../../include/dmsa_b200.h"
 #include "kernels_cost.cuh"
+#include "kernels_solve.cuh"
 #include "kernels_pose.cuh"
 #include "kernels_sets.cuh"
 #include "se3_math.cuh"
@@ -133,6 +134,7 @@ struct dmsa_b200_ctx {
     int model = MODEL_NONE;
     int rank = 0, world = 1;
     bool worldValid = false;  // globalPoints on the device correspond to the staged points (set by the base transform)
+    int solverMode = 1;  // 1 (default): LM step solved on the host (host_solve.cpp), 0: on the device (kernels_solve.cuh); bit-identical
     int meanMode = 0;  // 0: order-free exactly-rounded mean (default), 1: the reference's sequential float accumulation
 
     HostPoses poses;
@@ -191,7 +193,10 @@ struct dmsa_b200_ctx {
     size_t cubPer = 0;  // bytes of CUB temporary storage per resolution level
 
     // cost
-    DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart;
+    DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart, d_solve, d_iter;
+    bool solveAttr = false;
+    bool solveGeneral = false;  // force the general one-block kernel (any P <= 1024) instead of the P <= 128 fast path
+    long long* solveClk = nullptr;  // debug: device buffer of phase cycle stamps (dmsa_b200_lm_solve_device with DMSA_B200_SOLVE_CLK=1)
     DBuf<int> d_done;  // per-set completion counters of k_cost_quad (zeroed by the set build, self-resetting)
     size_t chunkBound = 0;
 
@@ -215,13 +220,13 @@ struct dmsa_b200_ctx {
 
 enum {
     PROF_POSE_FD = 0, PROF_POSE_LS, PROF_TRANSFORM, PROF_SETS_KEYS, PROF_SETS_SORT, PROF_SETS_STATS,
-    PROF_FUSED_FD, PROF_FUSED_LS, PROF_SUM_FD, PROF_SUM_LS, PROF_MEAN_FD, PROF_MEAN_LS, PROF_QUAD_FD, PROF_QUAD_LS, PROF_FIN_FD, PROF_FIN_LS, PROF_JTJ, PROF_COLSUM, PROF_HOST_SOLVE, PROF_HOST_ITER,
+    PROF_FUSED_FD, PROF_FUSED_LS, PROF_SUM_FD, PROF_SUM_LS, PROF_MEAN_FD, PROF_MEAN_LS, PROF_QUAD_FD, PROF_QUAD_LS, PROF_FIN_FD, PROF_FIN_LS, PROF_JTJ, PROF_COLSUM, PROF_LM_SOLVE, PROF_HOST_SOLVE, PROF_HOST_ITER,
     PROF_NUM
 };
 static const char* kProfNames[PROF_NUM] = {
     "pose_tables_fd", "pose_tables_ls", "transform_points", "sets_keys_root", "sets_sort_segment", "sets_gaussians_chunks",
     "k_cost_fused_fd", "k_cost_fused_ls", "k_cost_sum_fd", "k_cost_sum_ls", "k_cost_mean_fd", "k_cost_mean_ls", "k_cost_quad_fd", "k_cost_quad_ls", "k_cost_fin_fd", "k_cost_fin_ls",
-    "k_jtj", "k_col_sumsq", "host_lm_solve_wall", "host_iteration_wall"};
+    "k_jtj", "k_col_sumsq", "k_lm_solve", "host_lm_solve_wall", "host_iteration_wall"};
 
 static cudaEvent_t profEvent(dmsa_b200_ctx* ctx) {
     cudaEvent_t e;
@@ -814,13 +819,9 @@ int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
     return 0;
 }
 
-int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) {
+// the 9 trial costs of adaptiveStepSize for the step in d_step -> ls_dev[9]
+int lineSearchDev(dmsa_b200_ctx* ctx, double* ls_dev) {
     const int P = 6 * (ctx->poses.n - 1);
-    CKRC(ensurePinned(ctx, P));
-    CK(cudaEventSynchronize(ctx->evUpload));
-    std::copy(step_host, step_host + P, pinStep(ctx, P));
-    CK(cudaMemcpyAsync(ctx->d_step.p, pinStep(ctx, P), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->evUpload, ctx->stream));
     LAUNCH(k_make_ls_batch, cdiv((size_t)9 * P, 256), 256, 0, ctx->d_p.p, ctx->d_step.p, P, ctx->d_batch.p);
     ctx->phase = 1;
     int rc = runPoseTables(ctx, 9);
@@ -831,6 +832,69 @@ int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) 
     CK(ctx->d_lspart.ensure(9 * COLSUM_PARTS));
     LAUNCH(k_col_sumsq, dim3(9, COLSUM_PARTS), 256, 0, ctx->d_E.p, ctx->G + numExtra(ctx), ctx->curVld, ctx->d_lspart.p);
     LAUNCH(k_col_sumsq_fin, 1, 32, 0, ctx->d_lspart.p, ls_dev);
+    CK(cudaGetLastError());
+    return 0;
+}
+int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) {
+    const int P = 6 * (ctx->poses.n - 1);
+    CKRC(ensurePinned(ctx, P));
+    CK(cudaEventSynchronize(ctx->evUpload));
+    std::copy(step_host, step_host + P, pinStep(ctx, P));
+    CK(cudaMemcpyAsync(ctx->d_step.p, pinStep(ctx, P), P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->evUpload, ctx->stream));
+    return lineSearchDev(ctx, ls_dev);
+}
+
+// LM step on the device (kernels_solve.cuh): hg_dev = [H | g | err0] -> d_step (+ copy in step2), tail = [err0, nan flag]
+int lmSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, const double* hg_dev, double* step2, double* tail) {
+    if (P > LM_SOLVE_T) ARGFAIL("lm_solve: more than 1024 parameters are not supported by the device solver");
+    if (P <= LU_TILE_N && !ctx->solveGeneral) {
+        // fast path: register-tiled LU (one block) -> inverse columns (one warp per 32 columns) -> step
+        const int lda = P | 1;
+        CK(ctx->d_solve.ensure(2 * (size_t)P * lda + P + 2));
+        double* LU = ctx->d_solve.p;
+        double* X = LU + (size_t)P * lda;
+        int* piv = reinterpret_cast<int*>(X + (size_t)P * lda);
+        const size_t smem = ((size_t)P * lda + (size_t)P * 33) * sizeof(double);
+        if (!ctx->solveAttr) {
+            CK(cudaFuncSetAttribute(k_inv_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+            CK(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+            ctx->solveAttr = true;
+        }
+        ProfScope prof_(ctx, PROF_LM_SOLVE);
+        LuTileArgs la{hg_dev, P, lda, (double)st->lambda_diag, LU, piv};
+        LAUNCH(k_lu_tile, 1, LU_TILE_T, 0, la);
+        InvColsArgs ia{LU, piv, P, lda, X};
+        LAUNCH(k_inv_cols, (P + 31) / 32, INV_T, smem, ia);
+        StepFinArgs fa{hg_dev, X, P, lda, st->step_length_optim, st->max_step, ctx->d_step.p, step2, tail};
+        LAUNCH(k_step_fin, 1, LU_TILE_N, 0, fa);
+        CK(cudaGetLastError());
+        return 0;
+    }
+    LmSolveArgs q;
+    q.hg = hg_dev;
+    q.P = P;
+    q.lda = P | 1;
+    q.lambda = (double)st->lambda_diag;
+    q.alpha = st->step_length_optim;
+    q.max_step = st->max_step;
+    const size_t bytes = 2 * (size_t)P * q.lda * sizeof(double) + (size_t)P * sizeof(int) + 16;
+    q.use_smem = bytes <= (size_t)227 * 1024 - 2048 ? 1 : 0;
+    q.scratch = nullptr;
+    if (!q.use_smem) {
+        CK(ctx->d_solve.ensure(2 * (size_t)P * q.lda + P + 2));
+        q.scratch = ctx->d_solve.p;
+    } else if (!ctx->solveAttr) {
+        CK(cudaFuncSetAttribute(k_inv_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+        CK(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+        ctx->solveAttr = true;
+    }
+    q.step = ctx->d_step.p;
+    q.step2 = step2;
+    q.tail = tail;
+    q.clk = ctx->solveClk;
+    ProfScope prof_(ctx, PROF_LM_SOLVE);
+    LAUNCH(k_lm_solve, 1, LM_SOLVE_T, q.use_smem ? bytes : 0, q);
     CK(cudaGetLastError());
     return 0;
 }
@@ -932,6 +996,25 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     CK(ctx->d_hg.ensure((size_t)P * P + P + 1));
     CK(ctx->d_ls.ensure(16));
     CKRC(jtjInto(ctx, ctx->d_hg.p));  // :107
+    std::vector<double> step;
+    int nanStep;
+    double error0;
+    double ls[9];
+    const bool devSolve = ctx->solverMode == 0 && P <= LU_TILE_N;  // larger systems: the host solver is faster than one block
+    if (devSolve) {
+        // device-resident LM step: solve, line search and ONE read-back of [9 costs | step | err0 | NaN flag]
+        CK(ctx->d_iter.ensure(16 + (size_t)P + 2));
+        CKRC(lmSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
+        CKRC(lineSearchDev(ctx, ctx->d_iter.p));
+        CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_iter.p, (16 + (size_t)P + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const double* r = pinHg(ctx);
+        std::copy(r, r + 9, ls);
+        step.assign(r + 16, r + 16 + P);
+        error0 = r[16 + P];
+        nanStep = r[16 + P + 1] != 0.0;
+        ctx->lastErr0 = error0;
+    } else {
     ctx->h_hg.resize((size_t)P * P + P + 1);
     CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     dmsa_host_solver_arm();  // the solve follows this read-back immediately: helper threads spin up while the host waits
@@ -941,29 +1024,33 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
         return DMSA_B200_ERR_CUDA;
     }
     std::copy(pinHg(ctx), pinHg(ctx) + ctx->h_hg.size(), ctx->h_hg.begin());
-    const double error0 = ctx->h_hg[(size_t)P * P + P];
+    error0 = ctx->h_hg[(size_t)P * P + P];
     ctx->lastErr0 = error0;
-    std::vector<double> step;
-    int nanStep;
     {
         WallTimer ws{ctx, PROF_HOST_SOLVE};
         nanStep = solveStep(st, ctx->h_hg.data(), P, step);
     }
     dmsa_host_solver_disarm();
+    }
     if (nanStep) {  // :113-122
         // the last cost evaluation of calcNumericJacobian was p + h e_{P-1}: its global poses stay behind (see staleGlobal)
+        if (ctx->profiling) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            profCollect(ctx);
+        }
         std::vector<double> plast = paramVec;
         plast[P - 1] += 1.0 * (double)sqrtf(FLT_EPSILON);
         staleGlobal(ctx, plast.data(), paramVec.data());
         *stop = DMSA_B200_STOP_NAN;
         return 0;
     }
+    if (!devSolve) {
     // adaptiveStepSize :152-182 — the 9 trial costs in one batch
     CKRC(lineSearchInto(ctx, step.data(), ctx->d_ls.p));
-    double ls[9];
     CK(cudaMemcpyAsync(pinLs(ctx, P), ctx->d_ls.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     std::copy(pinLs(ctx, P), pinLs(ctx, P) + 9, ls);
+    }
     if (ctx->profiling) profCollect(ctx);
     double minError = error0;
     int best = 0;
@@ -1050,7 +1137,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_solve); REL(d_iter);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
@@ -1630,6 +1717,46 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
     if (explicit_inverse == 2) dmsa_host_solver_disarm();
     std::copy(st.begin(), st.end(), step);
     if (has_nan) *has_nan = nan;
+    return 0;
+}
+
+// Which solver dmsa_b200_iteration / dmsa_b200_optimize use for the LM step: 0 (default) the device kernel k_lm_solve
+// (no host round trip between the Jacobian pass and the line search), 1 the host solver.  Same operation sequence,
+// bit-identical steps.
+int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode) {
+    if (mode != 0 && mode != 1) ARGFAIL("set_lm_solver: 0 (device, default) or 1 (host)");
+    ctx->solverMode = mode;
+    return 0;
+}
+
+// The device LM step on a HOST copy of [H | g | err0] (any n_params <= 1024): upload, k_lm_solve, download.  Exists so
+// that the device solver can be checked against dmsa_b200_lm_solve (host) on arbitrary systems.
+int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step,
+                              int32_t* has_nan) {
+    if (!settings || !hg || !step || n_params <= 0) ARGFAIL("lm_solve_device: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int P = n_params;
+    const size_t nhg = (size_t)P * P + P + 1;
+    CK(ctx->d_hg.ensure(nhg));
+    CK(ctx->d_step.ensure(P));
+    CK(ctx->d_iter.ensure(16 + (size_t)P + 2));
+    CK(cudaMemcpyAsync(ctx->d_hg.p, hg, nhg * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->solveGeneral = getenv("DMSA_B200_SOLVE_GENERAL") != nullptr;
+    const bool dbg = getenv("DMSA_B200_SOLVE_CLK") != nullptr;
+    if (dbg && !ctx->solveClk) CK(cudaMalloc((void**)&ctx->solveClk, 8 * sizeof(long long)));
+    CKRC(lmSolveDev(ctx, settings, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
+    if (dbg) {
+        long long c[8];
+        CK(cudaMemcpyAsync(c, ctx->solveClk, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "k_lm_solve P=%d cycles: load %lld | LU %lld | forward %lld | backward %lld | matvec %lld\n", P, 0LL, c[1] - c[0], c[2] - c[1], c[3] - c[2],
+                c[4] - c[3]);
+    }
+    std::vector<double> r((size_t)P + 2);
+    CK(cudaMemcpyAsync(r.data(), ctx->d_iter.p + 16, r.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::copy(r.begin(), r.begin() + P, step);
+    if (has_nan) *has_nan = r[(size_t)P + 1] != 0.0;
     return 0;
 }
 

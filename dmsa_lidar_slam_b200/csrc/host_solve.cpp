@@ -6,6 +6,8 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstddef>
+#include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 #include <mutex>
 #include <thread>
@@ -48,22 +50,22 @@ DMSA_CLONES static void lu_factor_impl(std::vector<double>& a, std::vector<int>&
     }
 }
 // forward + back substitution of the right-hand-side columns [c0, c1) (independent of every other column)
-DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n, int c0, int c1) {
+DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n, int ldx, int c0, int c1) {
     for (int i = 0; i < n; ++i) {  // forward substitution, unit lower triangle
-        double* __restrict__ xi = &inv[(size_t)i * n];
+        double* __restrict__ xi = &inv[(size_t)i * ldx];
         const double* ai = &a[(size_t)i * n];
         for (int j = 0; j < i; ++j) {
             const double l = ai[j];
-            const double* __restrict__ xj = &inv[(size_t)j * n];
+            const double* __restrict__ xj = &inv[(size_t)j * ldx];
             for (int c = c0; c < c1; ++c) xi[c] -= l * xj[c];
         }
     }
     for (int i = n - 1; i >= 0; --i) {  // back substitution
-        double* __restrict__ xi = &inv[(size_t)i * n];
+        double* __restrict__ xi = &inv[(size_t)i * ldx];
         const double* ai = &a[(size_t)i * n];
         for (int j = i + 1; j < n; ++j) {
             const double u = ai[j];
-            const double* __restrict__ xj = &inv[(size_t)j * n];
+            const double* __restrict__ xj = &inv[(size_t)j * ldx];
             for (int c = c0; c < c1; ++c) xi[c] -= u * xj[c];
         }
         const double dinv = ai[i];
@@ -76,6 +78,8 @@ DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n,
 // armed workers spin on the job counter and start without a wake-up latency; disarmed workers sleep on a condition
 // variable.  Each column is still computed by exactly one thread with the serial operation order: results are identical.
 namespace {
+// columns per thread: a multiple of 8 doubles (one 64-byte cache line) so that no two threads ever write the same line of a row
+inline int colBlock(int n) { return ((n + 3) / 4 + 7) / 8 * 8; }
 struct SolvePool {
     static constexpr int kWorkers = 3;
     std::vector<std::thread> th;
@@ -87,15 +91,16 @@ struct SolvePool {
     std::atomic_flag busy = ATOMIC_FLAG_INIT;  // one solve at a time uses the helpers; a concurrent one runs serially
     const double* a = nullptr;
     double* inv = nullptr;
-    int n = 0;
+    int n = 0, ldx = 0;
     bool stop = false;
     bool disabled = false;
     void start() {
         if (!th.empty() || disabled) return;
-        // opt-in (DMSA_B200_SOLVER_THREADS=1): on the measured B200 host the helpers did not shorten the 0.32 ms solve at
-        // P = 114 (0.34 ms with, 0.32 ms without), so the default keeps the solve on the calling thread
+        // Three helper threads take cache-line aligned column blocks of the inverse while the caller takes the first
+        // (measured on the B200 host, P = 114: 0.25 ms alone, 0.19 ms with helpers).  DMSA_B200_SOLVER_THREADS=0 turns
+        // them off; they are also off on hosts with fewer than 8 hardware threads.
         const char* e = std::getenv("DMSA_B200_SOLVER_THREADS");
-        if (!e || std::atoi(e) <= 0) {
+        if ((e && std::atoi(e) <= 0) || (!e && std::thread::hardware_concurrency() < 8)) {
             disabled = true;
             return;
         }
@@ -113,8 +118,8 @@ struct SolvePool {
                 const unsigned long long g = gen.load(std::memory_order_acquire);
                 if (g != seen) {
                     seen = g;
-                    const int nb = kWorkers + 1, blk = w + 1;
-                    lu_subst_block_impl(a, inv, n, (int)((long long)n * blk / nb), (int)((long long)n * (blk + 1) / nb));
+                    const int blk = w + 1;
+                    lu_subst_block_impl(a, inv, n, ldx, std::min(n, colBlock(n) * blk), std::min(n, colBlock(n) * (blk + 1)));
                     remaining.fetch_sub(1, std::memory_order_acq_rel);
                 } else {
                     __builtin_ia32_pause();
@@ -149,20 +154,27 @@ static bool lu_solve_inverse_impl(const std::vector<double>& A, int n, std::vect
     std::vector<double> a(A);
     std::vector<int> piv(n);
     lu_factor_impl(a, piv, n);
-    inv.assign((size_t)n * n, 0.0);
-    for (int i = 0; i < n; ++i) inv[(size_t)i * n + piv[i]] = 1.0;  // P * I
+    // right-hand sides in a cache-line aligned, padded block (ldx multiple of 8): the helper threads own whole lines
+    const int ldx = (n + 7) / 8 * 8;
+    std::vector<double> xbuf((size_t)n * ldx + 8, 0.0);
+    double* x = xbuf.data();
+    while (reinterpret_cast<uintptr_t>(x) & 63) ++x;
+    for (int i = 0; i < n; ++i) x[(size_t)i * ldx + piv[i]] = 1.0;  // P * I
     if (n >= 64 && g_pool.armed.load(std::memory_order_acquire) > 0 && !g_pool.th.empty() && !g_pool.busy.test_and_set(std::memory_order_acquire)) {
         g_pool.a = a.data();
-        g_pool.inv = inv.data();
+        g_pool.inv = x;
         g_pool.n = n;
+        g_pool.ldx = ldx;
         g_pool.remaining.store(SolvePool::kWorkers, std::memory_order_release);
         g_pool.gen.fetch_add(1, std::memory_order_acq_rel);
-        lu_subst_block_impl(a.data(), inv.data(), n, 0, (int)((long long)n / (SolvePool::kWorkers + 1)));
+        lu_subst_block_impl(a.data(), x, n, ldx, 0, std::min(n, colBlock(n)));
         while (g_pool.remaining.load(std::memory_order_acquire) > 0) __builtin_ia32_pause();
         g_pool.busy.clear(std::memory_order_release);
     } else {
-        lu_subst_block_impl(a.data(), inv.data(), n, 0, n);
+        lu_subst_block_impl(a.data(), x, n, ldx, 0, n);
     }
+    inv.resize((size_t)n * n);
+    for (int i = 0; i < n; ++i) std::copy(x + (size_t)i * ldx, x + (size_t)i * ldx + n, inv.begin() + (size_t)i * n);
     return true;
 }
 

@@ -492,3 +492,55 @@ def test_call_order_is_checked():
         traj.evalCost(traj.getPoseParameters()[None, :])
     with pytest.raises(DmsaError):
         ContinuousTrajectory().initTraj(0.0, 1.0, 2)  # barycentric_rational of order 2 needs >= 3 poses
+
+
+@pytest.mark.parametrize("n", [12, 18, 31, 33, 64, 114, 116, 117, 128, 129, 234])
+def test_device_lm_solve_is_bit_identical_to_the_host_solver(n):
+    """k_lm_solve (kernels_solve.cuh) runs the operation sequence of the host solver (DmsaOptimizer.h:107-128 with Eigen's
+    PartialPivLU inverse): the clamped steps are bit-identical, in shared memory (n <= 116) and in global scratch."""
+    from dmsa_lidar_slam_b200.api import lm_solve
+
+    traj = ContinuousTrajectory()
+    rng = np.random.default_rng(1000 + n)
+    for trial in range(3):
+        J = rng.standard_normal((3 * n, n)) * np.logspace(0, -3, n)[None, :]  # ill-conditioned like lambda = 1e-5 systems
+        if trial == 2:
+            J[:, n // 2] = 0.0  # a zero column: the lambda diagonal alone keeps the pivot alive
+        r = rng.standard_normal(3 * n)
+        hg = np.concatenate([(J.T @ J).ravel(), J.T @ r, [float(r @ r)]])
+        s = DmsaOptimSettings(step_length_optim=0.2, max_step=0.3 if trial else 1e9, lambda_diag=1e-5)
+        a, nan_a = lm_solve(s, hg, n, 1)
+        for general in (False, True):  # n <= 128: register-tiled three-kernel path; forced general one-block kernel
+            os.environ.pop("DMSA_B200_SOLVE_GENERAL", None)
+            if general:
+                os.environ["DMSA_B200_SOLVE_GENERAL"] = "1"
+            b, nan_b = traj.lmSolveDevice(s, hg, n)
+            os.environ.pop("DMSA_B200_SOLVE_GENERAL", None)
+            assert nan_a == nan_b == 0
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), f"n={n} trial={trial} general={general}: max |diff| {np.abs(a - b).max():.3e}"
+    hg = np.zeros(n * n + n + 1)
+    hg[0] = np.nan
+    _, nan_h = lm_solve(DmsaOptimSettings(), hg, n, 1)
+    _, nan_d = traj.lmSolveDevice(DmsaOptimSettings(), hg, n)
+    assert nan_h == nan_d == 1
+    hg = np.zeros(n * n + n + 1)  # singular (lambda = 0): 0/0 pivots -> NaN step on both sides
+    s0 = DmsaOptimSettings(lambda_diag=0.0)
+    _, nan_h = lm_solve(s0, hg, n, 1)
+    _, nan_d = traj.lmSolveDevice(s0, hg, n)
+    assert nan_h == nan_d == 1
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])
+def test_device_and_host_solver_iterations_agree_bitwise(name):
+    """dmsa_b200_iteration with the device LM step (default, one read-back per iteration) and with the host solver."""
+    out = []
+    for mode in (0, 1):
+        win, traj, om, s, so = make_pair(name)
+        traj.setLmSolver(mode)
+        traj.centralize()
+        res = [traj.iteration(s) for _ in range(2)]
+        out.append((res, traj.getPoseParameters()))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert a["stop_reason"] == b["stop_reason"] and a["best_step"] == b["best_step"] and a["error0"] == b["error0"]
+        assert np.array_equal(a["step"], b["step"]) and np.array_equal(a["ls_cost"], b["ls_cost"])
+    assert np.array_equal(out[0][1], out[1][1])
