@@ -193,10 +193,12 @@ struct dmsa_b200_ctx {
     size_t cubPer = 0;  // bytes of CUB temporary storage per resolution level
 
     // cost
+    DBuf<double> d_mom;  // centred second moments of every set [g][6]
     DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart, d_solve, d_iter;
     bool solveAttr = false;
     bool solveGeneral = false;  // force the general one-block kernel (any P <= 1024) instead of the P <= 128 fast path
     long long* solveClk = nullptr;  // debug: device buffer of phase cycle stamps (dmsa_b200_lm_solve_device with DMSA_B200_SOLVE_CLK=1)
+    DBuf<int> d_biglist;  // sets with more than GAUSS_WARP_MAX members (+ the count at [cellCap])
     DBuf<int> d_done;  // per-set completion counters of k_cost_quad (zeroed by the set build, self-resetting)
     size_t chunkBound = 0;
 
@@ -708,11 +710,25 @@ phase2:
     if (G == 0) return 0;
     // phase 3: per-set statistics, weights, chunk list
     ProfScope prof_(ctx, PROF_SETS_STATS);
-    LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G);
-    LAUNCH(k_gaussian_big, std::min(G, 148 * 2), GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, G);
-    LAUNCH(k_weights, 1, 1024, 0, cs, G);
     CK(ctx->d_okey.ensure((size_t)cap));
     CK(ctx->d_oval.ensure((size_t)2 * cap + 4 * ORDER_CLASSES));
+    CK(ctx->d_biglist.ensure((size_t)cap + 1));
+    CK(ctx->d_mom.ensure((size_t)6 * cap));
+    // small sets (one warp each) on the context's stream, the sets with more than GAUSS_WARP_MAX members (one block each,
+    // compact list) on stream2, side by side; both write disjoint sets
+    {
+        int* cnt = ctx->d_biglist.p + cap;
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream));
+        LAUNCH(k_gauss_list, cdiv(G, 256), 256, 0, cs, G, ctx->d_biglist.p, cnt);
+        CK(cudaEventRecord(ctx->evFork, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+        LAUNCH_ON(ctx->stream2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
+        CK(cudaEventRecord(ctx->evJoin, ctx->stream2));
+        LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G, ctx->d_mom.p);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+        LAUNCH(k_gaussian_fin, cdiv(G, 128), 128, 0, cs, G, ctx->d_mom.p);
+    }
+    LAUNCH(k_weights, 1, 1024, 0, cs, G);
     int* hist = ctx->d_oval.p;  // [ORDER_CLASSES histogram | ORDER_CLASSES cursors], then the order at + cellCap
     CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_done.p, 0, ((size_t)G + 1) * sizeof(int), ctx->stream));
@@ -1137,7 +1153,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_solve); REL(d_iter);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_biglist); REL(d_mom); REL(d_solve); REL(d_iter);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);

@@ -702,9 +702,11 @@ __device__ inline void gaussian_finish(CellStore cs, int g, int n, const double 
     cs.w0[g] = fmul_(fdiv_(1.0f, nf), 1.0f);  // Gaussians.h:172-175, observation weight 1 (OptimizablePointSet.h:52)
 }
 
-#define GAUSS_WARP_MAX 1024
-// One warp per accepted set with n <= GAUSS_WARP_MAX members.
-__global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G) {
+#define GAUSS_WARP_MAX 256
+// One warp per accepted set with n <= GAUSS_WARP_MAX members (larger sets: k_gaussian_big over the compact list of
+// k_gauss_list): centred second moments -> mom[g][6]; k_gaussian_fin turns them into information matrices.  The member loops are unrolled so that the loads of four strides are in flight together; every
+// thread still adds its terms in ascending member order.
+__global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G, double* __restrict__ mom) {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= G) return;
@@ -712,6 +714,7 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G)
     if (n > GAUSS_WARP_MAX) return;
     // colwise().mean(): exactly-rounded sum, float division
     double sx = 0, sy = 0, sz = 0;
+#pragma unroll 4
     for (int j = lane; j < n; j += 32) {
         float4 p = wrec[s + j];
         sx += (double)p.x;
@@ -724,6 +727,7 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G)
     const float nf = (float)n;
     const float mx = fdiv_((float)sx, nf), my = fdiv_((float)sy, nf), mz = fdiv_((float)sz, nf);
     double a[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
     for (int j = lane; j < n; j += 32) {
         float4 p = wrec[s + j];
         double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
@@ -736,20 +740,31 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G)
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) a[k] = warp_sum(a[k]);
-    if (lane == 0) gaussian_finish(cs, g, n, a);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) mom[6 * (size_t)g + k] = a[k];
+}
+// compact list of the sets with n > GAUSS_WARP_MAX (order irrelevant: every set's result depends on the set alone)
+__global__ void k_gauss_list(CellStore cs, int G, int* __restrict__ list, int* __restrict__ count) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    if (cs.n[g] > GAUSS_WARP_MAX) list[atomicAdd(count, 1)] = g;
 }
 #define GAUSS_BIG_T 1024
-// Accepted sets with n > GAUSS_WARP_MAX members: one 1024-thread block per set, a persistent grid strides over the set
-// list (the big sets are few; a grid of G mostly-empty 1024-thread blocks costs more than the work itself).
-__global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __restrict__ wrec, CellStore cs, int G) {
+// Accepted sets with n > GAUSS_WARP_MAX members: one 1024-thread block per set, a persistent grid strides over the
+// compact list.
+__global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __restrict__ wrec, CellStore cs, const int* __restrict__ list,
+                                                               const int* __restrict__ count, double* __restrict__ mom) {
     __shared__ double red[GAUSS_BIG_T / 32][6];
     __shared__ float smean[3];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int g = blockIdx.x; g < G; g += gridDim.x) {  // block-uniform
+    const int nbig = *count;
+    for (int q = blockIdx.x; q < nbig; q += gridDim.x) {  // block-uniform
+        const int g = list[q];
         const int s = cs.start[g], n = cs.n[g];
-        if (n <= GAUSS_WARP_MAX) continue;
         __syncthreads();  // shared scratch of the previous set is free
         double sx = 0, sy = 0, sz = 0;
+#pragma unroll 4
         for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
             float4 p = wrec[s + j];
             sx += (double)p.x;
@@ -773,6 +788,7 @@ __global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __re
         __syncthreads();
         const float mx = smean[0], my = smean[1], mz = smean[2];
         double a[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 4
         for (int j = threadIdx.x; j < n; j += GAUSS_BIG_T) {
             float4 p = wrec[s + j];
             double cx = (double)fsub_(p.x, mx), cy = (double)fsub_(p.y, my), cz = (double)fsub_(p.z, mz);
@@ -795,9 +811,19 @@ __global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __re
                 t[k] = 0;
                 for (int w = 0; w < GAUSS_BIG_T / 32; ++w) t[k] += red[w][k];
             }
-            gaussian_finish(cs, g, n, t);
+            for (int k = 0; k < 6; ++k) mom[6 * (size_t)g + k] = t[k];
         }
     }
+}
+// Eigen clamp + information matrix + observation weight of every set from its centred second moments: one THREAD per
+// set (the 3x3 Jacobi sweeps are long dependent FP64 chains; with one lane per warp they cost 32x the issue slots).
+__global__ void k_gaussian_fin(CellStore cs, int G, const double* __restrict__ mom) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double a[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = mom[6 * (size_t)g + k];
+    gaussian_finish(cs, g, cs.n[g], a);
 }
 
 // Gaussians.h:177: w / w.mean()   (one block; deterministic double reduction, one rounding)
