@@ -119,6 +119,7 @@ def load_library():
         "dmsa_b200_line_search_costs_dev": (i32, [vp, vp, vp]),
         "dmsa_b200_lm_solve": (i32, [P(DmsaOptimSettings), vp, i32, i32, vp, P(i32)]),
         "dmsa_b200_set_lm_solver": (i32, [vp, i32]),
+        "dmsa_b200_set_pair_mode": (i32, [vp, i32]),
         "dmsa_b200_lm_solve_device": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
     }
     for name, (res, args) in sig.items():
@@ -140,7 +141,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_get_voxel_keys", "dmsa_b200_eval_cost", "dmsa_b200_cost_jacobian", "dmsa_b200_iteration", "dmsa_b200_optimize",
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
-    "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device",
+    "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode",
 ]
 
 
@@ -314,6 +315,10 @@ class OptimizablePointSet:
     def setMeanMode(self, mode):
         """0: order-free exactly-rounded per-set mean (default, fast); 1: the reference's sequential float accumulation."""
         self.ctx._ck(self.L.dmsa_b200_set_mean_mode(self.h, int(mode)))
+
+    def setPairMode(self, mode):
+        """1: pair-packed FP32x2 cost kernels for the forward-difference batch (default); 0: scalar kernels (bit-identical)."""
+        self.ctx._ck(self.L.dmsa_b200_set_pair_mode(self.h, int(mode)))
 
     def setLmSolver(self, mode):
         """0: LM step on the device (default; no host round trip inside an iteration); 1: host solver (bit-identical)."""

@@ -169,7 +169,8 @@ struct dmsa_b200_ctx {
 
     // pose batches
     DBuf<double> d_p, d_step, d_batch, d_globO, d_globT, d_quat, d_extra;
-    DBuf<float> d_Mtab;
+    DBuf<float> d_Mtab, d_Mpair;
+    int pairMode = 1;  // 1: pair-packed cost kernels (FMUL2/FADD2) for the forward-difference batch, 0: scalar kernels; bit-identical
     int curV = 0, curVld = 0;
 
     // set construction
@@ -383,6 +384,8 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
     CK(ctx->d_globT.ensure((size_t)3 * n * Vld));
     CK(ctx->d_quat.ensure((size_t)4 * n * Vld));
     CK(ctx->d_Mtab.ensure((size_t)(rows + 1) * Vld * 12));  // + the identity row used by static points
+    const bool pairTab = ctx->pairMode && V > 16 && ctx->meanMode == 0;
+    if (pairTab) CK(ctx->d_Mpair.ensure((size_t)(rows + 1) * Vld * 12));
     if (E > 0) CK(ctx->d_extra.ensure((size_t)E * Vld));
     PoseBatch pb;
     pb.V = V;
@@ -398,6 +401,7 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
     pb.globT_t = ctx->d_globT.p;
     pb.quat_t = ctx->d_quat.p;
     pb.extra = E > 0 ? ctx->d_extra.p : nullptr;
+    pb.Mpair = pairTab ? ctx->d_Mpair.p : nullptr;
     TrajTiming tt;
     tt.n_total = ctx->n_total;
     tt.seg = ctx->d_seg.p;
@@ -714,31 +718,34 @@ phase2:
     CK(ctx->d_oval.ensure((size_t)2 * cap + 4 * ORDER_CLASSES));
     CK(ctx->d_biglist.ensure((size_t)cap + 1));
     CK(ctx->d_mom.ensure((size_t)6 * cap));
-    // small sets (one warp each) on the context's stream, the sets with more than GAUSS_WARP_MAX members (one block each,
-    // compact list) on stream2, side by side; both write disjoint sets
+    // Context's stream: the small sets (one warp each).  stream2, side by side: the compact list of the sets with more than
+    // GAUSS_WARP_MAX members and their statistics (one block each), plus the work decomposition of the cost kernels
+    // (set kinds, issue order, chunk list), which depends on the set sizes only.  Disjoint outputs; joined before the
+    // eigen finish.
+    ctx->chunkBound = (size_t)2 * N / CHUNK + (size_t)2 * N / FUSE_MAX + 2;  // big sets only
+    CK(ctx->d_chunks.ensure(ctx->chunkBound));
     {
+        cudaStream_t s2 = ctx->stream2;
         int* cnt = ctx->d_biglist.p + cap;
-        CK(cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream));
-        LAUNCH(k_gauss_list, cdiv(G, 256), 256, 0, cs, G, ctx->d_biglist.p, cnt);
+        int* hist = ctx->d_oval.p;  // [ORDER_CLASSES histogram | ORDER_CLASSES cursors], then the order at + cellCap
         CK(cudaEventRecord(ctx->evFork, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
-        LAUNCH_ON(ctx->stream2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
-        CK(cudaEventRecord(ctx->evJoin, ctx->stream2));
+        CK(cudaStreamWaitEvent(s2, ctx->evFork, 0));
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int), s2));
+        LAUNCH_ON(s2, k_gauss_list, cdiv(G, 256), 256, 0, cs, G, ctx->d_biglist.p, cnt);
+        LAUNCH_ON(s2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
+        CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), s2));
+        CK(cudaMemsetAsync(ctx->d_done.p, 0, ((size_t)G + 1) * sizeof(int), s2));
+        LAUNCH_ON(s2, k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
+        LAUNCH_ON(s2, k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
+        CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), s2));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p + ctx->cubPer, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, s2));
+        LAUNCH_ON(s2, k_chunk_fill, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
+        CK(cudaEventRecord(ctx->evJoin, s2));
         LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G, ctx->d_mom.p);
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
         LAUNCH(k_gaussian_fin, cdiv(G, 128), 128, 0, cs, G, ctx->d_mom.p);
     }
     LAUNCH(k_weights, 1, 1024, 0, cs, G);
-    int* hist = ctx->d_oval.p;  // [ORDER_CLASSES histogram | ORDER_CLASSES cursors], then the order at + cellCap
-    CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_done.p, 0, ((size_t)G + 1) * sizeof(int), ctx->stream));
-    LAUNCH(k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
-    LAUNCH(k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
-    CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), ctx->stream));
-    CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, ctx->stream));
-    ctx->chunkBound = (size_t)2 * N / CHUNK + (size_t)2 * N / FUSE_MAX + 2;  // big sets only
-    CK(ctx->d_chunks.ensure(ctx->chunkBound));
-    LAUNCH(k_chunk_fill, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
     CK(cudaGetLastError());
     return 0;
 }
@@ -755,6 +762,8 @@ int runCost(dmsa_b200_ctx* ctx) {
     a.n_chunks = ctx->d_chunk_off.p + G;
     a.rec = ctx->d_rec.p;
     a.Mtab = reinterpret_cast<const float4*>(ctx->d_Mtab.p);
+    a.Mpair = reinterpret_cast<const unsigned long long*>(ctx->d_Mpair.p);
+    a.Vp = Vld / 2;
     a.V = V;
     a.Vld = Vld;
     a.S = (V <= 16) ? 32 / V : 1;
@@ -790,18 +799,39 @@ int runCost(dmsa_b200_ctx* ctx) {
         case 3: LAUNCH((KERN<false, 512, 2>), GRID, Vld, 0, __VA_ARGS__); break;           \
         default: LAUNCH((KERN<false, 1024, 1>), GRID, Vld, 0, __VA_ARGS__); break;         \
     }
+    const bool pair = !packed && ctx->pairMode;  // two parameter vectors per thread, packed FP32x2 (kernels_cost.cuh)
+#define DISPATCH2(KERN, GRID, ...)                                                         \
+    switch (cls) {                                                                         \
+        case 1: LAUNCH((KERN<64, 12>), GRID, Vld / 2, 0, __VA_ARGS__); break;              \
+        case 2: LAUNCH((KERN<128, 6>), GRID, Vld / 2, 0, __VA_ARGS__); break;              \
+        case 3: LAUNCH((KERN<256, 3>), GRID, Vld / 2, 0, __VA_ARGS__); break;              \
+        default: LAUNCH((KERN<512, 1>), GRID, Vld / 2, 0, __VA_ARGS__); break;             \
+    }
     {
         ProfScope p_(ctx, PROF_FUSED_FD + ph);
-        DISPATCH(k_cost_fused, G, a, G);
+        if (pair) {
+            DISPATCH2(k_cost_fused2, G, a, G);
+        } else {
+            DISPATCH(k_cost_fused, G, a, G);
+        }
     }
     {
         ProfScope p_(ctx, PROF_SUM_FD + ph);
-        DISPATCH(k_cost_sum, grid, a);
+        if (pair) {
+            DISPATCH2(k_cost_sum2, grid, a);
+        } else {
+            DISPATCH(k_cost_sum, grid, a);
+        }
     }
     {
         ProfScope p_(ctx, PROF_QUAD_FD + ph);  // includes the per-set mean and the final chunk reduction (last block of a set)
-        DISPATCH(k_cost_quad, grid, a);
+        if (pair) {
+            DISPATCH2(k_cost_quad2, grid, a);
+        } else {
+            DISPATCH(k_cost_quad, grid, a);
+        }
     }
+#undef DISPATCH2
 #undef DISPATCH
     if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaGetLastError());
@@ -1149,7 +1179,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
 #define REL(b) ctx->b.release()
     REL(d_stamps); REL(d_trajTime); REL(d_urel); REL(d_fh); REL(d_seg); REL(d_hit); REL(d_paramIdx); REL(d_imu); REL(d_kfD); REL(d_plausible);
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
-    REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_Mtab);
+    REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_Mtab); REL(d_Mpair);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
@@ -1742,6 +1772,13 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode) {
     if (mode != 0 && mode != 1) ARGFAIL("set_lm_solver: 0 (device, default) or 1 (host)");
     ctx->solverMode = mode;
+    return 0;
+}
+
+// Cost kernels of the forward-difference batch: 1 (default) pair-packed FP32x2 kernels, 0 scalar kernels (bit-identical).
+int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode) {
+    if (mode != 0 && mode != 1) ARGFAIL("set_pair_mode: 1 (pair-packed, default) or 0 (scalar)");
+    ctx->pairMode = mode;
     return 0;
 }
 

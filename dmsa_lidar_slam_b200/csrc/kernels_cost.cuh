@@ -26,6 +26,8 @@ struct CostArgs {
     const int* n_chunks;     // device scalar: total chunks of the big sets (grid is an upper bound)
     const float4* rec;       // member records, sorted order: local xyz + transform-table row (int bits)
     const float4* Mtab;      // [(row * Vld + v) * 3 + r]; the last row is the identity (static points)
+    const unsigned long long* Mpair;  // pair-interleaved copy [(row * Vp + tp) * 12 + c] = {M[row][2tp][c], M[row][2tp+1][c]}
+    int Vp;                  // Vld / 2
     int V, Vld;
     int S;                   // member sub-streams per warp: 1 when V > 16 (one thread per vector), else 32 / V lane groups
     const float* info;       // [g][9]
@@ -296,6 +298,46 @@ __global__ void __launch_bounds__(1024) k_cost_seq(CostArgs a, int G) {
     if (active) a.E[(size_t)g * a.Vld + v] = sqrt(fabs(acc));
 }
 
+#define COST_RED_Y 8
+// Fixed-order reduction of a big set's chunk partials: COST_RED_Y interleaved partial sums (chunk c goes to slot
+// c % COST_RED_Y, ascending c), then the slots in ascending order.
+__device__ __forceinline__ double reduce_chunks(const double* __restrict__ part, int nc, size_t stride) {
+    double t = 0.0;
+#pragma unroll 1
+    for (int y = 0; y < COST_RED_Y; ++y) {
+        double s = 0.0;
+        for (int c = y; c < nc; c += COST_RED_Y) s += __ldcg(part + (size_t)c * stride);
+        t += s;
+    }
+    return t;
+}
+// the same reduction for two adjacent vectors at once (16-byte loads; identical order per component)
+__device__ __forceinline__ double2 reduce_chunks2(const double* __restrict__ part, int nc, size_t stride) {
+    double2 t = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int y = 0; y < COST_RED_Y; ++y) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int c = y; c < nc; c += COST_RED_Y) {
+            const double2 q = __ldcg(reinterpret_cast<const double2*>(part + (size_t)c * stride));
+            s.x += q.x;
+            s.y += q.y;
+        }
+        t.x += s.x;
+        t.y += s.y;
+    }
+    return t;
+}
+// "last block of the set": fence, count, and tell the whole block whether every other chunk block of set g is done
+__device__ __forceinline__ bool last_block_of_set(int* counter, int nc, int* s_flag) {
+    __threadfence();  // this block's partials are visible device-wide before the counter moves
+    __syncthreads();
+    if (threadIdx.x == 0) *s_flag = (atomicAdd(counter, 1) == nc - 1) ? 1 : 0;
+    __syncthreads();
+    if (!*s_flag) return false;
+    __threadfence();
+    return true;
+}
+
 // Big sets, pass 1: per-chunk coordinate sums (double)
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
@@ -318,24 +360,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
     }
 }
 
-#define COST_RED_Y 8
-// Fixed-order reduction of a big set's chunk partials, identical for every reader: COST_RED_Y interleaved partial sums
-// (chunk c goes to slot c % COST_RED_Y, ascending c), then the slots in ascending order.  Every block of the set
-// recomputes it from the same partials, so all of them see bit-identical means.
-__device__ __forceinline__ double reduce_chunks(const double* __restrict__ part, int nc, size_t stride) {
-    double t = 0.0;
-#pragma unroll 1
-    for (int y = 0; y < COST_RED_Y; ++y) {
-        double s = 0.0;
-        for (int c = y; c < nc; c += COST_RED_Y) s += __ldcg(part + (size_t)c * stride);
-        t += s;
-    }
-    return t;
-}
-
-// Big sets, pass 2: mean = float(sum over the set's chunks) / float(n) (DmsaOptimizer.h:254, recomputed by every chunk
-// block from the chunk partials of pass 1), per-chunk sums of the Mahalanobis terms, and - in the block that finishes
-// last for its set (fence + per-set counter) - e = sqrt(|sum of the chunk partials|) in fixed chunk order (:267).
+// Big sets, pass 2: mean = float(sum over the set's chunks) / float(n) (DmsaOptimizer.h:254; every chunk block of the set
+// recomputes it from the same pass-1 partials in the same fixed order, so all of them see bit-identical means - measured
+// cheaper than a separate mean kernel or a last-block reduction in pass 1), per-chunk sums of the Mahalanobis terms, and -
+// in the block that finishes last for its set - e = sqrt(|sum of the chunk partials|) in fixed chunk order (:267).
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
@@ -358,14 +386,264 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
     acc = combine_subs<PACKED>(a, lm, acc);
     const bool writer = lm.active && lm.sub == 0;
     if (writer) a.Q[(size_t)c * a.Vld + lm.v] = acc;
-    __threadfence();  // the partials of this block are visible device-wide before the counter moves
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(a.done + g, 1) == nc - 1) ? 1 : 0;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (!last_block_of_set(a.done + g, nc, &s_last)) return;
     if (writer) a.E[(size_t)g * a.Vld + lm.v] = sqrt(fabs(reduce_chunks(a.Q + (size_t)o * a.Vld + lm.v, nc, (size_t)a.Vld)));
     if (threadIdx.x == 0) a.done[g] = 0;  // ready for the next launch
+}
+
+// =====================================================================================================================
+// Pair-packed variants of the three cost kernels for the forward-difference batch (V > 16): one thread evaluates TWO
+// parameter vectors (2 tp, 2 tp + 1) with Blackwell's packed FP32x2 instructions (SASS FMUL2 / FADD2).
+//
+// Why not simply pack everything: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false
+// (scripts/microbench/packed_fp32.cu shows the SASS and the changed results), and the reference arithmetic has no FMA.
+// The faithful packing keeps one SCALAR side on every multiply -> add edge: products are packed (FMUL2 with the member
+// coordinate / information entry as broadcast scalar operand), the adds they feed are scalar FADDs on the two halves,
+// adds that follow adds (+ translation, - mean) are packed again.  Per member and vector pair: 42 packed + 40 scalar
+// FP32 instructions instead of 124 scalar ones, the shared-memory load, the row test and the loop are shared by the
+// two vectors.  Bit-identical to the scalar kernels (tests/test_gpu_parity.py::test_pair_packed_...).
+// The transform table is read from a pair-interleaved copy: Mpair[(row * Vp + tp) * 12 + c] = {M[row][2tp][c], M[row][2tp+1][c]}.
+// =====================================================================================================================
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 p, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mul2s(u64 a, float s) { return mul2(a, pk2(s, s)); }
+
+#define DMSA_ROW_UPDATE2(t)                                                                                              \
+    if ((t) != tprev) {                                                                                                 \
+        const ulonglong2* Mp = reinterpret_cast<const ulonglong2*>(Mv + (size_t)(unsigned)(t) * (size_t)rowbytes);      \
+        _Pragma("unroll") for (int c_ = 0; c_ < 6; ++c_) {                                                              \
+            const ulonglong2 q_ = __ldg(Mp + c_);                                                                       \
+            m[2 * c_] = q_.x;                                                                                           \
+            m[2 * c_ + 1] = q_.y;                                                                                       \
+        }                                                                                                               \
+        tprev = (t);                                                                                                    \
+    }
+// one row of Matrix4f * Vector4f for the vector pair: ((m0 x + m1 y) + m2 z) + m3, products packed, their adds scalar
+#define DMSA_XROW2(b, r, OUT)                                                                                            \
+    {                                                                                                                   \
+        const u64 p0_ = mul2s(m[(b)], (r).x), p1_ = mul2s(m[(b) + 1], (r).y), p2_ = mul2s(m[(b) + 2], (r).z);           \
+        float p0a, p0b, p1a, p1b, p2a, p2b;                                                                             \
+        upk2(p0_, p0a, p0b);                                                                                            \
+        upk2(p1_, p1a, p1b);                                                                                            \
+        upk2(p2_, p2a, p2b);                                                                                            \
+        const float qa_ = fadd_(fadd_(p0a, p1a), p2a);                                                                  \
+        const float qb_ = fadd_(fadd_(p0b, p1b), p2b);                                                                  \
+        OUT = add2(pk2(qa_, qb_), m[(b) + 3]);                                                                          \
+    }
+// a0 + (a1 + a2) on both halves of three packed products (Eigen's 3-element redux order)
+#define DMSA_DOT3_2(P0, P1, P2, OUTA, OUTB)                                                                              \
+    {                                                                                                                   \
+        float a0_, b0_, a1_, b1_, a2_, b2_;                                                                             \
+        upk2(P0, a0_, b0_);                                                                                             \
+        upk2(P1, a1_, b1_);                                                                                             \
+        upk2(P2, a2_, b2_);                                                                                             \
+        OUTA = fadd_(a0_, fadd_(a1_, a2_));                                                                             \
+        OUTB = fadd_(b0_, fadd_(b1_, b2_));                                                                             \
+    }
+
+struct PairSums {
+    double x0, y0, z0, x1, y1, z1;
+};
+__device__ __forceinline__ void pass_sum2(const CostArgs& a, const float4* __restrict__ srec, int count, int tp, PairSums& S) {
+    S.x0 = S.y0 = S.z0 = S.x1 = S.y1 = S.z1 = 0.0;
+    int tprev = -1;
+    u64 m[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) m[c] = 0ull;
+    const char* __restrict__ Mv = reinterpret_cast<const char*>(a.Mpair) + (size_t)tp * 96u;
+    const unsigned rowbytes = (unsigned)a.Vp * 96u;
+#define DMSA_SUM_BODY2(jj)                   \
+    {                                        \
+        const float4 r = srec[(jj)];         \
+        const int t = __float_as_int(r.w);   \
+        DMSA_ROW_UPDATE2(t)                  \
+        u64 X, Y, Z;                         \
+        DMSA_XROW2(0, r, X)                  \
+        DMSA_XROW2(4, r, Y)                  \
+        DMSA_XROW2(8, r, Z)                  \
+        float lo, hi;                        \
+        upk2(X, lo, hi);                     \
+        S.x0 += (double)lo;                  \
+        S.x1 += (double)hi;                  \
+        upk2(Y, lo, hi);                     \
+        S.y0 += (double)lo;                  \
+        S.y1 += (double)hi;                  \
+        upk2(Z, lo, hi);                     \
+        S.z0 += (double)lo;                  \
+        S.z1 += (double)hi;                  \
+    }
+    int j = 0;
+    for (; j + 4 <= count; j += 4) {
+        DMSA_SUM_BODY2(j)
+        DMSA_SUM_BODY2(j + 1)
+        DMSA_SUM_BODY2(j + 2)
+        DMSA_SUM_BODY2(j + 3)
+    }
+    for (; j < count; ++j) DMSA_SUM_BODY2(j)
+#undef DMSA_SUM_BODY2
+}
+__device__ __forceinline__ void pass_quad2(const CostArgs& a, const float4* __restrict__ srec, int count, int tp, int g, u64 MX, u64 MY, u64 MZ,
+                                           double& acc0, double& acc1) {
+    const float* __restrict__ I = a.info + 9 * (size_t)g;
+    const float i0 = __ldg(I + 0), i1 = __ldg(I + 1), i2 = __ldg(I + 2), i3 = __ldg(I + 3), i4 = __ldg(I + 4), i5 = __ldg(I + 5), i6 = __ldg(I + 6),
+                i7 = __ldg(I + 7), i8 = __ldg(I + 8);
+    const float wk = __ldg(a.w + g);
+    acc0 = acc1 = 0.0;
+    int tprev = -1;
+    u64 m[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) m[c] = 0ull;
+    const char* __restrict__ Mv = reinterpret_cast<const char*>(a.Mpair) + (size_t)tp * 96u;
+    const unsigned rowbytes = (unsigned)a.Vp * 96u;
+#define DMSA_QUAD_BODY2(jj)                                                                  \
+    {                                                                                        \
+        const float4 r = srec[(jj)];                                                         \
+        const int t = __float_as_int(r.w);                                                   \
+        DMSA_ROW_UPDATE2(t)                                                                  \
+        u64 X, Y, Z;                                                                         \
+        DMSA_XROW2(0, r, X)                                                                  \
+        DMSA_XROW2(4, r, Y)                                                                  \
+        DMSA_XROW2(8, r, Z)                                                                  \
+        const u64 d0 = sub2(X, MX), d1 = sub2(Y, MY), d2 = sub2(Z, MZ);                      \
+        const u64 t0 = mul2s(d0, wk), t1 = mul2s(d1, wk), t2 = mul2s(d2, wk);                \
+        float r0a, r0b, r1a, r1b, r2a, r2b, sa, sb;                                          \
+        DMSA_DOT3_2(mul2s(t0, i0), mul2s(t1, i3), mul2s(t2, i6), r0a, r0b)                   \
+        DMSA_DOT3_2(mul2s(t0, i1), mul2s(t1, i4), mul2s(t2, i7), r1a, r1b)                   \
+        DMSA_DOT3_2(mul2s(t0, i2), mul2s(t1, i5), mul2s(t2, i8), r2a, r2b)                   \
+        DMSA_DOT3_2(mul2(pk2(r0a, r0b), d0), mul2(pk2(r1a, r1b), d1), mul2(pk2(r2a, r2b), d2), sa, sb) \
+        acc0 += (double)sa;                                                                  \
+        acc1 += (double)sb;                                                                  \
+    }
+    int j = 0;
+    for (; j + 4 <= count; j += 4) {
+        DMSA_QUAD_BODY2(j)
+        DMSA_QUAD_BODY2(j + 1)
+        DMSA_QUAD_BODY2(j + 2)
+        DMSA_QUAD_BODY2(j + 3)
+    }
+    for (; j < count; ++j) DMSA_QUAD_BODY2(j)
+#undef DMSA_QUAD_BODY2
+}
+
+// thread -> vector pair; threads beyond the last pair keep a valid table column and process no members
+struct PairMap {
+    int tp;
+    bool has0, has1;
+};
+__device__ __forceinline__ PairMap pair_map(const CostArgs& a) {
+    PairMap pm;
+    pm.tp = threadIdx.x;
+    pm.has0 = 2 * pm.tp < a.V;
+    pm.has1 = 2 * pm.tp + 1 < a.V;
+    if (!pm.has0) pm.tp = (a.V - 1) >> 1;
+    return pm;
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_fused2(CostArgs a, int G) {
+    __shared__ __align__(128) float4 srec[COST_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
+    if ((int)blockIdx.x >= G) return;
+    const int g = a.order[blockIdx.x];
+    const int kind = a.cell_kind[g];
+    if (kind == 2) return;
+    const PairMap pm = pair_map(a);
+    double* __restrict__ Eg = a.E + (size_t)g * a.Vld + 2 * threadIdx.x;
+    if (kind == 0) {
+        if (pm.has0) Eg[0] = 0.0;
+        if (pm.has1) Eg[1] = 0.0;
+        return;
+    }
+    const int n = a.cell_n[g];
+    stage_records(srec, a.rec + a.cell_start[g], n, &bar);
+    const int cnt = pm.has0 ? n : 0;
+    PairSums S;
+    pass_sum2(a, srec, cnt, pm.tp, S);
+    const float nf = (float)n;
+    const u64 MX = pk2(fdiv_((float)S.x0, nf), fdiv_((float)S.x1, nf));  // DmsaOptimizer.h:254
+    const u64 MY = pk2(fdiv_((float)S.y0, nf), fdiv_((float)S.y1, nf));
+    const u64 MZ = pk2(fdiv_((float)S.z0, nf), fdiv_((float)S.z1, nf));
+    double q0, q1;
+    pass_quad2(a, srec, cnt, pm.tp, g, MX, MY, MZ, q0, q1);
+    if (pm.has0) Eg[0] = sqrt(fabs(q0));  // :267
+    if (pm.has1) Eg[1] = sqrt(fabs(q1));
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
+    __shared__ __align__(128) float4 srec[COST_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
+    const int c = blockIdx.x;
+    if (c >= *a.n_chunks) return;
+    const PairMap pm = pair_map(a);
+    const Chunk ch = a.chunks[c];
+    stage_records(srec, a.rec + ch.start, ch.count, &bar);
+    PairSums S;
+    pass_sum2(a, srec, pm.has0 ? ch.count : 0, pm.tp, S);
+    double* __restrict__ Sp = a.S_part + (size_t)c * 3 * a.Vld + 2 * threadIdx.x;
+    if (pm.has0) {
+        Sp[0] = S.x0;
+        Sp[a.Vld] = S.y0;
+        Sp[2 * (size_t)a.Vld] = S.z0;
+    }
+    if (pm.has1) {
+        Sp[1] = S.x1;
+        Sp[a.Vld + 1] = S.y1;
+        Sp[2 * (size_t)a.Vld + 1] = S.z1;
+    }
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_quad2(CostArgs a) {
+    __shared__ __align__(128) float4 srec[COST_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ int s_last;
+    const int c = blockIdx.x;
+    if (c >= *a.n_chunks) return;
+    const PairMap pm = pair_map(a);
+    const Chunk ch = a.chunks[c];
+    const int g = ch.cell;
+    stage_records(srec, a.rec + ch.start, ch.count, &bar);
+    const int nc = a.nchunk[g], o = ch.first;
+    const float nf = (float)a.cell_n[g];
+    const size_t st3 = (size_t)3 * a.Vld;
+    // (an odd V leaves the last thread's second half on a padding slot of S_part: computed, never stored)
+    const double* __restrict__ Sp = a.S_part + (size_t)o * st3 + 2 * pm.tp;
+    const double2 sx = reduce_chunks2(Sp, nc, st3), sy = reduce_chunks2(Sp + a.Vld, nc, st3), sz = reduce_chunks2(Sp + 2 * (size_t)a.Vld, nc, st3);
+    const u64 MX = pk2(fdiv_((float)sx.x, nf), fdiv_((float)sx.y, nf));
+    const u64 MY = pk2(fdiv_((float)sy.x, nf), fdiv_((float)sy.y, nf));
+    const u64 MZ = pk2(fdiv_((float)sz.x, nf), fdiv_((float)sz.y, nf));
+    double q0, q1;
+    pass_quad2(a, srec, pm.has0 ? ch.count : 0, pm.tp, g, MX, MY, MZ, q0, q1);
+    double* __restrict__ Qc = a.Q + (size_t)c * a.Vld + 2 * threadIdx.x;
+    if (pm.has0) Qc[0] = q0;
+    if (pm.has1) Qc[1] = q1;
+    if (!last_block_of_set(a.done + g, nc, &s_last)) return;
+    double* __restrict__ Eg = a.E + (size_t)g * a.Vld + 2 * threadIdx.x;
+    const double2 qs = reduce_chunks2(a.Q + (size_t)o * a.Vld + 2 * pm.tp, nc, (size_t)a.Vld);
+    if (pm.has0) Eg[0] = sqrt(fabs(qs.x));
+    if (pm.has1) Eg[1] = sqrt(fabs(qs.y));
+    if (threadIdx.x == 0) a.done[g] = 0;
 }
 
 // per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): COLSUM_PARTS row slices per vector, fixed reduction order

@@ -28,6 +28,7 @@ struct PoseBatch {
     double* globT_t;       // [(k*3+a)*Vld + v]
     double* quat_t;        // [(k*4+c)*Vld + v]
     double* extra;         // [E][Vld] additional residual rows (may be null)
+    float* Mpair;          // pair-interleaved second copy of the table (may be null)
 };
 
 struct TrajTiming {
@@ -74,6 +75,16 @@ __global__ void k_make_ls_batch(const double* __restrict__ p, const double* __re
     if (i >= 9 * P) return;
     int v = i / P, k = i % P;
     out[i] = p[k] + 0.1 * (double)(v + 1) * step[k];
+}
+
+// second copy of a table entry in the pair-interleaved layout read by the pair-packed cost kernels:
+// Mpair[((row * Vld/2 + v/2) * 12 + c) * 2 + (v & 1)] = M[row][v][c]
+__device__ __forceinline__ void store_pair_entry(float* __restrict__ Mpair, int row, int v, int Vld, const float4& r0, const float4& r1, const float4& r2) {
+    if (Mpair == nullptr) return;
+    float* b = Mpair + ((size_t)row * (Vld >> 1) + (v >> 1)) * 24 + (v & 1);
+    b[0] = r0.x; b[2] = r0.y; b[4] = r0.z; b[6] = r0.w;
+    b[8] = r1.x; b[10] = r1.y; b[12] = r1.z; b[14] = r1.w;
+    b[16] = r2.x; b[18] = r2.y; b[20] = r2.z; b[22] = r2.w;
 }
 
 // One block per parameter vector.  Shared memory: n * (9 + 9 + 3 + 3) doubles.
@@ -139,11 +150,13 @@ __global__ void k_pose_chain(PoseBatch pb, float* __restrict__ Mtab, ImuFactors 
             // MapManagement.h:133-138: currRot = axang2rotm(globalPoses.Orientations.col(k)).cast<float>()
             Mat3 Rr = so3_exp(o);
             float* M = Mtab + ((size_t)k * Vld + v) * 12;
+            float4 rows[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                float4 row = make_float4((float)Rr.m[3 * r], (float)Rr.m[3 * r + 1], (float)Rr.m[3 * r + 2], (float)sT[3 * k + r]);
-                reinterpret_cast<float4*>(M)[r] = row;
+                rows[r] = make_float4((float)Rr.m[3 * r], (float)Rr.m[3 * r + 1], (float)Rr.m[3 * r + 2], (float)sT[3 * k + r]);
+                reinterpret_cast<float4*>(M)[r] = rows[r];
             }
+            store_pair_entry(pb.Mpair, k, v, Vld, rows[0], rows[1], rows[2]);
         }
     }
     if (MODEL == 1 && threadIdx.x == 0) {  // identity row (unused by keyframe points, kept for uniformity)
@@ -151,6 +164,7 @@ __global__ void k_pose_chain(PoseBatch pb, float* __restrict__ Mtab, ImuFactors 
         M[0] = make_float4(1.f, 0.f, 0.f, 0.f);
         M[1] = make_float4(0.f, 1.f, 0.f, 0.f);
         M[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+        store_pair_entry(pb.Mpair, n, v, Vld, M[0], M[1], M[2]);
     }
     if (pb.extra == nullptr) return;
     __syncthreads();
@@ -260,6 +274,7 @@ __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ M
         M[0] = make_float4(1.f, 0.f, 0.f, 0.f);
         M[1] = make_float4(0.f, 1.f, 0.f, 0.f);
         M[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+        store_pair_entry(pb.Mpair, j, v, Vld, M[0], M[1], M[2]);
         return;
     }
     // orientation (:194-198, :570-591)
@@ -301,9 +316,13 @@ __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ M
     // :221-225
     Mat3 R = so3_exp(aa);
     float4* M = reinterpret_cast<float4*>(Mtab + ((size_t)j * Vld + v) * 12);
-    M[0] = make_float4((float)R.m[0], (float)R.m[1], (float)R.m[2], (float)T[0]);
-    M[1] = make_float4((float)R.m[3], (float)R.m[4], (float)R.m[5], (float)T[1]);
-    M[2] = make_float4((float)R.m[6], (float)R.m[7], (float)R.m[8], (float)T[2]);
+    const float4 r0 = make_float4((float)R.m[0], (float)R.m[1], (float)R.m[2], (float)T[0]);
+    const float4 r1 = make_float4((float)R.m[3], (float)R.m[4], (float)R.m[5], (float)T[1]);
+    const float4 r2 = make_float4((float)R.m[6], (float)R.m[7], (float)R.m[8], (float)T[2]);
+    M[0] = r0;
+    M[1] = r1;
+    M[2] = r2;
+    store_pair_entry(pb.Mpair, j, v, Vld, r0, r1, r2);
 }
 
 }  // namespace dmsa

@@ -208,6 +208,10 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
  * kernel (the iteration then has no host round trip between the Jacobian pass and the line search), 1 = host solver.
  * Both run the same operation sequence (LU with partial pivoting, explicit inverse, ascending accumulation): bit-identical. */
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode);
+/* Cost kernels of the forward-difference batch (V = P + 1 vectors): 1 (default) = two vectors per thread with Blackwell's
+ * packed FP32x2 instructions (FMUL2 / FADD2; every multiply->add edge keeps a scalar side, so nothing is fused), 0 = one
+ * vector per thread.  Same rounding sequence per value: bit-identical results. */
+int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode);
 /* The device LM step on a HOST copy of [H | g | err0] (n_params <= 1024); validation twin of dmsa_b200_lm_solve(.., 1, ..). */
 int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step,
                               int32_t* has_nan);

@@ -544,3 +544,32 @@ def test_device_and_host_solver_iterations_agree_bitwise(name):
         assert a["stop_reason"] == b["stop_reason"] and a["best_step"] == b["best_step"] and a["error0"] == b["error0"]
         assert np.array_equal(a["step"], b["step"]) and np.array_equal(a["ls_cost"], b["ls_cost"])
     assert np.array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])
+def test_pair_packed_cost_kernels_equal_the_scalar_kernels_bitwise(name):
+    """The forward-difference batch runs two parameter vectors per thread with packed FP32x2 instructions (FMUL2 / FADD2,
+    no fused multiply-add: every multiply->add edge keeps a scalar side).  Same rounding sequence per value as the
+    one-vector-per-thread kernels: e0, J, H, g and whole iterations are bit-identical."""
+    res = []
+    for mode in (1, 0):
+        win, traj, om, s, so = make_pair(name)
+        traj.setPairMode(mode)
+        traj.centralize()
+        traj.updateGlobalPoints()
+        traj.buildSets(s)
+        cj = traj.costJacobian(with_rows=True)
+        p = traj.getPoseParameters()
+        rng = np.random.default_rng(5)
+        batch = p[None, :] + 1e-3 * rng.standard_normal((19, p.size))  # odd V > 16: the last thread holds a single vector
+        e = traj.evalCost(batch)
+        it = [traj.iteration(s) for _ in range(2)]
+        res.append((cj, e, it, traj.getPoseParameters()))
+    a, b = res
+    for k in ("e0", "J", "H", "g"):
+        assert np.array_equal(a[0][k], b[0][k]), k
+    assert np.array_equal(a[1], b[1])
+    for x, y in zip(a[2], b[2]):
+        assert x["error0"] == y["error0"] and x["best_step"] == y["best_step"]
+        assert np.array_equal(x["step"], y["step"]) and np.array_equal(x["ls_cost"], y["ls_cost"])
+    assert np.array_equal(a[3], b[3])
