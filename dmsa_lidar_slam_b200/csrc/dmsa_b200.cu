@@ -851,10 +851,23 @@ int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
     const int P = 6 * (ctx->poses.n - 1), R = ctx->G + numExtra(ctx), Vld = ctx->curVld;
     const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
     const double inv_h = 1.0 / h;  // one_div_incr, DmsaOptimizer.h:210
+    const int n1 = P + 1;
+    if (n1 <= JD_MAXN) {
+        // FP64 tensor cores (DMMA m8n8k4): one block per row range keeps every upper-triangular output tile in registers
+        int nblk = std::max(1, std::min(148, (R + JD_ROWS - 1) / JD_ROWS));
+        int rpb = ((R + nblk - 1) / nblk + JD_ROWS - 1) / JD_ROWS * JD_ROWS;
+        nblk = (R + rpb - 1) / rpb;
+        CK(ctx->d_jpart.ensure((size_t)nblk * n1 * n1));
+        ProfScope prof_(ctx, PROF_JTJ);
+        LAUNCH(k_jtj_dmma, nblk, JD_T, 0, ctx->d_E.p, R, Vld, P, inv_h, rpb, ctx->d_jpart.p);
+        LAUNCH(k_jtj_reduce8, cdiv((size_t)n1 * n1, 32), dim3(32, 8), 0, ctx->d_jpart.p, nblk, P, hg_dev);
+        CK(cudaGetLastError());
+        return 0;
+    }
     int nsplit = std::max(1, std::min(64, (R + 127) / 128));  // enough blocks to fill the chip: the product is only ~0.2 GFLOP
     int rps = ((R + nsplit - 1) / nsplit + JTJ_T - 1) / JTJ_T * JTJ_T;
     nsplit = (R + rps - 1) / rps;
-    const int n1 = P + 1, nt = (n1 + JTJ_T - 1) / JTJ_T;
+    const int nt = (n1 + JTJ_T - 1) / JTJ_T;
     CK(ctx->d_jpart.ensure((size_t)nsplit * n1 * n1));
     CK(cudaMemsetAsync(ctx->d_jpart.p, 0, (size_t)nsplit * n1 * n1 * sizeof(double), ctx->stream));
     dim3 grid(nt * (nt + 1) / 2, nsplit);

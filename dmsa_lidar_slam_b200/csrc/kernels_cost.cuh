@@ -755,6 +755,108 @@ __global__ void k_jtj_reduce(const double* __restrict__ part, int nsplit, int P,
         out[(size_t)P * P + P] = s;
 }
 
+// ---- [J e0]^T [J e0] on the FP64 tensor cores (n1 = P + 1 <= 128) -----------------------------------------------
+// The one genuine GEMM of the path: C = A^T A with A = [J | e0] (R x n1).  mma.sync.aligned.m8n8k4 (DMMA): the "A" operand
+// is an 8 x 4 tile of A^T, i.e. A[k0 + t][8 ti + g], the "B" operand the 4 x 8 tile A[k0 + t][8 tj + g] (g = lane / 4,
+// t = lane % 4): both are the same shared-memory access pattern.  A block owns a row range, stages 32-row panels of A in
+// shared memory (row stride 132 doubles: conflict-free 8-byte fragment loads) and keeps ALL upper-triangular 8 x 8 output
+// tiles in registers (<= 8 tiles per warp, 16 warps); per-block partials are reduced in fixed order by k_jtj_reduce8.
+#define JD_ROWS 32
+#define JD_LD 132
+#define JD_T 512
+#define JD_MAXN 128
+__global__ void __launch_bounds__(JD_T, 1) k_jtj_dmma(const double* __restrict__ E, int R, int Vld, int P, double inv_h, int rows_per_block,
+                                                       double* __restrict__ part /*[block][n1*n1]*/) {
+    __shared__ __align__(16) double As[JD_ROWS * JD_LD];
+    __shared__ unsigned char tij[JD_MAXN / 8 * (JD_MAXN / 8 + 1) / 2][2];
+    const int n1 = P + 1, nt = (n1 + 7) >> 3, ntile = nt * (nt + 1) / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int q = threadIdx.x; q < ntile; q += JD_T) {  // upper-triangular tile list, row by row
+        int rem = q, ti = 0;
+        while (rem >= nt - ti) {
+            rem -= nt - ti;
+            ++ti;
+        }
+        tij[q][0] = (unsigned char)ti;
+        tij[q][1] = (unsigned char)(ti + rem);
+    }
+    double acc[8][2];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) acc[m][0] = acc[m][1] = 0.0;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+    for (int rb = r0; rb < r1; rb += JD_ROWS) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < JD_ROWS * JD_MAXN; idx += JD_T) {
+            const int rr = idx >> 7, cc = idx & 127, r = rb + rr;
+            double v = 0.0;
+            if (r < r1 && cc < n1) {
+                const double e0 = E[(size_t)r * Vld];
+                v = cc < P ? inv_h * (E[(size_t)r * Vld + cc + 1] - e0) : e0;  // DmsaOptimizer.h:227 | e0
+            }
+            As[rr * JD_LD + cc] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const int q = warp + (JD_T / 32) * m;
+            if (q < ntile) {  // warp-uniform
+                const double* __restrict__ pa = As + t * JD_LD + 8 * tij[q][0] + g;
+                const double* __restrict__ pb = As + t * JD_LD + 8 * tij[q][1] + g;
+#pragma unroll
+                for (int k0 = 0; k0 < JD_ROWS; k0 += 4) {
+                    const double a = pa[k0 * JD_LD], b = pb[k0 * JD_LD];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[m][0]), "+d"(acc[m][1])
+                                 : "d"(a), "d"(b));
+                }
+            }
+        }
+    }
+    double* __restrict__ out = part + (size_t)blockIdx.x * n1 * n1;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const int q = warp + (JD_T / 32) * m;
+        if (q < ntile) {
+            const int i = 8 * tij[q][0] + g, j = 8 * tij[q][1] + 2 * t;
+            if (i < n1 && j < n1) out[(size_t)i * n1 + j] = acc[m][0];
+            if (i < n1 && j + 1 < n1) out[(size_t)i * n1 + j + 1] = acc[m][1];
+        }
+    }
+}
+// out = [H (P*P row-major) | g (P) | err0] from the per-block partials of k_jtj_dmma (8 x 8 tiles, lower tiles mirrored).
+// blockDim = (32, 8): 32 consecutive output elements x 8 interleaved partial streams (partial k goes to stream k % 8,
+// ascending k), the streams are combined in ascending order: fixed summation order, coalesced 256-byte reads.
+__global__ void __launch_bounds__(256) k_jtj_reduce8(const double* __restrict__ part, int nsplit, int P, double* __restrict__ out) {
+    __shared__ double red[8][33];
+    const int n1 = P + 1;
+    const int q = blockIdx.x * 32 + threadIdx.x;
+    const bool ok = q < n1 * n1;
+    const int i = ok ? q / n1 : 0, j = ok ? q % n1 : 0;
+    int ii = i, jj = j;
+    if ((i >> 3) > (j >> 3)) {
+        ii = j;
+        jj = i;
+    }
+    double s = 0.0;
+    if (ok) {
+        const double* __restrict__ src = part + (size_t)ii * n1 + jj;
+#pragma unroll 4
+        for (int k = threadIdx.y; k < nsplit; k += 8) s += src[(size_t)k * n1 * n1];
+    }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y != 0 || !ok) return;
+    double tsum = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tsum += red[y][threadIdx.x];
+    if (i < P && j < P)
+        out[(size_t)i * P + j] = tsum;
+    else if (i < P && j == P)
+        out[(size_t)P * P + i] = tsum;
+    else if (i == P && j == P)
+        out[(size_t)P * P + P] = tsum;
+}
+
 // ---- base-pose world points (updateGlobalPoints): scan points through column v of the table ----------------------
 // ContinuousTrajectory.h:137-155 | MapManagement.h:140-147
 __global__ void k_transform_points(const float4* __restrict__ local, const int* __restrict__ tid, int n, const float4* __restrict__ Mtab, int Vld,
