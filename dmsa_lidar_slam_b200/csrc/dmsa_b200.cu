@@ -200,7 +200,8 @@ struct dmsa_b200_ctx {
     bool solveGeneral = false;  // force the general one-block kernel (any P <= 1024) instead of the P <= 128 fast path
     long long* solveClk = nullptr;  // debug: device buffer of phase cycle stamps (dmsa_b200_lm_solve_device with DMSA_B200_SOLVE_CLK=1)
     DBuf<int> d_biglist;  // sets with more than GAUSS_WARP_MAX members (+ the count at [cellCap])
-    DBuf<int> d_done;  // per-set completion counters of k_cost_quad (zeroed by the set build, self-resetting)
+    DBuf<int> d_done;  // per-set completion counters of k_cost_quad [0, cap] and k_cost_sum [cap + 1, 2 cap + 1] (zeroed by the set build, self-resetting)
+    DBuf<float> d_mu;  // means of the sets cut into more than MEAN_INLINE_MAX chunks [(g*3 + a) * Vld + v]
     size_t chunkBound = 0;
 
     // host mirrors; the small per-iteration read-backs / uploads go through one pinned block so that
@@ -566,7 +567,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     CK(ctx->d_cell_w.ensure(cap));
     CK(ctx->d_nchunk.ensure((size_t)cap + 1));
     CK(ctx->d_chunk_off.ensure((size_t)cap + 1));
-    CK(ctx->d_done.ensure((size_t)cap + 1));
+    CK(ctx->d_done.ensure(2 * ((size_t)cap + 1)));
     CKRC(ensureCub(ctx, N, cap));
     CellStore cs;
     cs.start = ctx->d_cell_start.p;
@@ -734,7 +735,7 @@ phase2:
         LAUNCH_ON(s2, k_gauss_list, cdiv(G, 256), 256, 0, cs, G, ctx->d_biglist.p, cnt);
         LAUNCH_ON(s2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
         CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), s2));
-        CK(cudaMemsetAsync(ctx->d_done.p, 0, ((size_t)G + 1) * sizeof(int), s2));
+        CK(cudaMemsetAsync(ctx->d_done.p, 0, 2 * ((size_t)cap + 1) * sizeof(int), s2));
         LAUNCH_ON(s2, k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
         LAUNCH_ON(s2, k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
         CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), s2));
@@ -757,6 +758,7 @@ int runCost(dmsa_b200_ctx* ctx) {
     CK(ctx->d_S.ensure(ctx->chunkBound * 3 * Vld));
     CK(ctx->d_Q.ensure(ctx->chunkBound * Vld));
     CK(ctx->d_E.ensure((size_t)(G + E) * Vld));
+    CK(ctx->d_mu.ensure((size_t)G * 3 * Vld));
     CostArgs a;
     a.chunks = ctx->d_chunks.p;
     a.n_chunks = ctx->d_chunk_off.p + G;
@@ -777,6 +779,8 @@ int runCost(dmsa_b200_ctx* ctx) {
     a.chunk_off = ctx->d_chunk_off.p;
     a.S_part = ctx->d_S.p;
     a.done = ctx->d_done.p;
+    a.done1 = ctx->d_done.p + ctx->cellCap + 1;
+    a.mu = ctx->d_mu.p;
     a.Q = ctx->d_Q.p;
     a.E = ctx->d_E.p;
     a.order = ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES;
@@ -1196,7 +1200,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_biglist); REL(d_mom); REL(d_solve); REL(d_iter);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_mom); REL(d_solve); REL(d_iter);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);

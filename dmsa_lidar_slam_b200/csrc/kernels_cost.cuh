@@ -39,7 +39,9 @@ struct CostArgs {
     const int* nchunk;       // [g]
     const int* chunk_off;    // [g]
     double* S_part;          // partial sums   [(c*3 + a) * Vld + v]
+    float* mu;               // means of the sets with more than MEAN_INLINE_MAX chunks [(g*3 + a) * Vld + v] (written by pass 1)
     int* done;               // [g] chunk blocks of set g that finished pass 2 (self-resetting counter)
+    int* done1;              // [g] same for pass 1 (sets with more than MEAN_INLINE_MAX chunks only)
     double* Q;               // partial quadratic forms [c * Vld + v]
     double* E;               // residuals      [g * Vld + v]
 };
@@ -299,31 +301,56 @@ __global__ void __launch_bounds__(1024) k_cost_seq(CostArgs a, int G) {
 }
 
 #define COST_RED_Y 8
-// Fixed-order reduction of a big set's chunk partials: COST_RED_Y interleaved partial sums (chunk c goes to slot
-// c % COST_RED_Y, ascending c), then the slots in ascending order.
+#define MEAN_INLINE_MAX 128  // sets with at most this many chunks (65 536 members): pass 2 recomputes the mean per chunk block (measured
+                             // cheaper than a hand-over); beyond it the redundant reads would grow quadratically, pass 1 hands the mean over
+// Fixed-order reduction of a big set's chunk partials: COST_RED_Y interleaved partial sums (chunk c goes to stream
+// c % COST_RED_Y, ascending c), then the streams in ascending order.
 __device__ __forceinline__ double reduce_chunks(const double* __restrict__ part, int nc, size_t stride) {
-    double t = 0.0;
-#pragma unroll 1
-    for (int y = 0; y < COST_RED_Y; ++y) {
-        double s = 0.0;
-        for (int c = y; c < nc; c += COST_RED_Y) s += __ldcg(part + (size_t)c * stride);
-        t += s;
+    double s[COST_RED_Y];
+#pragma unroll
+    for (int y = 0; y < COST_RED_Y; ++y) s[y] = 0.0;
+    int c = 0;
+    for (; c + COST_RED_Y <= nc; c += COST_RED_Y) {  // eight independent loads in flight, one per stream
+#pragma unroll
+        for (int y = 0; y < COST_RED_Y; ++y) s[y] += __ldcg(part + (size_t)(c + y) * stride);
     }
+#pragma unroll
+    for (int y = 0; y < COST_RED_Y; ++y)
+        if (c + y < nc) s[y] += __ldcg(part + (size_t)(c + y) * stride);
+    double t = 0.0;
+#pragma unroll
+    for (int y = 0; y < COST_RED_Y; ++y) t += s[y];
     return t;
 }
 // the same reduction for two adjacent vectors at once (16-byte loads; identical order per component)
 __device__ __forceinline__ double2 reduce_chunks2(const double* __restrict__ part, int nc, size_t stride) {
     double2 t = make_double2(0.0, 0.0);
 #pragma unroll 1
-    for (int y = 0; y < COST_RED_Y; ++y) {
-        double2 s = make_double2(0.0, 0.0);
-        for (int c = y; c < nc; c += COST_RED_Y) {
-            const double2 q = __ldcg(reinterpret_cast<const double2*>(part + (size_t)c * stride));
-            s.x += q.x;
-            s.y += q.y;
+    for (int h = 0; h < COST_RED_Y; h += 4) {  // four streams (loads in flight) at a time: half the registers of eight
+        double2 s[4];
+#pragma unroll
+        for (int y = 0; y < 4; ++y) s[y] = make_double2(0.0, 0.0);
+        int c = 0;
+        for (; c + COST_RED_Y <= nc; c += COST_RED_Y) {
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                const double2 q = __ldcg(reinterpret_cast<const double2*>(part + (size_t)(c + h + y) * stride));
+                s[y].x += q.x;
+                s[y].y += q.y;
+            }
         }
-        t.x += s.x;
-        t.y += s.y;
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+            if (c + h + y < nc) {
+                const double2 q = __ldcg(reinterpret_cast<const double2*>(part + (size_t)(c + h + y) * stride));
+                s[y].x += q.x;
+                s[y].y += q.y;
+            }
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+            t.x += s[y].x;
+            t.y += s[y].y;
+        }
     }
     return t;
 }
@@ -343,6 +370,7 @@ template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ int s_last;
     const int c = blockIdx.x;
     if (c >= *a.n_chunks) return;
     const LaneMap lm = lane_map<PACKED>(a);
@@ -353,11 +381,27 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
     sx = combine_subs<PACKED>(a, lm, sx);
     sy = combine_subs<PACKED>(a, lm, sy);
     sz = combine_subs<PACKED>(a, lm, sz);
-    if (lm.active && lm.sub == 0) {
+    const bool writer = lm.active && lm.sub == 0;
+    if (writer) {
         a.S_part[((size_t)c * 3 + 0) * a.Vld + lm.v] = sx;
         a.S_part[((size_t)c * 3 + 1) * a.Vld + lm.v] = sy;
         a.S_part[((size_t)c * 3 + 2) * a.Vld + lm.v] = sz;
     }
+    // sets cut into many chunks: the block that finishes last reduces the partials to the set's mean once (pass 2 would
+    // otherwise repeat that reduction in every one of the set's chunk blocks)
+    const int g = ch.cell, nc = a.nchunk[g];
+    if (nc <= MEAN_INLINE_MAX) return;
+    if (!last_block_of_set(a.done1 + g, nc, &s_last)) return;
+    if (writer) {
+        const float nf = (float)a.cell_n[g];
+        const size_t st3 = (size_t)3 * a.Vld;
+        const double* __restrict__ Sp = a.S_part + (size_t)ch.first * st3 + lm.v;
+        float* __restrict__ mu = a.mu + (size_t)g * st3 + lm.v;
+        mu[0] = fdiv_((float)reduce_chunks(Sp, nc, st3), nf);  // DmsaOptimizer.h:254
+        mu[a.Vld] = fdiv_((float)reduce_chunks(Sp + a.Vld, nc, st3), nf);
+        mu[2 * (size_t)a.Vld] = fdiv_((float)reduce_chunks(Sp + 2 * (size_t)a.Vld, nc, st3), nf);
+    }
+    if (threadIdx.x == 0) a.done1[g] = 0;  // ready for the next launch
 }
 
 // Big sets, pass 2: mean = float(sum over the set's chunks) / float(n) (DmsaOptimizer.h:254; every chunk block of the set
@@ -378,10 +422,18 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
     const int nc = a.nchunk[g], o = ch.first;
     const float nf = (float)a.cell_n[g];
     const size_t st3 = (size_t)3 * a.Vld;
-    const double* __restrict__ Sp = a.S_part + (size_t)o * st3 + lm.v;
-    const float mx = fdiv_((float)reduce_chunks(Sp, nc, st3), nf);
-    const float my = fdiv_((float)reduce_chunks(Sp + a.Vld, nc, st3), nf);
-    const float mz = fdiv_((float)reduce_chunks(Sp + 2 * (size_t)a.Vld, nc, st3), nf);
+    float mx, my, mz;
+    if (nc <= MEAN_INLINE_MAX) {
+        const double* __restrict__ Sp = a.S_part + (size_t)o * st3 + lm.v;
+        mx = fdiv_((float)reduce_chunks(Sp, nc, st3), nf);
+        my = fdiv_((float)reduce_chunks(Sp + a.Vld, nc, st3), nf);
+        mz = fdiv_((float)reduce_chunks(Sp + 2 * (size_t)a.Vld, nc, st3), nf);
+    } else {
+        const float* __restrict__ mu = a.mu + (size_t)g * st3 + lm.v;
+        mx = mu[0];
+        my = mu[a.Vld];
+        mz = mu[2 * (size_t)a.Vld];
+    }
     double acc = pass_quad<PACKED>(a, srec, lm.active ? ch.count : 0, lm, g, mx, my, mz);
     acc = combine_subs<PACKED>(a, lm, acc);
     const bool writer = lm.active && lm.sub == 0;
@@ -593,6 +645,7 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ int s_last;
     const int c = blockIdx.x;
     if (c >= *a.n_chunks) return;
     const PairMap pm = pair_map(a);
@@ -611,6 +664,23 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
         Sp[a.Vld + 1] = S.y1;
         Sp[2 * (size_t)a.Vld + 1] = S.z1;
     }
+    const int g = ch.cell, nc = a.nchunk[g];
+    if (nc <= MEAN_INLINE_MAX) return;
+    if (!last_block_of_set(a.done1 + g, nc, &s_last)) return;
+    if (pm.has0) {  // (an odd V: the second half of the last pair lands on a padding slot)
+        const float nf = (float)a.cell_n[g];
+        const size_t st3 = (size_t)3 * a.Vld;
+        const double* __restrict__ Sq = a.S_part + (size_t)ch.first * st3 + 2 * pm.tp;
+        float* __restrict__ mu = a.mu + (size_t)g * st3 + 2 * pm.tp;
+        const double2 sx = reduce_chunks2(Sq, nc, st3), sy = reduce_chunks2(Sq + a.Vld, nc, st3), sz = reduce_chunks2(Sq + 2 * (size_t)a.Vld, nc, st3);
+        mu[0] = fdiv_((float)sx.x, nf);
+        mu[1] = fdiv_((float)sx.y, nf);
+        mu[a.Vld] = fdiv_((float)sy.x, nf);
+        mu[a.Vld + 1] = fdiv_((float)sy.y, nf);
+        mu[2 * (size_t)a.Vld] = fdiv_((float)sz.x, nf);
+        mu[2 * (size_t)a.Vld + 1] = fdiv_((float)sz.y, nf);
+    }
+    if (threadIdx.x == 0) a.done1[g] = 0;
 }
 
 template <int MAXT, int MINB>
@@ -628,11 +698,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad2(CostArgs a) {
     const float nf = (float)a.cell_n[g];
     const size_t st3 = (size_t)3 * a.Vld;
     // (an odd V leaves the last thread's second half on a padding slot of S_part: computed, never stored)
-    const double* __restrict__ Sp = a.S_part + (size_t)o * st3 + 2 * pm.tp;
-    const double2 sx = reduce_chunks2(Sp, nc, st3), sy = reduce_chunks2(Sp + a.Vld, nc, st3), sz = reduce_chunks2(Sp + 2 * (size_t)a.Vld, nc, st3);
-    const u64 MX = pk2(fdiv_((float)sx.x, nf), fdiv_((float)sx.y, nf));
-    const u64 MY = pk2(fdiv_((float)sy.x, nf), fdiv_((float)sy.y, nf));
-    const u64 MZ = pk2(fdiv_((float)sz.x, nf), fdiv_((float)sz.y, nf));
+    u64 MX, MY, MZ;
+    if (nc <= MEAN_INLINE_MAX) {
+        const double* __restrict__ Sp = a.S_part + (size_t)o * st3 + 2 * pm.tp;
+        const double2 sx = reduce_chunks2(Sp, nc, st3), sy = reduce_chunks2(Sp + a.Vld, nc, st3), sz = reduce_chunks2(Sp + 2 * (size_t)a.Vld, nc, st3);
+        MX = pk2(fdiv_((float)sx.x, nf), fdiv_((float)sx.y, nf));
+        MY = pk2(fdiv_((float)sy.x, nf), fdiv_((float)sy.y, nf));
+        MZ = pk2(fdiv_((float)sz.x, nf), fdiv_((float)sz.y, nf));
+    } else {  // written by the last block of pass 1: adjacent floats of the pair, one 8-byte load per axis
+        const u64* __restrict__ mu2 = reinterpret_cast<const u64*>(a.mu + (size_t)g * st3) + pm.tp;
+        MX = mu2[0];
+        MY = mu2[a.Vp];
+        MZ = mu2[2 * (size_t)a.Vp];
+    }
     double q0, q1;
     pass_quad2(a, srec, pm.has0 ? ch.count : 0, pm.tp, g, MX, MY, MZ, q0, q1);
     double* __restrict__ Qc = a.Q + (size_t)c * a.Vld + 2 * threadIdx.x;
