@@ -107,12 +107,12 @@ struct HostPoses {
 // per-ISA clones: AVX-512 / AVX2 / baseline — element-wise IEEE arithmetic, identical results on every path)
 }  // namespace
 bool dmsa_host_lu_inverse(const std::vector<double>& A, int n, std::vector<double>& inv);
+bool dmsa_host_lm_step(const double* hg, int n, double lambda, double alpha, double* step);
 void dmsa_host_solver_arm();
 void dmsa_host_solver_disarm();
 bool dmsa_host_lu_solve(const std::vector<double>& A, int n, const double* b, std::vector<double>& x);
 bool dmsa_host_chol_solve(const std::vector<double>& A, int n, const double* b, std::vector<double>& x);
 namespace {
-inline bool lu_solve_inverse(const std::vector<double>& A, int n, std::vector<double>& inv) { return dmsa_host_lu_inverse(A, n, inv); }
 inline bool lu_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) { return dmsa_host_lu_solve(A, n, b, x); }
 inline bool chol_solve_vec(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) { return dmsa_host_chol_solve(A, n, b, x); }
 
@@ -719,10 +719,9 @@ phase2:
     CK(ctx->d_oval.ensure((size_t)2 * cap + 4 * ORDER_CLASSES));
     CK(ctx->d_biglist.ensure((size_t)cap + 1));
     CK(ctx->d_mom.ensure((size_t)6 * cap));
-    // Context's stream: the small sets (one warp each).  stream2, side by side: the compact list of the sets with more than
-    // GAUSS_WARP_MAX members and their statistics (one block each), plus the work decomposition of the cost kernels
-    // (set kinds, issue order, chunk list), which depends on the set sizes only.  Disjoint outputs; joined before the
-    // eigen finish.
+    // stream2: the compact list of the sets with more than GAUSS_WARP_MAX members and their statistics (one block each).
+    // Context's stream, side by side: the small sets (one warp each) and the work decomposition of the cost kernels (set
+    // kinds, issue order, chunk list), which depends on the set sizes only.  Disjoint outputs; joined before the eigen finish.
     ctx->chunkBound = (size_t)2 * N / CHUNK + (size_t)2 * N / FUSE_MAX + 2;  // big sets only
     CK(ctx->d_chunks.ensure(ctx->chunkBound));
     {
@@ -734,15 +733,15 @@ phase2:
         CK(cudaMemsetAsync(cnt, 0, sizeof(int), s2));
         LAUNCH_ON(s2, k_gauss_list, cdiv(G, 256), 256, 0, cs, G, ctx->d_biglist.p, cnt);
         LAUNCH_ON(s2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
-        CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), s2));
-        CK(cudaMemsetAsync(ctx->d_done.p, 0, 2 * ((size_t)cap + 1) * sizeof(int), s2));
-        LAUNCH_ON(s2, k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
-        LAUNCH_ON(s2, k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
-        CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), s2));
-        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p + ctx->cubPer, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, s2));
-        LAUNCH_ON(s2, k_chunk_fill, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
         CK(cudaEventRecord(ctx->evJoin, s2));
         LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G, ctx->d_mom.p);
+        CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_done.p, 0, 2 * ((size_t)cap + 1) * sizeof(int), ctx->stream));
+        LAUNCH(k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
+        LAUNCH(k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
+        CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), ctx->stream));
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, ctx->stream));
+        LAUNCH(k_chunk_fill, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
         LAUNCH(k_gaussian_fin, cdiv(G, 128), 128, 0, cs, G, ctx->d_mom.p);
     }
@@ -965,20 +964,14 @@ int lmSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, const do
 // H.diag += lambda; step = -alpha * H^-1 * (J^T e0); NaN guard; infinity-norm clamp      DmsaOptimizer.h:107-128
 // returns 1 if the step contains NaN
 int solveStep(const dmsa_b200_settings* st, const double* hg, int P, std::vector<double>& step, bool explicit_inverse = true) {
-    std::vector<double> H(hg, hg + (size_t)P * P), Hinv;
-    const double* g = hg + (size_t)P * P;
-    for (int i = 0; i < P; ++i) H[(size_t)i * P + i] += (double)st->lambda_diag;
     step.assign(P, 0.0);
     bool nan = false;
     if (explicit_inverse) {  // the reference's expression: (-alpha * H.inverse()) * (J^T e)
-        lu_solve_inverse(H, P, Hinv);
-        for (int a = 0; a < P; ++a) {
-            double s = 0;
-            for (int b = 0; b < P; ++b) s += (-st->step_length_optim * Hinv[(size_t)a * P + b]) * g[b];
-            step[a] = s;
-            if (std::isnan(s)) nan = true;
-        }
+        nan = dmsa_host_lm_step(hg, P, (double)st->lambda_diag, st->step_length_optim, step.data());
     } else {
+        std::vector<double> H(hg, hg + (size_t)P * P);
+        const double* g = hg + (size_t)P * P;
+        for (int i = 0; i < P; ++i) H[(size_t)i * P + i] += (double)st->lambda_diag;
         std::vector<double> x;
         if (!chol_solve_vec(H, P, g, x)) lu_solve_vec(H, P, g, x);
         for (int a = 0; a < P; ++a) {
@@ -1086,12 +1079,11 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
         ctx->err = "cudaStreamSynchronize failed before the LM solve";
         return DMSA_B200_ERR_CUDA;
     }
-    std::copy(pinHg(ctx), pinHg(ctx) + ctx->h_hg.size(), ctx->h_hg.begin());
-    error0 = ctx->h_hg[(size_t)P * P + P];
+    error0 = pinHg(ctx)[(size_t)P * P + P];
     ctx->lastErr0 = error0;
     {
         WallTimer ws{ctx, PROF_HOST_SOLVE};
-        nanStep = solveStep(st, ctx->h_hg.data(), P, step);
+        nanStep = solveStep(st, pinHg(ctx), P, step);
     }
     dmsa_host_solver_disarm();
     }

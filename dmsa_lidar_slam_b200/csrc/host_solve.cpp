@@ -150,13 +150,16 @@ void dmsa_host_solver_arm() {
 }
 void dmsa_host_solver_disarm() { g_pool.armed.store(0, std::memory_order_release); }
 
-static bool lu_solve_inverse_impl(const std::vector<double>& A, int n, std::vector<double>& inv) {
-    std::vector<double> a(A);
-    std::vector<int> piv(n);
+// LU + substitution of P*I into a cache-line aligned, padded block x (n x ldx, ldx a multiple of 8 doubles: the helper
+// threads own whole lines of every row).  a: n x n row-major, factorised in place.  Scratch lives in thread-local
+// buffers that are reused from call to call.
+static double* lu_inverse_padded(std::vector<double>& a, int n, int& ldx_out) {
+    thread_local std::vector<int> piv;
+    thread_local std::vector<double> xbuf;
+    piv.resize(n);
     lu_factor_impl(a, piv, n);
-    // right-hand sides in a cache-line aligned, padded block (ldx multiple of 8): the helper threads own whole lines
     const int ldx = (n + 7) / 8 * 8;
-    std::vector<double> xbuf((size_t)n * ldx + 8, 0.0);
+    xbuf.assign((size_t)n * ldx + 8, 0.0);
     double* x = xbuf.data();
     while (reinterpret_cast<uintptr_t>(x) & 63) ++x;
     for (int i = 0; i < n; ++i) x[(size_t)i * ldx + piv[i]] = 1.0;  // P * I
@@ -173,9 +176,35 @@ static bool lu_solve_inverse_impl(const std::vector<double>& A, int n, std::vect
     } else {
         lu_subst_block_impl(a.data(), x, n, ldx, 0, n);
     }
+    ldx_out = ldx;
+    return x;
+}
+static bool lu_solve_inverse_impl(const std::vector<double>& A, int n, std::vector<double>& inv) {
+    std::vector<double> a(A);
+    int ldx = 0;
+    const double* x = lu_inverse_padded(a, n, ldx);
     inv.resize((size_t)n * n);
     for (int i = 0; i < n; ++i) std::copy(x + (size_t)i * ldx, x + (size_t)i * ldx + n, inv.begin() + (size_t)i * n);
     return true;
+}
+// The reference's LM step in one go (DmsaOptimizer.h:108-113): H.diag += lambda, step = (-alpha * H.inverse()) * g.
+// Same arithmetic as lu_solve_inverse_impl + the caller's product, without the intermediate copies.
+bool dmsa_host_lm_step(const double* hg, int n, double lambda, double alpha, double* step) {
+    thread_local std::vector<double> a;
+    a.assign(hg, hg + (size_t)n * n);
+    for (int i = 0; i < n; ++i) a[(size_t)i * n + i] += lambda;
+    const double* g = hg + (size_t)n * n;
+    int ldx = 0;
+    const double* x = lu_inverse_padded(a, n, ldx);
+    bool nan = false;
+    for (int r = 0; r < n; ++r) {
+        const double* xr = x + (size_t)r * ldx;
+        double s = 0;
+        for (int b = 0; b < n; ++b) s += (-alpha * xr[b]) * g[b];
+        step[r] = s;
+        if (std::isnan(s)) nan = true;
+    }
+    return nan;
 }
 
 DMSA_CLONES bool lu_solve_vec_impl(const std::vector<double>& A, int n, const double* b, std::vector<double>& x) {
