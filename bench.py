@@ -27,6 +27,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG", "WARN")  # NCCL's version banner goes to stdout otherwise; stdout carries exactly one JSON line
 
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries (NCCL's version banner when the box exports NCCL_DEBUG)
+    write to file descriptor 1 behind Python's back: keep a private duplicate of the real stdout for the result line and
+    point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
+RESULT_OUT = None
+
+
+def emit(line):
+    out = RESULT_OUT if RESULT_OUT is not None else sys.__stdout__
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
 SETTINGS = dict(num_iter=1, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10, min_num_gaussians=30)  # SURVEY §8d
 METRIC = "DMSA iterations/sec"
 UNIT = "iterations/s"
@@ -171,7 +191,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def pinned_copy(arr):
@@ -347,7 +367,7 @@ def run_sliding(args):
         cb = oracle_cpu_baseline(win, threads)
         line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_iteration"], "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "median of 2 full iterations of the same workload; oracle/dmsa_oracle.cpp -O2 -fopenmp, faithful arithmetic"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -361,6 +381,8 @@ def main():
     ap.add_argument("--workload", default="sliding", choices=["sliding", "keyframe"])
     ap.add_argument("--config", default="cfg2")
     args = ap.parse_args()
+    global RESULT_OUT
+    RESULT_OUT = _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "keyframe":

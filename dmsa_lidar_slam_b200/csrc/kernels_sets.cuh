@@ -118,12 +118,23 @@ __global__ void k_keys(const float4* __restrict__ world, int N, LevelPlan plan, 
         valid = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
         if (valid) {
             double c[3] = {(double)p.x, (double)p.y, (double)p.z};
+            const double inv_res = 1.0 / res;
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
-                double q = (c[a] - info->min0[a]) / res;
+                // PCL divides: key = floor((x - min) / res).  The product with 1 / res differs from the quotient by a few ulp
+                // (< 1e-15 |q|), so away from the integers both floor to the same key; only within `guard` of a voxel face
+                // the exact division decides (rare), and the edge-point test below always sees the exact fraction there.
+                const double d = c[a] - info->min0[a];
+                double q = d * inv_res;
                 double fl = floor(q);
-                k[a] = kx[a] = (int)fl;
                 double frac = q - fl;
+                const double guard = 4e-9 + 4e-15 * fabs(q);
+                if (frac < guard || frac > 1.0 - guard) {
+                    q = d / res;
+                    fl = floor(q);
+                    frac = q - fl;
+                }
+                k[a] = kx[a] = (int)fl;
                 if (frac < 1e-9 || (1.0 - frac) * res <= 2.4e-7) ek[a] = ekx[a] = (int)fl;
             }
         }
