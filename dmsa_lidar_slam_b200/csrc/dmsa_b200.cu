@@ -596,7 +596,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     if (plan.n > 0) {
         LAUNCH(k_anchor, 1, 32, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p);
         LAUNCH(k_keys, dim3(nb, plan.n), DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_keys.p, ctx->d_bb.p, nb);
-        LAUNCH(k_root, plan.n, 256, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_bb.p, nb);
+        LAUNCH(k_root, plan.n, 1024, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_bb.p, nb);
     }
     }
     // The radix sort needs the number of key bits (3 * octree depth + 1) on the host.  The depth of the previous build of

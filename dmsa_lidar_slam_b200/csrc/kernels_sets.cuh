@@ -178,10 +178,6 @@ __global__ void k_keys(const float4* __restrict__ world, int N, LevelPlan plan, 
         bbmax[3 * blockIdx.x + a] = mx;
         ebmin[3 * blockIdx.x + a] = emn;
         ebmax[3 * blockIdx.x + a] = emx;
-        if (mn <= mx) {
-            atomicMin(&info->kmin[a], mn);
-            atomicMax(&info->kmax[a], mx);
-        }
     }
 }
 
