@@ -796,7 +796,7 @@ int runCost(dmsa_b200_ctx* ctx) {
     const int cls = packed ? 0 : (Vld <= 128 ? 1 : (Vld <= 256 ? 2 : (Vld <= 512 ? 3 : 4)));
 #define DISPATCH(KERN, GRID, ...)                                                          \
     switch (cls) {                                                                         \
-        case 0: LAUNCH((KERN<true, 32, 24>), GRID, 32, 0, __VA_ARGS__); break;             \
+        case 0: LAUNCH((KERN<true, 32 * PACKED_WARPS, 16>), GRID, 32 * PACKED_WARPS, 0, __VA_ARGS__); break; \
         case 1: LAUNCH((KERN<false, 128, 10>), GRID, Vld, 0, __VA_ARGS__); break;          \
         case 2: LAUNCH((KERN<false, 256, 5>), GRID, Vld, 0, __VA_ARGS__); break;           \
         case 3: LAUNCH((KERN<false, 512, 2>), GRID, Vld, 0, __VA_ARGS__); break;           \

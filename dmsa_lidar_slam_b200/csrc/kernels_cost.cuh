@@ -53,8 +53,11 @@ __device__ __forceinline__ void xform(const float4& m0, const float4& m1, const 
 }
 
 // Lane mapping.  PACKED = false (V > 16): blockDim = Vld, thread = vector, every thread walks all members.
-// PACKED = true (V <= 16, the 9 line-search vectors): blockDim = 32, lane = sub * V + v; the S = 32 / V sub-streams walk
-// interleaved members and are combined in fixed order (sub 0 + sub 1 + ...) with warp shuffles.
+// PACKED = true (V <= 16, the 9 line-search vectors): blockDim = 32 * PACKED_WARPS; in every warp lane = sub * V + v, the
+// S = 32 / V sub-streams of each warp walk interleaved members (PACKED_WARPS * S streams per set) and are combined in fixed
+// order: inside a warp with shuffles (sub 0 + sub 1 + ...), then warp 0 + warp 1 through shared memory.  The small batch is
+// latency bound (one dependent chain per lane): two warps per set double the resident warps for the same staging buffer.
+#define PACKED_WARPS 2
 struct LaneMap {
     int v, sub, stride;
     bool active;
@@ -69,19 +72,29 @@ __device__ __forceinline__ LaneMap lane_map(const CostArgs& a) {
         m.active = m.v < a.V;
         if (!m.active) m.v = a.V - 1;
     } else {
-        m.sub = threadIdx.x / a.V;
-        m.v = threadIdx.x - m.sub * a.V;
-        m.stride = a.S;
-        m.active = m.sub < a.S;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        const int sw = lane / a.V;  // sub-stream inside the warp
+        m.v = lane - sw * a.V;
+        m.sub = w * a.S + sw;
+        m.stride = a.S * PACKED_WARPS;
+        m.active = sw < a.S;
     }
     return m;
 }
+// ex: shared double[PACKED_WARPS][16].  Every thread returns the total of its vector (block-uniform per vector).
 template <bool PACKED>
-__device__ __forceinline__ double combine_subs(const CostArgs& a, const LaneMap& lm, double val) {
+__device__ __forceinline__ double combine_subs(const CostArgs& a, const LaneMap& lm, double val, double (*ex)[16]) {
     if (!PACKED) return val;
     double tot = 0.0;
     for (int s = 0; s < a.S; ++s) tot += __shfl_sync(0xffffffffu, val, lm.v + s * a.V);
-    return tot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane < a.V) ex[w][lane] = tot;
+    __syncthreads();
+    double all = ex[0][lm.v];
+#pragma unroll
+    for (int k = 1; k < PACKED_WARPS; ++k) all += ex[k][lm.v];
+    __syncthreads();  // ex is reused by the next combine
+    return all;
 }
 
 // Staging of `count` member records (16 B each, contiguous in HBM) into shared memory with ONE bulk asynchronous copy
@@ -207,6 +220,7 @@ template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ double ex[PACKED_WARPS][16];
     if ((int)blockIdx.x >= G) return;
     const int g = a.order[blockIdx.x];
     const int kind = a.cell_kind[g];
@@ -221,13 +235,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
     const int cnt = lm.active ? n : 0;
     double sx, sy, sz;
     pass_sum<PACKED>(a, srec, cnt, lm, sx, sy, sz);
-    sx = combine_subs<PACKED>(a, lm, sx);
-    sy = combine_subs<PACKED>(a, lm, sy);
-    sz = combine_subs<PACKED>(a, lm, sz);
+    sx = combine_subs<PACKED>(a, lm, sx, ex);
+    sy = combine_subs<PACKED>(a, lm, sy, ex);
+    sz = combine_subs<PACKED>(a, lm, sz, ex);
     const float nf = (float)n;
     const float mx = fdiv_((float)sx, nf), my = fdiv_((float)sy, nf), mz = fdiv_((float)sz, nf);  // DmsaOptimizer.h:254
     double q = pass_quad<PACKED>(a, srec, cnt, lm, g, mx, my, mz);
-    q = combine_subs<PACKED>(a, lm, q);
+    q = combine_subs<PACKED>(a, lm, q, ex);
     if (lm.active && lm.sub == 0) a.E[(size_t)g * a.Vld + lm.v] = sqrt(fabs(q));  // :267
 }
 
@@ -370,6 +384,7 @@ template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ double ex[PACKED_WARPS][16];
     __shared__ int s_last;
     const int c = blockIdx.x;
     if (c >= *a.n_chunks) return;
@@ -378,9 +393,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
     stage_records(srec, a.rec + ch.start, ch.count, &bar);
     double sx, sy, sz;
     pass_sum<PACKED>(a, srec, lm.active ? ch.count : 0, lm, sx, sy, sz);
-    sx = combine_subs<PACKED>(a, lm, sx);
-    sy = combine_subs<PACKED>(a, lm, sy);
-    sz = combine_subs<PACKED>(a, lm, sz);
+    sx = combine_subs<PACKED>(a, lm, sx, ex);
+    sy = combine_subs<PACKED>(a, lm, sy, ex);
+    sz = combine_subs<PACKED>(a, lm, sz, ex);
     const bool writer = lm.active && lm.sub == 0;
     if (writer) {
         a.S_part[((size_t)c * 3 + 0) * a.Vld + lm.v] = sx;
@@ -412,6 +427,7 @@ template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
+    __shared__ double ex[PACKED_WARPS][16];
     __shared__ int s_last;
     const int c = blockIdx.x;
     if (c >= *a.n_chunks) return;
@@ -435,7 +451,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
         mz = mu[2 * (size_t)a.Vld];
     }
     double acc = pass_quad<PACKED>(a, srec, lm.active ? ch.count : 0, lm, g, mx, my, mz);
-    acc = combine_subs<PACKED>(a, lm, acc);
+    acc = combine_subs<PACKED>(a, lm, acc, ex);
     const bool writer = lm.active && lm.sub == 0;
     if (writer) a.Q[(size_t)c * a.Vld + lm.v] = acc;
     if (!last_block_of_set(a.done + g, nc, &s_last)) return;

@@ -130,6 +130,30 @@ def test_barycentric_rational_weights_and_eval(n):
     assert abs(c - (a + 2 * b)) < 1e-12
 
 
+@pytest.mark.parametrize("n", [3, 4, 7, 20, 40])
+def test_barycentric_rational_matches_scipy_floater_hormann(n):
+    """Third-party pin of the Boost restatement: scipy.interpolate.FloaterHormannInterpolator (an independent implementation
+    of the same Floater-Hormann family, blending degree d = 2 like ContinuousTrajectory.h:214) must give the same interpolant
+    - weights up to the common scale factor of the barycentric form, values to rounding - on the control-pose time grids
+    the trajectory model uses (LinSpaced stamps, ContinuousTrajectory.h:332) and on irregular grids."""
+    from scipy.interpolate import FloaterHormannInterpolator
+
+    for x in (np.linspace(0.0, 0.1 * (n - 1), n), np.concatenate([[0.0], np.sort(rng.uniform(0.01, 2.0, n - 1))])):
+        y = np.stack([np.sin(3 * x) + 0.2 * x, np.cos(2 * x), 0.05 * x**3], axis=1)
+        w = np.zeros(n)
+        L.orc_fh_weights(_p(x), n, 2, _p(w))
+        fh = FloaterHormannInterpolator(x, y, d=2)
+        ws = np.asarray(fh.weights, dtype=np.float64).ravel()
+        k = int(np.argmax(np.abs(ws)))
+        np.testing.assert_allclose(w / w[k], ws / ws[k], rtol=1e-10, atol=1e-13)
+        ts = rng.uniform(x[0], x[-1], 40)
+        ref = np.asarray(fh(ts))
+        for a in range(3):
+            ya = np.ascontiguousarray(y[:, a])
+            got = np.array([L.orc_fh_eval(_p(x), _p(ya), _p(w), n, float(t)) for t in ts])
+            np.testing.assert_allclose(got, ref[:, a], rtol=1e-10, atol=1e-12)
+
+
 def limit_covariance_numpy(pts):
     """Independent float32 restatement of Gaussians.h:146-154,181-201 with LAPACK's general real eigensolver
     (sgeev — the same class of algorithm as Eigen::EigenSolver<Matrix3f>)."""
