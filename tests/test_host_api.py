@@ -130,3 +130,27 @@ def test_lm_solve_variants():
     hg[3] = np.nan
     _, nan = lm_solve(api.DmsaOptimSettings(), hg, n, 1)
     assert nan
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours): stdout carries ONE JSON line with the contract's
+    keys even when native libraries write banners to file descriptor 1; works under a torchrun-style environment where only
+    rank 0 reports."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "cfg1", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="2"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in d["config"]
+    quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
