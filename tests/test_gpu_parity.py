@@ -573,3 +573,33 @@ def test_pair_packed_cost_kernels_equal_the_scalar_kernels_bitwise(name):
         assert x["error0"] == y["error0"] and x["best_step"] == y["best_step"]
         assert np.array_equal(x["step"], y["step"]) and np.array_equal(x["ls_cost"], y["ls_cost"])
     assert np.array_equal(a[3], b[3])
+
+
+def test_many_poses_wide_batch_pair_kernels_and_fma_jtj():
+    """24 control poses: P = 138, V = 139 > 128 - the 128-thread class of the pair kernels (two vectors per thread, Vld = 160)
+    and the FP64-FMA J^T J path (n1 > 128; the DMMA kernel covers n1 <= 128).  Pair-packed == scalar kernels bitwise, and both
+    against the oracle's arithmetic."""
+    win = synth.make_sliding_window(n_scans=2, sensor="cfg1", n_static=3000, n_poses=24, seed=11)
+    st = dict(num_iter=1, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10, min_num_gaussians=30)
+    s, so = DmsaOptimSettings(**st), ob.settings(**st)
+    out = []
+    for mode in (1, 0):
+        traj = ContinuousTrajectory.from_window(win)
+        traj.setPairMode(mode)
+        traj.centralize()
+        traj.updateGlobalPoints()
+        G, _ = traj.buildSets(s)
+        out.append((traj.costJacobian(with_rows=True), G))
+    (a, Ga), (b, Gb) = out
+    assert Ga == Gb and a["J"].shape[1] == 138
+    for k in ("e0", "J", "H", "g"):
+        assert np.array_equal(a[k], b[k]), k
+    om = ob.OracleModel.from_window(win)
+    om.set_threads(os.cpu_count() or 8)
+    om.set_mode(2)
+    om.centralize()
+    om.update_global_points()
+    assert om.build_sets(so) == Ga
+    e0, J = om.jacobian()
+    assert rel(a["e0"], e0) < TOL_SAME_ARITH and rel(a["J"], J) < TOL_SAME_ARITH
+    assert rel(a["H"], J.T @ J) < TOL_SAME_ARITH and rel(a["g"], J.T @ e0) < TOL_SAME_ARITH
