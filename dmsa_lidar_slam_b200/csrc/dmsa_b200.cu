@@ -733,6 +733,7 @@ phase2:
         CK(cudaMemsetAsync(cnt, 0, sizeof(int), s2));
         LAUNCH_ON(s2, k_gauss_list, cdiv(G, 256), 256, 0, cs, G, ctx->d_biglist.p, cnt);
         LAUNCH_ON(s2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
+        LAUNCH_ON(s2, k_weights, 1, 1024, 0, cs, G);  // depends on the set sizes only
         CK(cudaEventRecord(ctx->evJoin, s2));
         LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G, ctx->d_mom.p);
         CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
@@ -745,7 +746,6 @@ phase2:
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
         LAUNCH(k_gaussian_fin, cdiv(G, 128), 128, 0, cs, G, ctx->d_mom.p);
     }
-    LAUNCH(k_weights, 1, 1024, 0, cs, G);
     CK(cudaGetLastError());
     return 0;
 }

@@ -673,7 +673,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // Gaussians.h:146-154, 181-201 given the exactly-rounded coordinate sums (s) and centred second moments (acc)
 __device__ inline void gaussian_finish(CellStore cs, int g, int n, const double acc[6]) {
-    const float nf = (float)n;
     const float den = (float)(n - 1);
     const float cxx = fdiv_((float)acc[0], den), cxy = fdiv_((float)acc[1], den), cxz = fdiv_((float)acc[2], den);
     const float cyy = fdiv_((float)acc[3], den), cyz = fdiv_((float)acc[4], den), czz = fdiv_((float)acc[5], den);
@@ -706,7 +705,6 @@ __device__ inline void gaussian_finish(CellStore cs, int g, int n, const double 
     I[5] = fmul_(cof3(cov, 2, 1), invdet);
     I[6] = fmul_(cof3(cov, 0, 2), invdet);
     I[8] = fmul_(cof3(cov, 2, 2), invdet);
-    cs.w0[g] = fmul_(fdiv_(1.0f, nf), 1.0f);  // Gaussians.h:172-175, observation weight 1 (OptimizablePointSet.h:52)
 }
 
 #define GAUSS_WARP_MAX 256
@@ -833,11 +831,16 @@ __global__ void k_gaussian_fin(CellStore cs, int G, const double* __restrict__ m
     gaussian_finish(cs, g, cs.n[g], a);
 }
 
-// Gaussians.h:177: w / w.mean()   (one block; deterministic double reduction, one rounding)
+// Gaussians.h:172-177: w0 = (1 / n) * observation weight (1, OptimizablePointSet.h:52), w = w0 / mean(w0)   (one block;
+// deterministic double reduction, one rounding).  Depends on the set sizes only, so it runs beside the set statistics.
 __global__ void k_weights(CellStore cs, int G) {
     __shared__ double part[1024];
     double s = 0;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) s += (double)cs.w0[g];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const float w0 = fmul_(fdiv_(1.0f, (float)cs.n[g]), 1.0f);
+        cs.w0[g] = w0;
+        s += (double)w0;
+    }
     part[threadIdx.x] = s;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) {
