@@ -129,6 +129,7 @@ struct dmsa_b200_ctx {
     // second stream: the two resolution levels of a set build run side by side (fork / join with events)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr, evLevel0 = nullptr;
+    std::vector<cudaEvent_t> evScan;  // one per uploaded scan (register_scans)
     std::string err;
     int64_t launches = 0;
     int model = MODEL_NONE;
@@ -144,6 +145,9 @@ struct dmsa_b200_ctx {
     // trajectory timing (ContinuousTrajectory.h:301-346)
     double t0 = 0, horizon = 0, dt_res = 1e-3;
     int n_total = 0;
+    bool tabValid = false;  // timing tables in HBM correspond to (tabHorizon, tabPoses, tabDt)
+    double tabHorizon = 0, tabDt = 0;
+    int tabPoses = 0;
     bool useImu = false, imuSet = false;
     std::vector<double> stamps, trajTime;
     std::vector<int> paramIndices;
@@ -1185,6 +1189,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     }
     for (cudaEvent_t e : {ctx->evFork, ctx->evJoin, ctx->evLevel0})
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->evScan) cudaEventDestroy(e);
 #define REL(b) ctx->b.release()
     REL(d_stamps); REL(d_trajTime); REL(d_urel); REL(d_fh); REL(d_seg); REL(d_hit); REL(d_paramIdx); REL(d_imu); REL(d_kfD); REL(d_plausible);
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
@@ -1219,6 +1224,17 @@ int dmsa_b200_traj_init(dmsa_b200_ctx* ctx, double t_min, double t_max, int32_t 
     ctx->horizon = t_max - t_min + dt_res;                             // :309
     ctx->n_total = (int)std::round(ctx->horizon / dt_res) + 1;          // :310
     const int nt = ctx->n_total, n = n_poses;
+    // every table below depends on (horizon, n_poses, dt_res) only - all times are relative to t_min - so a window with the
+    // same shape as the previous one (the steady state of a sliding window) keeps the tables already in HBM
+    if (ctx->tabValid && ctx->tabHorizon == ctx->horizon && ctx->tabPoses == n && ctx->tabDt == dt_res) {
+        ctx->poses.resize(n);
+        ctx->gravity[0] = 0.0;
+        ctx->gravity[1] = 0.0;
+        ctx->gravity[2] = -9.805;  // :345
+        ctx->n_scan = ctx->n_static = 0;
+        return 0;
+    }
+    ctx->tabValid = false;
     auto linspaced = [](int m, double lo, double hi, std::vector<double>& v) {  // Eigen LinSpaced: lo + i*step, last == hi
         v.resize(m);
         double step = (m > 1) ? (hi - lo) / (double)(m - 1) : 0.0;
@@ -1284,6 +1300,10 @@ int dmsa_b200_traj_init(dmsa_b200_ctx* ctx, double t_min, double t_max, int32_t 
     CK(cudaMemcpyAsync(ctx->d_hit.p, hit.data(), nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_paramIdx.p, ctx->paramIndices.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // host vectors above go out of scope
+    ctx->tabValid = true;
+    ctx->tabHorizon = ctx->horizon;
+    ctx->tabPoses = n;
+    ctx->tabDt = dt_res;
     return 0;
 }
 
@@ -1308,11 +1328,22 @@ int dmsa_b200_traj_register_scans(dmsa_b200_ctx* ctx, int32_t n_scans, const dms
     CK(ctx->d_ring.ensure(cap));
     CK(ctx->d_stage.ensure((size_t)total * 32 + 64));
     CK(cudaMemsetAsync(ctx->d_flag.p, 0, sizeof(int), ctx->stream));
+    // the copies go back to back on stream2 (copy engine), the unpack kernel of scan s waits for its copy only: the
+    // unpacking of one scan overlaps the transfer of the next
+    while ((int)ctx->evScan.size() < n_scans) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->evScan.push_back(e);
+    }
+    CK(cudaEventRecord(ctx->evFork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
     int64_t off = 0;
     for (int s = 0; s < n_scans; ++s) {
         if (sizes[s] == 0) continue;
         unsigned char* dst = ctx->d_stage.p + (size_t)off * 32;
-        CK(cudaMemcpyAsync(dst, scans[s], (size_t)sizes[s] * 32, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dst, scans[s], (size_t)sizes[s] * 32, cudaMemcpyHostToDevice, ctx->stream2));
+        CK(cudaEventRecord(ctx->evScan[s], ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->evScan[s], 0));
         LAUNCH(k_unpack_psi, cdiv(sizes[s], 256), 256, 0, dst, (int)sizes[s], (int)off, ctx->d_trajTime.p, ctx->n_total, ctx->t0, 0, ctx->d_local.p,
                ctx->d_world.p, ctx->d_ring.p, ctx->d_tid.p, ctx->d_flag.p);
         off += sizes[s];
@@ -1425,6 +1456,7 @@ int dmsa_b200_traj_set_imu_factors(dmsa_b200_ctx* ctx, const double* preint_rot,
 int dmsa_b200_kf_init(dmsa_b200_ctx* ctx, int32_t n_keyframes) {
     if (n_keyframes < 2) ARGFAIL("kf_init: need at least two keyframes");
     ctx->model = MODEL_KF;
+    ctx->tabValid = false;
     ctx->poses.resize(n_keyframes);
     ctx->kfClouds.assign(n_keyframes, {});
     ctx->kfRings.assign(n_keyframes, {});
