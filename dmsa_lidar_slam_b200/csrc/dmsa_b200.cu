@@ -1226,7 +1226,10 @@ int dmsa_b200_traj_init(dmsa_b200_ctx* ctx, double t_min, double t_max, int32_t 
     const int nt = ctx->n_total, n = n_poses;
     // every table below depends on (horizon, n_poses, dt_res) only - all times are relative to t_min - so a window with the
     // same shape as the previous one (the steady state of a sliding window) keeps the tables already in HBM
-    if (ctx->tabValid && ctx->tabHorizon == ctx->horizon && ctx->tabPoses == n && ctx->tabDt == dt_res) {
+    // (DMSA_B200_TABLE_CACHE=0 turns the reuse off: bench.py measures its end-to-end leg that way, because it feeds the same
+    // window every step and would otherwise never pay for the tables)
+    static const bool cacheOn = !(getenv("DMSA_B200_TABLE_CACHE") && atoi(getenv("DMSA_B200_TABLE_CACHE")) == 0);
+    if (cacheOn && ctx->tabValid && ctx->tabHorizon == ctx->horizon && ctx->tabPoses == n && ctx->tabDt == dt_res) {
         ctx->poses.resize(n);
         ctx->gravity[0] = 0.0;
         ctx->gravity[1] = 0.0;
