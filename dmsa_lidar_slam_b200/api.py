@@ -120,6 +120,8 @@ def load_library():
         "dmsa_b200_lm_solve": (i32, [P(DmsaOptimSettings), vp, i32, i32, vp, P(i32)]),
         "dmsa_b200_set_lm_solver": (i32, [vp, i32]),
         "dmsa_b200_set_pair_mode": (i32, [vp, i32]),
+        "dmsa_b200_select_static_points": (i32, [vp, vp, i64, vp, C.c_float, vp, P(i64)]),
+        "dmsa_b200_overlap": (i32, [vp, vp, i64, C.c_float, P(C.c_float)]),
         "dmsa_b200_lm_solve_device": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
     }
     for name, (res, args) in sig.items():
@@ -142,6 +144,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode",
+    "dmsa_b200_select_static_points", "dmsa_b200_overlap",
 ]
 
 
@@ -315,6 +318,23 @@ class OptimizablePointSet:
     def setMeanMode(self, mode):
         """0: order-free exactly-rounded per-set mean (default, fast); 1: the reference's sequential float accumulation."""
         self.ctx._ck(self.L.dmsa_b200_set_mean_mode(self.h, int(mode)))
+
+    def selectStaticPoints(self, cloud, pos, max_dist):
+        """DmsaSlam.h:304-339 for one keyframe cloud (48-byte PointNormal records, world frame): (selected uint8[n], currOverlap)."""
+        c = np.ascontiguousarray(cloud)
+        assert c.dtype.itemsize == 48, "pcl::PointNormal records (48 bytes)"
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        sel = np.zeros(len(c), dtype=np.uint8)
+        cnt = C.c_int64(0)
+        self.ctx._ck(self.L.dmsa_b200_select_static_points(self.h, _p(c), len(c), _p(pos), float(max_dist), _p(sel), C.byref(cnt)))
+        return sel, int(cnt.value)
+
+    def overlap(self, pc1_xyzw, max_dist):
+        """getOverlap(pc1, window cloud, max_dist), DmsaSlam.h:377-414."""
+        a = np.ascontiguousarray(pc1_xyzw, dtype=np.float32).reshape(-1, 4)
+        out = C.c_float(0.0)
+        self.ctx._ck(self.L.dmsa_b200_overlap(self.h, _p(a), len(a), float(max_dist), C.byref(out)))
+        return float(out.value)
 
     def setPairMode(self, mode):
         """1: pair-packed FP32x2 cost kernels for the forward-difference batch (default); 0: scalar kernels (bit-identical)."""

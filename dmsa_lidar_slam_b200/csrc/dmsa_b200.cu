@@ -19,6 +19,7 @@
 #include "../../include/dmsa_b200.h"
 #include "kernels_cost.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_knn.cuh"
 #include "kernels_pose.cuh"
 #include "kernels_sets.cuh"
 #include "se3_math.cuh"
@@ -199,6 +200,11 @@ struct dmsa_b200_ctx {
 
     // cost
     DBuf<double> d_mom;  // centred second moments of every set [g][6]
+    // uniform grids for the radius queries of addStaticPoints / getOverlap
+    DBuf<unsigned long long> d_gkeys, d_gskeys;
+    DBuf<int> d_gidx, d_gsidx, d_gcount;
+    DBuf<float4> d_gpts, d_gquery;
+    DBuf<unsigned char> d_gsel;
     DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart, d_solve, d_iter;
     bool solveAttr = false;
     bool solveGeneral = false;  // force the general one-block kernel (any P <= 1024) instead of the P <= 128 fast path
@@ -1197,7 +1203,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_mom); REL(d_solve); REL(d_iter);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_gkeys); REL(d_gskeys); REL(d_gidx); REL(d_gsidx); REL(d_gcount); REL(d_gpts); REL(d_gquery); REL(d_gsel); REL(d_mom); REL(d_solve); REL(d_iter);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
@@ -1854,6 +1860,87 @@ int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* sett
     CK(cudaStreamSynchronize(ctx->stream));
     std::copy(r.begin(), r.begin() + P, step);
     if (has_nan) *has_nan = r[(size_t)P + 1] != 0.0;
+    return 0;
+}
+
+// ---- static-point selection and overlap ratio (DmsaSlam.h:264-414) ---------------------------------
+namespace {
+// grid over `n` points (device, xyzw) with cell edge radius * 1.000001 -> sorted keys + points in key order
+int buildRadiusGrid(dmsa_b200_ctx* ctx, const float4* pts, int n, float radius, GridView* view) {
+    double h = (double)radius * 1.000001;
+    if (!(h > 0.0)) h = 1e-6;
+    view->n = n;
+    view->h = h;
+    view->keys = nullptr;
+    view->pts = nullptr;
+    if (n == 0) return 0;
+    CK(ctx->d_gkeys.ensure(n));
+    CK(ctx->d_gskeys.ensure(n));
+    CK(ctx->d_gidx.ensure(n));
+    CK(ctx->d_gsidx.ensure(n));
+    CK(ctx->d_gpts.ensure(n));
+    CKRC(ensureCub(ctx, n, 1));
+    LAUNCH(k_grid_keys, cdiv(n, 256), 256, 0, pts, n, h, ctx->d_gkeys.p, ctx->d_gidx.p);
+    size_t bytes = ctx->cubPer;
+    CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, bytes, ctx->d_gkeys.p, ctx->d_gskeys.p, ctx->d_gidx.p, ctx->d_gsidx.p, n, 0, 64, ctx->stream));
+    LAUNCH(k_grid_gather, cdiv(n, 256), 256, 0, pts, ctx->d_gsidx.p, n, ctx->d_gpts.p);
+    view->keys = ctx->d_gskeys.p;
+    view->pts = ctx->d_gpts.p;
+    return 0;
+}
+}  // namespace
+
+// addStaticPoints, inner loop for ONE keyframe cloud (DmsaSlam.h:304-339): selected[j] = 1 iff the nearest point of the
+// staged window cloud (globalPoints as of the last update_global_points / add_static_points) is within max_dist and the
+// point is visible from pos; *num_selected = currOverlap.  The window grid is rebuilt on every call (the reference builds
+// its kd-tree once per addStaticPoints call; keyframe clouds are ~1e5 points, the grid build is a 64-bit sort of the window).
+int dmsa_b200_select_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_normal* cloud, int64_t n, const float* pos, float max_dist,
+                                   uint8_t* selected, int64_t* num_selected) {
+    if ((n > 0 && (!cloud || !selected)) || !pos || n < 0 || n > 0x3fffffff) ARGFAIL("select_static_points: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (num_selected) *num_selected = 0;
+    if (n == 0) return 0;
+    const int64_t N = numPoints(ctx);
+    if (N > 0 && !ctx->worldValid) ARGFAIL("select_static_points: call update_global_points first (the search runs on globalPoints)");
+    GridView g;
+    CKRC(buildRadiusGrid(ctx, ctx->d_world.p, (int)N, max_dist, &g));
+    const float max_sq = (float)std::pow((double)(1.0f * max_dist), 2);  // DmsaSlam.h:293
+    CK(ctx->d_gquery.ensure((size_t)3 * n));
+    CK(ctx->d_gsel.ensure((size_t)n));
+    CK(ctx->d_gcount.ensure(1));
+    CK(cudaMemcpyAsync(ctx->d_gquery.p, cloud, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_gcount.p, 0, sizeof(int), ctx->stream));
+    LAUNCH(k_select_static, cdiv(n, 128), 128, 0, g, ctx->d_gquery.p, (int)n, pos[0], pos[1], pos[2], max_sq, ctx->d_gsel.p, ctx->d_gcount.p);
+    int cnt = 0;
+    CK(cudaMemcpyAsync(selected, ctx->d_gsel.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&cnt, ctx->d_gcount.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    if (num_selected) *num_selected = cnt;
+    return 0;
+}
+
+// getOverlap(pc1, pc2 = the staged window cloud, max_dist) (DmsaSlam.h:377-414): pc1 = n1 x (x, y, z, w) floats on the host
+int dmsa_b200_overlap(dmsa_b200_ctx* ctx, const float* pc1_xyzw, int64_t n1, float max_dist, float* overlap) {
+    if (!overlap || n1 < 0 || n1 > 0x3fffffff || (n1 > 0 && !pc1_xyzw)) ARGFAIL("overlap: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    *overlap = 0.0f;
+    const int64_t N = numPoints(ctx);
+    if (n1 == 0 || N == 0) return 0;  // :380-381
+    if (!ctx->worldValid) ARGFAIL("overlap: call update_global_points first (the search runs on globalPoints)");
+    CK(ctx->d_gquery.ensure((size_t)n1));
+    CK(cudaMemcpyAsync(ctx->d_gquery.p, pc1_xyzw, (size_t)n1 * 16, cudaMemcpyHostToDevice, ctx->stream));
+    GridView g;
+    CKRC(buildRadiusGrid(ctx, ctx->d_gquery.p, (int)n1, max_dist, &g));
+    const float max_sq = max_dist * max_dist;  // :386
+    CK(ctx->d_gcount.ensure(1));
+    CK(cudaMemsetAsync(ctx->d_gcount.p, 0, sizeof(int), ctx->stream));
+    LAUNCH(k_overlap_count, cdiv(N, 128), 128, 0, g, ctx->d_world.p, (int)N, max_sq, ctx->d_gcount.p);
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, ctx->d_gcount.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    *overlap = static_cast<float>(cnt) / static_cast<float>((int)N);  // :412
     return 0;
 }
 

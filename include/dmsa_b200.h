@@ -216,6 +216,17 @@ int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode);
 int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step,
                               int32_t* has_nan);
 
+/* ---- the nearest-neighbour step right before the sliding-window pass (DmsaSlam.h:264-414) ----
+ * Both search the window cloud staged in this context (globalPoints as of the last update_global_points).
+ * addStaticPoints, inner loop for ONE keyframe cloud in the world frame (DmsaSlam.h:304-339): selected[j] = 1 iff the nearest
+ * window point is within max_dist (PCL KdTreeFLANN / flann::L2_Simple<float> squared distance <= pow(max_dist, 2), :293-315)
+ * and the point is visible from pos (isVisible, :347-363).  *num_selected = currOverlap of that keyframe (:331). */
+int dmsa_b200_select_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_normal* cloud, int64_t n, const float* pos /*3*/, float max_dist,
+                                   uint8_t* selected /*n*/, int64_t* num_selected);
+/* getOverlap(pc1, pc2 = the window cloud, max_dist) (DmsaSlam.h:377-414): fraction of window points whose nearest pc1 point
+ * (n1 x {x, y, z, w} floats on the host) is within max_dist; 0 when either cloud is empty. */
+int dmsa_b200_overlap(dmsa_b200_ctx* ctx, const float* pc1_xyzw, int64_t n1, float max_dist, float* overlap);
+
 #ifdef __cplusplus
 }
 #endif

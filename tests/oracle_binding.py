@@ -96,6 +96,10 @@ def lib(opt="O2"):
     L.orc_relative2global.argtypes = [i32, vp, vp, vp, vp]
     L.orc_global2relative.argtypes = [i32, vp, vp, vp, vp]
     L.orc_lu_inverse.argtypes = [vp, i32, vp]
+    L.orc_select_static_points.restype = i64
+    L.orc_select_static_points.argtypes = [vp, i64, vp, i64, vp, C.c_float, C.c_float, vp]
+    L.orc_overlap.restype = C.c_float
+    L.orc_overlap.argtypes = [vp, i64, vp, i64, C.c_float]
     _LIBS[opt] = L
     return L
 
@@ -306,3 +310,22 @@ class OracleModel:
         s = C.c_int()
         t = self.L.orc_time_iteration(self.h, C.byref(st), C.byref(s))
         return t, s.value
+
+
+def select_static_points(window_xyzw, cloud_xyz_nrm, pos, max_dist_sq, radius):
+    """addStaticPoints inner loop for one keyframe cloud (DmsaSlam.h:304-339): (selected uint8[n], currOverlap)."""
+    L = lib()
+    w = np.ascontiguousarray(window_xyzw, dtype=np.float32).reshape(-1, 4)
+    c = np.ascontiguousarray(cloud_xyz_nrm, dtype=np.float32).reshape(-1, 8)
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    sel = np.zeros(len(c), dtype=np.uint8)
+    cnt = L.orc_select_static_points(_p(w), len(w), _p(c), len(c), _p(pos), float(max_dist_sq), float(radius), _p(sel))
+    return sel, int(cnt)
+
+
+def overlap(pc1_xyzw, window_xyzw, max_dist):
+    """getOverlap(pc1, window, maxDist), DmsaSlam.h:377-414."""
+    L = lib()
+    a = np.ascontiguousarray(pc1_xyzw, dtype=np.float32).reshape(-1, 4)
+    w = np.ascontiguousarray(window_xyzw, dtype=np.float32).reshape(-1, 4)
+    return float(L.orc_overlap(_p(a), len(a), _p(w), len(w), float(max_dist)))

@@ -603,3 +603,42 @@ def test_many_poses_wide_batch_pair_kernels_and_fma_jtj():
     e0, J = om.jacobian()
     assert rel(a["e0"], e0) < TOL_SAME_ARITH and rel(a["J"], J) < TOL_SAME_ARITH
     assert rel(a["H"], J.T @ J) < TOL_SAME_ARITH and rel(a["g"], J.T @ e0) < TOL_SAME_ARITH
+
+
+def test_static_point_selection_and_overlap_match_oracle():
+    """SURVEY §8(f) rank 2 (DmsaSlam.h:264-414): the radius decisions of addStaticPoints / getOverlap on the device are
+    bit-exact against the oracle (FLANN L2_Simple float distances, isVisible in float) on the window cloud staged in HBM."""
+    win = synth.make_config("cfg1")
+    traj = ContinuousTrajectory.from_window(win)
+    traj.updateGlobalPoints()
+    W = np.ascontiguousarray(traj.globalPoints(), dtype=np.float32).reshape(-1, 4)
+    assert len(W) == traj.numPoints
+    radius = np.float32(0.3)
+    rng = np.random.default_rng(21)
+    n = 20000
+    src = W[rng.integers(0, len(W), n), :3]
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dist = np.where(rng.random(n) < 0.3, 0.0, np.where(rng.random(n) < 0.5, float(radius) * (1 + 1e-6 * rng.normal(size=n)), rng.uniform(0, 1.0, n)))
+    cloud = np.zeros(n, dtype=synth.POINT_NORMAL)
+    xyz = (src + dirs * dist[:, None]).astype(np.float32)
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    cloud["x"], cloud["y"], cloud["z"], cloud["w"] = xyz[:, 0], xyz[:, 1], xyz[:, 2], 1.0
+    cloud["nx"], cloud["ny"], cloud["nz"] = nrm[:, 0].astype(np.float32), nrm[:, 1].astype(np.float32), nrm[:, 2].astype(np.float32)
+    pos = np.array([2.0, 15.0, 1.5], dtype=np.float32)
+    sel, cnt = traj.selectStaticPoints(cloud, pos, radius)
+    flat = np.zeros((n, 8), dtype=np.float32)
+    flat[:, :3], flat[:, 3], flat[:, 4:7] = xyz, 1.0, nrm.astype(np.float32)
+    sel_o, cnt_o = ob.select_static_points(W, flat, pos, np.float32(float(radius) ** 2), radius)
+    assert cnt == cnt_o and 0 < cnt < n
+    assert np.array_equal(sel, sel_o)
+    # getOverlap: the selected points as the active map cloud
+    active = np.ones((int(sel.sum()), 4), dtype=np.float32)
+    active[:, :3] = xyz[sel == 1]
+    ov = traj.overlap(active, radius)
+    assert ov == ob.overlap(active, W, radius) and 0.0 < ov < 1.0
+    assert traj.overlap(active[:0], radius) == 0.0
+    assert traj.overlap(W, radius) == 1.0
+    s0, c0 = traj.selectStaticPoints(cloud[:0], pos, radius)
+    assert c0 == 0 and len(s0) == 0
