@@ -95,6 +95,7 @@ struct SolvePool {
     bool stop = false;
     bool disabled = false;
     void start() {
+        std::lock_guard<std::mutex> lk(m);  // two contexts may arm from two host threads at the same time
         if (!th.empty() || disabled) return;
         // Three helper threads take cache-line aligned column blocks of the inverse while the caller takes the first
         // (measured on the B200 host, P = 114: 0.25 ms alone, 0.19 ms with helpers).  DMSA_B200_SOLVER_THREADS=0 turns

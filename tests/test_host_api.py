@@ -154,3 +154,24 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert "workload" in d["config"]
     quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_host_solver_pool_is_race_free_under_thread_sanitizer(tmp_path):
+    """The LM solve's helper threads are on by default: two host threads (two contexts) arming, solving and disarming at the
+    same time must produce the serial result bit for bit, with ThreadSanitizer silent (the function multi-versioning
+    attribute is compiled out for this build: ifunc resolvers run before the sanitizer runtime is up)."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    src = open(os.path.join(ROOT, "dmsa_lidar_slam_b200", "csrc", "host_solve.cpp")).read()
+    marker = '#define DMSA_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))'
+    assert marker in src
+    (tmp_path / "host_solve_noclone.cpp").write_text(src.replace(marker, "#define DMSA_CLONES"))
+    exe = str(tmp_path / "solver_pool_tsan")
+    cmd = [cxx, "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-mavx2", "-ffp-contract=off", "-pthread", "-o", exe,
+           os.path.join(ROOT, "tests", "cpp", "solver_pool_tsan.cpp"), str(tmp_path / "host_solve_noclone.cpp")]
+    b = subprocess.run(cmd, capture_output=True, text=True)
+    if b.returncode != 0 and "tsan" in (b.stderr + b.stdout).lower():
+        pytest.skip("ThreadSanitizer runtime not available")
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, DMSA_B200_SOLVER_THREADS="1"))
+    assert "mismatches 0" in r.stdout, r.stdout + r.stderr[-2000:]
+    assert "ThreadSanitizer" not in r.stderr and r.returncode == 0, r.stderr[-3000:]
