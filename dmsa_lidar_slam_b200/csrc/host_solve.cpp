@@ -99,9 +99,12 @@ struct SolvePool {
         if (!th.empty() || disabled) return;
         // Three helper threads take cache-line aligned column blocks of the inverse while the caller takes the first
         // (measured on the B200 host, P = 114: 0.25 ms alone, 0.19 ms with helpers).  DMSA_B200_SOLVER_THREADS=0 turns
-        // them off; they are also off on hosts with fewer than 8 hardware threads.
+        // them off, =1 forces them on; by default they need 8 hardware threads PER LOCAL RANK (one process per GPU under
+        // torchrun: LOCAL_WORLD_SIZE), so that N ranks on a small host do not oversubscribe it with spinning helpers.
         const char* e = std::getenv("DMSA_B200_SOLVER_THREADS");
-        if ((e && std::atoi(e) <= 0) || (!e && std::thread::hardware_concurrency() < 8)) {
+        const char* lws = std::getenv("LOCAL_WORLD_SIZE");
+        const unsigned ranks = (lws && std::atoi(lws) > 0) ? (unsigned)std::atoi(lws) : 1u;
+        if ((e && std::atoi(e) <= 0) || (!e && std::thread::hardware_concurrency() / ranks < 8)) {
             disabled = true;
             return;
         }
