@@ -176,6 +176,26 @@ public:
         if (verbose && rep.stop_reason != DMSA_B200_STOP_MAX_ITER) std::printf("%s after iteration %d . . . \n", message(rep.stop_reason), rep.iterations - 1);
         return OptimReport{rep.iterations, rep.stop_reason, rep.num_gaussians, rep.error0};
     }
+
+    // ---- the nearest-neighbour step right before the sliding-window pass ----
+    // DmsaSlam.h:304-339 for one keyframe cloud in the world frame, against the window cloud staged by the last optimizeSet /
+    // update_global_points of this optimizer: selected[j] in {0, 1}; returns currOverlap.
+    int64_t selectStaticPoints(const dmsa_b200_point_normal* cloud, int64_t n, const float pos[3], float maxDist, uint8_t* selected) {
+        int64_t cnt = 0;
+        check(dmsa_b200_select_static_points(ctx_, cloud, n, pos, maxDist, selected, &cnt), "select_static_points");
+        return cnt;
+    }
+    // getOverlap(pc1, window cloud, maxDistOverlap), DmsaSlam.h:377-414
+    float getOverlap(const float* pc1_xyzw, int64_t n1, float maxDistOverlap) {
+        float ov = 0.0f;
+        check(dmsa_b200_overlap(ctx_, pc1_xyzw, n1, maxDistOverlap, &ov), "overlap");
+        return ov;
+    }
+
+    // ---- switches (every alternative is bit-identical) ----
+    void setLmSolverOnDevice(bool on) { check(dmsa_b200_set_lm_solver(ctx_, on ? 0 : 1), "set_lm_solver"); }
+    void setPairPackedKernels(bool on) { check(dmsa_b200_set_pair_mode(ctx_, on ? 1 : 0), "set_pair_mode"); }
+    void setReferenceOrderMean(bool on) { check(dmsa_b200_set_mean_mode(ctx_, on ? 1 : 0), "set_mean_mode"); }
 };
 
 }  // namespace dmsa_b200
