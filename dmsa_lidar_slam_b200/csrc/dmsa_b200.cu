@@ -764,6 +764,8 @@ phase2:
 int runCost(dmsa_b200_ctx* ctx) {
     const int V = ctx->curV, Vld = ctx->curVld, G = ctx->G, E = numExtra(ctx);
     if (Vld > 1024) ARGFAIL("more than 1023 pose parameters are not supported by the cost kernels");
+    if (ctx->model == MODEL_TRAJ && ctx->useImu && !ctx->imuSet)
+        ARGFAIL("cost evaluation: traj_init was called with use_imu = 1 but the IMU factors of this window are missing: call traj_set_imu_factors after traj_init");
     CK(ctx->d_S.ensure(ctx->chunkBound * 3 * Vld));
     CK(ctx->d_Q.ensure(ctx->chunkBound * Vld));
     CK(ctx->d_E.ensure((size_t)(G + E) * Vld));
@@ -1446,6 +1448,8 @@ int dmsa_b200_traj_get_tform_ids(dmsa_b200_ctx* ctx, int32_t* out) {
 int dmsa_b200_traj_set_imu_factors(dmsa_b200_ctx* ctx, const double* preint_rot, const double* preint_pos, const double* preint_vel,
                                    const double* cov_inv, double balancing_imu, const double* gravity3) {
     if (ctx->model != MODEL_TRAJ) ARGFAIL("set_imu_factors: no trajectory model");
+    if (!preint_rot || !preint_pos || !preint_vel || !cov_inv) ARGFAIL("set_imu_factors: null factor array (preint_rot / preint_pos / preint_vel / cov_inv)");
+    CK(cudaSetDevice(ctx->device));
     const int n = ctx->poses.n;
     CK(ctx->d_imu.ensure((size_t)n * (9 + 3 + 3 + 81)));
     double* d = ctx->d_imu.p;
@@ -1535,6 +1539,9 @@ int dmsa_b200_kf_commit(dmsa_b200_ctx* ctx) {
 
 int dmsa_b200_kf_set_gravity_terms(dmsa_b200_ctx* ctx, const double* measured_gravity, const int32_t* plausible, double balance) {
     if (ctx->model != MODEL_KF) ARGFAIL("kf_set_gravity_terms: no keyframe model");
+    if (!measured_gravity || !plausible) ARGFAIL("kf_set_gravity_terms: null array");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
     const int n = ctx->poses.n;
     CK(ctx->d_kfD.ensure((size_t)n * 15));
     CK(ctx->d_plausible.ensure(n));
@@ -1547,6 +1554,9 @@ int dmsa_b200_kf_set_gravity_terms(dmsa_b200_ctx* ctx, const double* measured_gr
 
 int dmsa_b200_kf_set_odometry_terms(dmsa_b200_ctx* ctx, const double* rel_transl, const double* rel_orient_mat, double balance) {
     if (ctx->model != MODEL_KF) ARGFAIL("kf_set_odometry_terms: no keyframe model");
+    if (!rel_transl || !rel_orient_mat) ARGFAIL("kf_set_odometry_terms: null array");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
     const int n = ctx->poses.n;
     CK(ctx->d_kfD.ensure((size_t)n * 15));
     CK(ctx->d_plausible.ensure(n));
@@ -1642,6 +1652,7 @@ int dmsa_b200_build_sets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings,
     if (num_gaussians) *num_gaussians = ctx->G;
     if (num_memberships) {
         std::vector<int> n(ctx->G);
+        CK(cudaStreamSynchronize(ctx->stream));
         if (ctx->G) CK(cudaMemcpy(n.data(), ctx->d_cell_n.p, (size_t)ctx->G * sizeof(int), cudaMemcpyDeviceToHost));
         int64_t M = 0;
         for (int v : n) M += v;
@@ -1655,6 +1666,9 @@ int dmsa_b200_get_sets(dmsa_b200_ctx* ctx, int64_t* offsets, int32_t* members, f
     const int G = ctx->G;
     const int64_t N = numPoints(ctx);
     std::vector<int> start(G), n(G);
+    // the set statistics run asynchronously on the context's (non-blocking) streams; stream2 is joined into ctx->stream by
+    // buildSets, so one synchronisation here orders every blocking copy below behind them
+    CK(cudaStreamSynchronize(ctx->stream));
     if (G) {
         CK(cudaMemcpy(start.data(), ctx->d_cell_start.p, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(n.data(), ctx->d_cell_n.p, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1683,6 +1697,7 @@ int dmsa_b200_get_sets(dmsa_b200_ctx* ctx, int64_t* offsets, int32_t* members, f
 int dmsa_b200_get_voxel_keys(dmsa_b200_ctx* ctx, int32_t level, int32_t* keys, int64_t* root_lo, int32_t* depth) {
     if (level < 0 || level > 1 || !ctx->levelOn[level]) ARGFAIL("get_voxel_keys: level not built");
     const int64_t N = numPoints(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
     if (keys) CK(cudaMemcpy(keys, ctx->d_keys.p + (size_t)3 * N * level, (size_t)3 * N * sizeof(int), cudaMemcpyDeviceToHost));
     if (root_lo)
         for (int a = 0; a < 3; ++a) root_lo[a] = ctx->h_linfo[level].lo[a];
@@ -1816,11 +1831,11 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
     return 0;
 }
 
-// Which solver dmsa_b200_iteration / dmsa_b200_optimize use for the LM step: 0 (default) the device kernel k_lm_solve
-// (no host round trip between the Jacobian pass and the line search), 1 the host solver.  Same operation sequence,
-// bit-identical steps.
+// Which solver dmsa_b200_iteration / dmsa_b200_optimize use for the LM step: 1 (default) the host solver, 0 the device
+// kernels (no host round trip between the Jacobian pass and the line search; P <= 128, larger systems use the host
+// solver in either mode).  Same operation sequence, bit-identical steps.
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode) {
-    if (mode != 0 && mode != 1) ARGFAIL("set_lm_solver: 0 (device, default) or 1 (host)");
+    if (mode != 0 && mode != 1) ARGFAIL("set_lm_solver: 1 (host, default) or 0 (device)");
     ctx->solverMode = mode;
     return 0;
 }
@@ -1947,6 +1962,7 @@ int dmsa_b200_overlap(dmsa_b200_ctx* ctx, const float* pc1_xyzw, int64_t n1, flo
 // ---- multi-GPU row sharding -----------------------------------------------------------------------------
 int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world) {
     if (world < 1 || rank < 0 || rank >= world) ARGFAIL("set_shard: bad rank/world");
+    if (rank != ctx->rank || world != ctx->world) ctx->G = 0;  // the ownership plan of the last build_sets is stale
     ctx->rank = rank;
     ctx->world = world;
     return 0;

@@ -115,9 +115,11 @@ struct SolvePool {
         for (;;) {
             {
                 std::unique_lock<std::mutex> lk(m);
-                cv.wait(lk, [&] { return stop || armed.load() > 0; });
+                cv.wait(lk, [&] { return stop || armed.load() > 0 || gen.load() != seen; });
                 if (stop) return;
             }
+            // `armed` is a reference count: every arm() holds one reference and the publisher of a job holds one for the
+            // job's duration, so a published generation is always consumed (the count cannot reach 0 while a job is open)
             while (armed.load(std::memory_order_acquire) > 0) {
                 const unsigned long long g = gen.load(std::memory_order_acquire);
                 if (g != seen) {
@@ -144,15 +146,20 @@ struct SolvePool {
 SolvePool g_pool;
 }  // namespace
 
-void dmsa_host_solver_arm() {
-    g_pool.start();
+static void pool_ref() {
     {
         std::lock_guard<std::mutex> lk(g_pool.m);
-        g_pool.armed.store(1, std::memory_order_release);
+        g_pool.armed.fetch_add(1, std::memory_order_acq_rel);
     }
     g_pool.cv.notify_all();
 }
-void dmsa_host_solver_disarm() { g_pool.armed.store(0, std::memory_order_release); }
+static void pool_unref() { g_pool.armed.fetch_sub(1, std::memory_order_acq_rel); }
+// arm / disarm are reference counted: two contexts solving on two host threads cannot switch each other's helpers off
+void dmsa_host_solver_arm() {
+    g_pool.start();
+    pool_ref();
+}
+void dmsa_host_solver_disarm() { pool_unref(); }
 
 // LU + substitution of P*I into a cache-line aligned, padded block x (n x ldx, ldx a multiple of 8 doubles: the helper
 // threads own whole lines of every row).  a: n x n row-major, factorised in place.  Scratch lives in thread-local
@@ -173,9 +180,11 @@ static double* lu_inverse_padded(std::vector<double>& a, int n, int& ldx_out) {
         g_pool.n = n;
         g_pool.ldx = ldx;
         g_pool.remaining.store(SolvePool::kWorkers, std::memory_order_release);
+        pool_ref();  // the publisher's own reference: the helpers stay in their spin loop until this job is consumed
         g_pool.gen.fetch_add(1, std::memory_order_acq_rel);
         lu_subst_block_impl(a.data(), x, n, ldx, 0, std::min(n, colBlock(n)));
         while (g_pool.remaining.load(std::memory_order_acquire) > 0) __builtin_ia32_pause();
+        pool_unref();
         g_pool.busy.clear(std::memory_order_release);
     } else {
         lu_subst_block_impl(a.data(), x, n, ldx, 0, n);

@@ -204,8 +204,9 @@ int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, doub
 int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, int32_t explicit_inverse, double* step,
                        int32_t* has_nan);
 
-/* Solver of the LM step inside dmsa_b200_iteration / dmsa_b200_optimize (DmsaOptimizer.h:107-128): 0 (default) = device
- * kernel (the iteration then has no host round trip between the Jacobian pass and the line search), 1 = host solver.
+/* Solver of the LM step inside dmsa_b200_iteration / dmsa_b200_optimize (DmsaOptimizer.h:107-128): 1 (default) = host
+ * solver, 0 = device kernels for P <= 128 (the iteration then has no host round trip between the Jacobian pass and the
+ * line search; larger systems use the host solver in either mode).
  * Both run the same operation sequence (LU with partial pivoting, explicit inverse, ascending accumulation): bit-identical. */
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode);
 /* Cost kernels of the forward-difference batch (V = P + 1 vectors): 1 (default) = two vectors per thread with Blackwell's
