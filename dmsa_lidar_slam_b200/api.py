@@ -80,6 +80,8 @@ def load_library():
         "dmsa_b200_launch_count": (i64, [vp]),
         "dmsa_b200_synchronize": (i32, [vp]),
         "dmsa_b200_traj_init": (i32, [vp, f64, f64, i32, i32, f64]),
+        "dmsa_b200_traj_init_window": (i32, [vp, f64, f64, i32, i32, f64]),
+        "dmsa_b200_traj_get_dense_poses": (i32, [vp, vp, vp]),
         "dmsa_b200_traj_register_scans": (i32, [vp, i32, P(vp), P(i64), P(f32)]),
         "dmsa_b200_traj_add_static_points": (i32, [vp, vp, i64]),
         "dmsa_b200_traj_remove_static_points": (i32, [vp]),
@@ -144,7 +146,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode",
-    "dmsa_b200_select_static_points", "dmsa_b200_overlap",
+    "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
 ]
 
 
@@ -423,6 +425,13 @@ class ContinuousTrajectory(OptimizablePointSet):
         out = np.zeros((nt, 12), dtype=np.float32)
         self.ctx._ck(self.L.dmsa_b200_traj_get_dense_tforms(self.h, _p(out)))
         return out
+
+    def denseGlobalPoses(self):
+        """denseGlobalPoses (ContinuousTrajectory.h:29): (orientations 3 x n_total, translations 3 x n_total) doubles."""
+        nt = self.timing()["n_total"]
+        o, t = np.zeros((nt, 3)), np.zeros((nt, 3))
+        self.ctx._ck(self.L.dmsa_b200_traj_get_dense_poses(self.h, _p(o), _p(t)))
+        return o.T.copy(), t.T.copy()
 
     def setImuFactors(self, preint_rot, preint_pos, preint_vel, cov_inv, balancing=0.001, gravity=(0.0, 0.0, -9.805)):
         a = [_c64(preint_rot), _c64(preint_pos), _c64(preint_vel), _c64(cov_inv), _c64(gravity)]

@@ -173,7 +173,7 @@ struct dmsa_b200_ctx {
     DBuf<int> d_tid, d_ring, d_flag;
 
     // pose batches
-    DBuf<double> d_p, d_step, d_batch, d_globO, d_globT, d_quat, d_extra;
+    DBuf<double> d_p, d_step, d_batch, d_globO, d_globT, d_quat, d_extra, d_dense;
     DBuf<float> d_Mtab, d_Mpair;
     int pairMode = 1;  // 1: pair-packed cost kernels (FMUL2/FADD2) for the forward-difference batch, 0: scalar kernels; bit-identical
     int curV = 0, curVld = 0;
@@ -1201,7 +1201,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
 #define REL(b) ctx->b.release()
     REL(d_stamps); REL(d_trajTime); REL(d_urel); REL(d_fh); REL(d_seg); REL(d_hit); REL(d_paramIdx); REL(d_imu); REL(d_kfD); REL(d_plausible);
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
-    REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_Mtab); REL(d_Mpair);
+    REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_dense); REL(d_Mtab); REL(d_Mpair);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
@@ -1222,14 +1222,21 @@ int dmsa_b200_synchronize(dmsa_b200_ctx* ctx) {
 
 // ---- trajectory model ---------------------------------------------------------------------------
 int dmsa_b200_traj_init(dmsa_b200_ctx* ctx, double t_min, double t_max, int32_t n_poses, int32_t use_imu, double dt_res) {
+    return dmsa_b200_traj_init_window(ctx, t_min, t_max - t_min + dt_res /* :309 */, n_poses, use_imu, dt_res);
+}
+
+// initTraj given the members it leaves behind (t0, horizon): what a binding that sees an already initialised
+// ContinuousTrajectory passes, so that `horizon` is the very double the reference computed (no re-derived t_max).
+int dmsa_b200_traj_init_window(dmsa_b200_ctx* ctx, double t0, double horizon, int32_t n_poses, int32_t use_imu, double dt_res) {
     if (n_poses < 3) ARGFAIL("traj_init: barycentric_rational of order 2 needs at least 3 control poses");
+    if (!(horizon > 0.0) || !(dt_res > 0.0)) ARGFAIL("traj_init: horizon and dt_res must be positive");
     CK(cudaSetDevice(ctx->device));
     ctx->model = MODEL_TRAJ;
     ctx->dt_res = dt_res;
     ctx->useImu = use_imu != 0;
     ctx->imuSet = false;
-    ctx->t0 = t_min;
-    ctx->horizon = t_max - t_min + dt_res;                             // :309
+    ctx->t0 = t0;
+    ctx->horizon = horizon;
     ctx->n_total = (int)std::round(ctx->horizon / dt_res) + 1;          // :310
     const int nt = ctx->n_total, n = n_poses;
     // every table below depends on (horizon, n_poses, dt_res) only - all times are relative to t_min - so a window with the
@@ -1643,6 +1650,34 @@ int dmsa_b200_traj_get_dense_tforms(dmsa_b200_ctx* ctx, float* out) {
     // column v = 0 of the table
     CK(cudaMemcpy2DAsync(out, 48, ctx->d_Mtab.p, (size_t)ctx->curVld * 48, 48, ctx->n_total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// denseGlobalPoses of the current parameters (ContinuousTrajectory.h:194-218): 3 x n_total column-major doubles each
+int dmsa_b200_traj_get_dense_poses(dmsa_b200_ctx* ctx, double* orient, double* transl) {
+    if (ctx->model != MODEL_TRAJ || ctx->curVld == 0) ARGFAIL("get_dense_poses: call update_global_points first");
+    CK(cudaSetDevice(ctx->device));
+    const int nt = ctx->n_total;
+    CK(ctx->d_dense.ensure((size_t)6 * nt));
+    PoseBatch pb;
+    memset(&pb, 0, sizeof(pb));
+    pb.V = ctx->curV;
+    pb.Vld = ctx->curVld;
+    pb.n = ctx->poses.n;
+    pb.globO_t = ctx->d_globO.p;
+    pb.globT_t = ctx->d_globT.p;
+    pb.quat_t = ctx->d_quat.p;
+    TrajTiming tt;
+    tt.n_total = nt;
+    tt.seg = ctx->d_seg.p;
+    tt.urel = ctx->d_urel.p;
+    tt.fh = ctx->d_fh.p;
+    tt.hit = ctx->d_hit.p;
+    LAUNCH(k_dense_poses, cdiv(nt, 128), 128, 0, pb, tt, 0, ctx->d_dense.p, ctx->d_dense.p + (size_t)3 * nt);
+    if (orient) CK(cudaMemcpyAsync(orient, ctx->d_dense.p, (size_t)3 * nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (transl) CK(cudaMemcpyAsync(transl, ctx->d_dense.p + (size_t)3 * nt, (size_t)3 * nt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
     return 0;
 }
 

@@ -263,23 +263,10 @@ __global__ void k_pose_chain(PoseBatch pb, float* __restrict__ Mtab, ImuFactors 
     }
 }
 
-// Dense trajectory table: thread (v, j).  ContinuousTrajectory.h:194-225.
-__global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ Mtab) {
-    const int v = blockIdx.x * 32 + threadIdx.x;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y;
-    if (v >= pb.V || j > tt.n_total) return;
+// Dense pose of sample j for vector v: orientation (:194-198, :570-591) and translation (:201-218)
+__device__ __forceinline__ void dense_pose(const PoseBatch& pb, const TrajTiming& tt, int v, int j, Vec3& aa, double T[3]) {
     const int n = pb.n, Vld = pb.Vld;
-    if (j == tt.n_total) {  // identity row: static points (already in the world frame) go through the same code path
-        float4* M = reinterpret_cast<float4*>(Mtab + ((size_t)j * Vld + v) * 12);
-        M[0] = make_float4(1.f, 0.f, 0.f, 0.f);
-        M[1] = make_float4(0.f, 1.f, 0.f, 0.f);
-        M[2] = make_float4(0.f, 0.f, 1.f, 0.f);
-        store_pair_entry(pb.Mpair, j, v, Vld, M[0], M[1], M[2]);
-        return;
-    }
-    // orientation (:194-198, :570-591)
     const int r = tt.seg[j];
-    Vec3 aa;
     if (r > 0) {
         Quat q1, q2;
         q1.w = pb.quat_t[(size_t)(4 * (r - 1) + 0) * Vld + v];
@@ -294,8 +281,7 @@ __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ M
     } else {
         aa = mk3(pb.globO_t[(size_t)0 * Vld + v], pb.globO_t[(size_t)1 * Vld + v], pb.globO_t[(size_t)2 * Vld + v]);
     }
-    // translation (:201-218): Boost barycentric_rational::operator()
-    double T[3];
+    // Boost barycentric_rational::operator()
     const int hi = tt.hit[j];
     if (hi >= 0) {
 #pragma unroll
@@ -313,6 +299,25 @@ __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ M
 #pragma unroll
         for (int a = 0; a < 3; ++a) T[a] = num[a] / den;
     }
+}
+
+// Dense trajectory table: thread (v, j).  ContinuousTrajectory.h:194-225.
+__global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ Mtab) {
+    const int v = blockIdx.x * 32 + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (v >= pb.V || j > tt.n_total) return;
+    const int Vld = pb.Vld;
+    if (j == tt.n_total) {  // identity row: static points (already in the world frame) go through the same code path
+        float4* M = reinterpret_cast<float4*>(Mtab + ((size_t)j * Vld + v) * 12);
+        M[0] = make_float4(1.f, 0.f, 0.f, 0.f);
+        M[1] = make_float4(0.f, 1.f, 0.f, 0.f);
+        M[2] = make_float4(0.f, 0.f, 1.f, 0.f);
+        store_pair_entry(pb.Mpair, j, v, Vld, M[0], M[1], M[2]);
+        return;
+    }
+    Vec3 aa;
+    double T[3];
+    dense_pose(pb, tt, v, j, aa, T);
     // :221-225
     Mat3 R = so3_exp(aa);
     float4* M = reinterpret_cast<float4*>(Mtab + ((size_t)j * Vld + v) * 12);
@@ -323,6 +328,21 @@ __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ M
     M[1] = r1;
     M[2] = r2;
     store_pair_entry(pb.Mpair, j, v, Vld, r0, r1, r2);
+}
+
+// denseGlobalPoses of vector v (the double poses behind the table): orient / transl are 3 x n_total column-major
+__global__ void k_dense_poses(PoseBatch pb, TrajTiming tt, int v, double* __restrict__ orient, double* __restrict__ transl) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= tt.n_total) return;
+    Vec3 aa;
+    double T[3];
+    dense_pose(pb, tt, v, j, aa, T);
+    orient[3 * (size_t)j] = aa.x;
+    orient[3 * (size_t)j + 1] = aa.y;
+    orient[3 * (size_t)j + 2] = aa.z;
+    transl[3 * (size_t)j] = T[0];
+    transl[3 * (size_t)j + 1] = T[1];
+    transl[3 * (size_t)j + 2] = T[2];
 }
 
 }  // namespace dmsa

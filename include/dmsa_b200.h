@@ -104,6 +104,9 @@ int dmsa_b200_synchronize(dmsa_b200_ctx* ctx);
 /* ---- sliding-window model: hot members of ContinuousTrajectory ---------------------------- */
 /* initTraj(t_min, t_max, numControlPoses, useImu, dt_res)        ContinuousTrajectory.h:301-346 */
 int dmsa_b200_traj_init(dmsa_b200_ctx* ctx, double t_min, double t_max, int32_t n_poses, int32_t use_imu, double dt_res);
+/* the same, given the members initTraj leaves behind (t0, horizon = t_max - t_min + dt_res): what a binding passes that
+ * sees an already initialised ContinuousTrajectory (ContinuousTrajectory.h:46-49), so `horizon` is not re-derived */
+int dmsa_b200_traj_init_window(dmsa_b200_ctx* ctx, double t0, double horizon, int32_t n_poses, int32_t use_imu, double dt_res);
 /* registerPcBuffer: scans in chronological ring-buffer order; computes tformIdPerPoint on device,
  * minGridSize = min(grid_sizes)                                  ContinuousTrajectory.h:228-261 */
 int dmsa_b200_traj_register_scans(dmsa_b200_ctx* ctx, int32_t n_scans, const dmsa_b200_point_stamp_id* const* scans,
@@ -150,6 +153,9 @@ int64_t dmsa_b200_num_points(const dmsa_b200_ctx* ctx);
 int dmsa_b200_get_global_points(dmsa_b200_ctx* ctx, float* xyzw, float* normals);
 /* dense local->global transforms of the current parameters: n_total x 12 floats (rows 0..2 of Matrix4f) */
 int dmsa_b200_traj_get_dense_tforms(dmsa_b200_ctx* ctx, float* out);
+/* denseGlobalPoses of the current parameters (ContinuousTrajectory.h:29, 194-218): orientations (axis-angle) and
+ * translations, 3 x n_total column-major doubles each (either may be NULL) */
+int dmsa_b200_traj_get_dense_poses(dmsa_b200_ctx* ctx, double* orient, double* transl);
 
 /* reset + createGaussianSets(res1) + createGaussianSets(res2) + updateRebalancingWeights on the current
  * global points                                   DmsaOptimizer.h:78-96, 275-350; Gaussians.h:130-201 */
