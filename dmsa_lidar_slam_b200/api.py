@@ -81,6 +81,10 @@ def load_library():
         "dmsa_b200_synchronize": (i32, [vp]),
         "dmsa_b200_traj_init": (i32, [vp, f64, f64, i32, i32, f64]),
         "dmsa_b200_traj_init_window": (i32, [vp, f64, f64, i32, i32, f64]),
+        "dmsa_b200_comm_unique_id": (i32, [vp]),
+        "dmsa_b200_comm_init": (i32, [vp, vp, i32, i32]),
+        "dmsa_b200_comm_destroy": (i32, [vp]),
+        "dmsa_b200_collective_count": (i64, [vp]),
         "dmsa_b200_traj_get_dense_poses": (i32, [vp, vp, vp]),
         "dmsa_b200_traj_register_scans": (i32, [vp, i32, P(vp), P(i64), P(f32)]),
         "dmsa_b200_traj_add_static_points": (i32, [vp, vp, i64]),
@@ -147,6 +151,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode",
     "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
+    "dmsa_b200_comm_unique_id", "dmsa_b200_comm_init", "dmsa_b200_comm_destroy", "dmsa_b200_collective_count",
 ]
 
 
@@ -378,6 +383,18 @@ class OptimizablePointSet:
     def setShard(self, rank, world):
         self.ctx._ck(self.L.dmsa_b200_set_shard(self.h, int(rank), int(world)))
 
+    def commInit(self, unique_id: bytes, rank, world):
+        """Row sharding across ranks with the in-library NCCL exchange (every rank stages the same set)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.ctx._ck(self.L.dmsa_b200_comm_init(self.h, buf, int(rank), int(world)))
+
+    def commDestroy(self):
+        self.ctx._ck(self.L.dmsa_b200_comm_destroy(self.h))
+
+    @property
+    def collective_count(self):
+        return self.L.dmsa_b200_collective_count(self.h)
+
 
 class ContinuousTrajectory(OptimizablePointSet):
     """Sliding-window model.  Mirrors ContinuousTrajectory: initTraj, registerPcBuffer, add/removeStaticPoints."""
@@ -505,6 +522,16 @@ class DmsaOptimizer:
         self.last_report = rep.asdict()
         s._G = rep.num_gaussians
         return self.last_report
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id for dmsa_b200_comm_init: create on rank 0, broadcast to the other ranks."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.dmsa_b200_comm_unique_id(buf)
+    if rc != 0:
+        raise DmsaError(f"dmsa_b200_comm_unique_id failed ({rc}): is libnccl.so.2 loadable?")
+    return buf.raw
 
 
 def lm_solve(settings, hg, n_params, explicit_inverse=True):

@@ -22,6 +22,7 @@
 #include "kernels_knn.cuh"
 #include "kernels_pose.cuh"
 #include "kernels_sets.cuh"
+#include "nccl_dyn.h"
 #include "se3_math.cuh"
 
 using namespace dmsa;
@@ -135,8 +136,10 @@ struct dmsa_b200_ctx {
     int64_t launches = 0;
     int model = MODEL_NONE;
     int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;  // set by dmsa_b200_comm_init: the row-sharded iteration all-reduces [H | g | e0^T e0] and the 9 trial costs
+    int64_t collectives = 0;    // NCCL all-reduces issued on the context's stream
     bool worldValid = false;  // globalPoints on the device correspond to the staged points (set by the base transform)
-    int solverMode = 1;  // 1 (default): LM step solved on the host (host_solve.cpp), 0: on the device (kernels_solve.cuh); bit-identical
+    int solverMode = 0;  // 0 (default): LM step solved on the device for P <= 128 (kernels_solve.cuh), 1: on the host (host_solve.cpp); bit-identical
     int meanMode = 0;  // 0: order-free exactly-rounded mean (default), 1: the reference's sequential float accumulation
 
     HostPoses poses;
@@ -191,7 +194,9 @@ struct dmsa_b200_ctx {
     DBuf<int> d_cell_start, d_cell_n, d_cell_level, d_cell_key, d_cell_sub, d_cell_kind, d_nchunk, d_chunk_off, d_okey, d_oval;
     DBuf<float> d_cell_info, d_cell_w0, d_cell_w;
     DBuf<Chunk> d_chunks;
-    int G = 0;
+    int G = 0;       // accepted sets of the last build (host copy; -1 while a deferred build's count is still on the device only)
+    int Gb = 0;      // bound the per-set grids / buffers of the last build were sized for (== G after a synchronous build)
+    int Gguess = 0;  // set count of the previous build of this context: sizes the grids of a deferred build (verified late)
     int64_t M = 0;
     bool levelOn[2] = {false, false};
     int cachedDepth[2] = {0, 0};
@@ -207,8 +212,6 @@ struct dmsa_b200_ctx {
     DBuf<unsigned char> d_gsel;
     DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart, d_solve, d_iter;
     bool solveAttr = false;
-    bool solveGeneral = false;  // force the general one-block kernel (any P <= 1024) instead of the P <= 128 fast path
-    long long* solveClk = nullptr;  // debug: device buffer of phase cycle stamps (dmsa_b200_lm_solve_device with DMSA_B200_SOLVE_CLK=1)
     DBuf<int> d_biglist;  // sets with more than GAUSS_WARP_MAX members (+ the count at [cellCap])
     DBuf<int> d_done;  // per-set completion counters of k_cost_quad [0, cap] and k_cost_sum [cap + 1, 2 cap + 1] (zeroed by the set build, self-resetting)
     DBuf<float> d_mu;  // means of the sets cut into more than MEAN_INLINE_MAX chunks [(g*3 + a) * Vld + v]
@@ -525,7 +528,10 @@ int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
 }
 
 // reset + both createGaussianSets + updateRebalancingWeights + work decomposition   DmsaOptimizer.h:78-96
-int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
+// defer = true (inside an iteration, when a previous build gives a grid-size guess): no host synchronisation at all; the
+// set count stays on the device (LevelInfo::G), the kernels behind the build read it there, and the caller verifies the
+// guess (and the octree depth guess) with the iteration's single read-back.
+int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = false) {
     const int64_t N64 = numPoints(ctx);
     if (N64 <= 0 || N64 > 0x3fffffff) ARGFAIL("build_sets: no points staged (or more than 2^30)");
     if (!ctx->worldValid) ARGFAIL("build_sets: call update_global_points first (the sets are built on globalPoints)");
@@ -589,6 +595,11 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     cs.w0 = ctx->d_cell_w0.p;
     cs.w = ctx->d_cell_w.p;
 
+    // a deferred build sizes every per-set grid and row buffer from the previous build's count (verified by the caller)
+    for (int l = 0; l < 2; ++l)
+        if ((l == 0 ? st->grid_size_1_factor : st->grid_size_2_factor) > std::numeric_limits<float>::min() && ctx->cachedDepth[l] <= 0) defer = false;
+    if (ctx->Gguess <= 0) defer = false;
+    const int deferBound = defer ? (int)std::min<int64_t>(cap, (int64_t)ctx->Gguess + ctx->Gguess / 4 + 1024) : cap;
     const float factors[2] = {st->grid_size_1_factor, st->grid_size_2_factor};
     for (int l = 0; l < 2; ++l) ctx->levelOn[l] = factors[l] > std::numeric_limits<float>::min();  // DmsaOptimizer.h:81,85
     CK(cudaMemsetAsync(ctx->d_linfo.p, 0, 2 * sizeof(LevelInfo), ctx->stream));
@@ -604,7 +615,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
         plan.n++;
     }
     if (plan.n > 0) {
-        LAUNCH(k_anchor, 1, 32, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p);
+        LAUNCH(k_anchor, 1, 32, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, deferBound);
         LAUNCH(k_keys, dim3(nb, plan.n), DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_keys.p, ctx->d_bb.p, nb);
         LAUNCH(k_root, plan.n, 1024, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_bb.p, nb);
     }
@@ -618,6 +629,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st) {
     bool haveGuess = true;
     for (int l = 0; l < 2; ++l)
         if (ctx->levelOn[l] && depthUsed[l] <= 0) haveGuess = false;
+    if (!haveGuess || ctx->Gguess <= 0) defer = false;
     if (!haveGuess) {
         CKRC(ensurePinned(ctx, Ppin));
         CK(cudaMemcpyAsync(pinLinfo(ctx, Ppin), ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
@@ -697,6 +709,11 @@ phase2:
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
     }
     }
+    int Gb = 0;
+    if (defer) {
+        Gb = deferBound;
+        ctx->G = -1;
+    } else {
     CKRC(ensurePinned(ctx, Ppin));
     CK(cudaMemcpyAsync(pinLinfo(ctx, Ppin), ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -721,9 +738,15 @@ phase2:
         if (ctx->levelOn[l]) G += ctx->h_linfo[l].G;
     if (G > cap) ARGFAIL("build_sets: Gaussian store capacity exceeded");
     ctx->G = G;
+    ctx->Gguess = G;
+    ctx->Gb = G;
     ctx->M = 0;
     if (G == 0) return 0;
-    // phase 3: per-set statistics, weights, chunk list
+    Gb = G;
+    }
+    ctx->Gb = Gb;
+    const LevelInfo* li = ctx->d_linfo.p;
+    // phase 3: per-set statistics, weights, chunk list (grids sized for Gb sets; the kernels read the count on the device)
     ProfScope prof_(ctx, PROF_SETS_STATS);
     CK(ctx->d_okey.ensure((size_t)cap));
     CK(ctx->d_oval.ensure((size_t)2 * cap + 4 * ORDER_CLASSES));
@@ -741,20 +764,20 @@ phase2:
         CK(cudaEventRecord(ctx->evFork, ctx->stream));
         CK(cudaStreamWaitEvent(s2, ctx->evFork, 0));
         CK(cudaMemsetAsync(cnt, 0, sizeof(int), s2));
-        LAUNCH_ON(s2, k_gauss_list, cdiv(G, 256), 256, 0, cs, G, ctx->d_biglist.p, cnt);
+        LAUNCH_ON(s2, k_gauss_list, cdiv(Gb, 256), 256, 0, cs, li, ctx->d_biglist.p, cnt);
         LAUNCH_ON(s2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
-        LAUNCH_ON(s2, k_weights, 1, 1024, 0, cs, G);  // depends on the set sizes only
+        LAUNCH_ON(s2, k_weights, 1, 1024, 0, cs, li);  // depends on the set sizes only
         CK(cudaEventRecord(ctx->evJoin, s2));
-        LAUNCH(k_gaussian, cdiv((size_t)G * 32, 256), 256, 0, ctx->d_wrec.p, cs, G, ctx->d_mom.p);
+        LAUNCH(k_gaussian, cdiv((size_t)Gb * 32, 256), 256, 0, ctx->d_wrec.p, cs, li, ctx->d_mom.p);
         CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_done.p, 0, 2 * ((size_t)cap + 1) * sizeof(int), ctx->stream));
-        LAUNCH(k_cell_plan, cdiv(G, 256), 256, 0, cs, G, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
-        LAUNCH(k_cell_order, cdiv(G, 256), 256, 0, G, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
-        CK(cudaMemsetAsync(ctx->d_nchunk.p + G, 0, sizeof(int), ctx->stream));
-        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, G + 1, ctx->stream));
-        LAUNCH(k_chunk_fill, cdiv(G, 256), 256, 0, cs, G, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
+        CK(cudaMemsetAsync(ctx->d_nchunk.p, 0, ((size_t)Gb + 1) * sizeof(int), ctx->stream));  // entries behind the last set stay 0
+        LAUNCH(k_cell_plan, cdiv(Gb, 256), 256, 0, cs, li, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
+        LAUNCH(k_cell_order, cdiv(Gb, 256), 256, 0, li, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
+        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, Gb + 1, ctx->stream));  // [Gb] = total
+        LAUNCH(k_chunk_fill, cdiv(Gb, 256), 256, 0, cs, li, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
-        LAUNCH(k_gaussian_fin, cdiv(G, 128), 128, 0, cs, G, ctx->d_mom.p);
+        LAUNCH(k_gaussian_fin, cdiv(Gb, 128), 128, 0, cs, li, ctx->d_mom.p);
     }
     CK(cudaGetLastError());
     return 0;
@@ -762,7 +785,7 @@ phase2:
 
 // V cost evaluations on the tables in Mtab -> E rows [0, G) (+ extra rows)
 int runCost(dmsa_b200_ctx* ctx) {
-    const int V = ctx->curV, Vld = ctx->curVld, G = ctx->G, E = numExtra(ctx);
+    const int V = ctx->curV, Vld = ctx->curVld, G = ctx->Gb, E = numExtra(ctx);  // G: the bound the build sized its grids for
     if (Vld > 1024) ARGFAIL("more than 1023 pose parameters are not supported by the cost kernels");
     if (ctx->model == MODEL_TRAJ && ctx->useImu && !ctx->imuSet)
         ARGFAIL("cost evaluation: traj_init was called with use_imu = 1 but the IMU factors of this window are missing: call traj_set_imu_factors after traj_init");
@@ -772,7 +795,8 @@ int runCost(dmsa_b200_ctx* ctx) {
     CK(ctx->d_mu.ensure((size_t)G * 3 * Vld));
     CostArgs a;
     a.chunks = ctx->d_chunks.p;
-    a.n_chunks = ctx->d_chunk_off.p + G;
+    a.n_chunks = ctx->d_chunk_off.p + G;  // the scan ran over Gb + 1 entries, the ones behind the last set are 0
+    a.li = ctx->d_linfo.p;
     a.rec = ctx->d_rec.p;
     a.Mtab = reinterpret_cast<const float4*>(ctx->d_Mtab.p);
     a.Mpair = reinterpret_cast<const unsigned long long*>(ctx->d_Mpair.p);
@@ -799,8 +823,8 @@ int runCost(dmsa_b200_ctx* ctx) {
     const int ph = ctx->phase ? 1 : 0;
     if (ctx->meanMode == 1) {
         ProfScope p_(ctx, PROF_FUSED_FD + ph);
-        LAUNCH(k_cost_seq, G, Vld, 0, a, G);
-        if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        LAUNCH(k_cost_seq, G, Vld, 0, a);
+        if (E > 0) LAUNCH(k_append_extra, cdiv((size_t)E * Vld, 256), 256, 0, ctx->d_E.p, ctx->d_linfo.p, ctx->d_extra.p, E, Vld);
         CK(cudaGetLastError());
         return 0;
     }
@@ -825,9 +849,9 @@ int runCost(dmsa_b200_ctx* ctx) {
     {
         ProfScope p_(ctx, PROF_FUSED_FD + ph);
         if (pair) {
-            DISPATCH2(k_cost_fused2, G, a, G);
+            DISPATCH2(k_cost_fused2, G, a);
         } else {
-            DISPATCH(k_cost_fused, G, a, G);
+            DISPATCH(k_cost_fused, G, a);
         }
     }
     {
@@ -848,7 +872,7 @@ int runCost(dmsa_b200_ctx* ctx) {
     }
 #undef DISPATCH2
 #undef DISPATCH
-    if (E > 0) CK(cudaMemcpyAsync(ctx->d_E.p + (size_t)G * Vld, ctx->d_extra.p, (size_t)E * Vld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (E > 0) LAUNCH(k_append_extra, cdiv((size_t)E * Vld, 256), 256, 0, ctx->d_E.p, ctx->d_linfo.p, ctx->d_extra.p, E, Vld);
     CK(cudaGetLastError());
     return 0;
 }
@@ -863,32 +887,28 @@ int prepareFdBatch(dmsa_b200_ctx* ctx) {
 }
 
 int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
-    const int P = 6 * (ctx->poses.n - 1), R = ctx->G + numExtra(ctx), Vld = ctx->curVld;
+    const int P = 6 * (ctx->poses.n - 1), E = numExtra(ctx), Vld = ctx->curVld;
     const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
     const double inv_h = 1.0 / h;  // one_div_incr, DmsaOptimizer.h:210
     const int n1 = P + 1;
+    const LevelInfo* li = ctx->d_linfo.p;  // the row count G + E is read on the device; so is the row partition (jd_partition)
     if (n1 <= JD_MAXN) {
         // FP64 tensor cores (DMMA m8n8k4): one block per row range keeps every upper-triangular output tile in registers
-        int nblk = std::max(1, std::min(148, (R + JD_ROWS - 1) / JD_ROWS));
-        int rpb = ((R + nblk - 1) / nblk + JD_ROWS - 1) / JD_ROWS * JD_ROWS;
-        nblk = (R + rpb - 1) / rpb;
-        CK(ctx->d_jpart.ensure((size_t)nblk * n1 * n1));
+        CK(ctx->d_jpart.ensure((size_t)JD_MAXBLK * n1 * n1));
         ProfScope prof_(ctx, PROF_JTJ);
-        LAUNCH(k_jtj_dmma, nblk, JD_T, 0, ctx->d_E.p, R, Vld, P, inv_h, rpb, ctx->d_jpart.p);
-        LAUNCH(k_jtj_reduce8, cdiv((size_t)n1 * n1, 32), dim3(32, 8), 0, ctx->d_jpart.p, nblk, P, hg_dev);
+        LAUNCH(k_jtj_dmma, JD_MAXBLK, JD_T, 0, ctx->d_E.p, li, E, Vld, P, inv_h, ctx->d_jpart.p);
+        LAUNCH(k_jtj_reduce8, cdiv((size_t)n1 * n1, 32), dim3(32, 8), 0, ctx->d_jpart.p, li, E, P, hg_dev);
         CK(cudaGetLastError());
         return 0;
     }
-    int nsplit = std::max(1, std::min(64, (R + 127) / 128));  // enough blocks to fill the chip: the product is only ~0.2 GFLOP
-    int rps = ((R + nsplit - 1) / nsplit + JTJ_T - 1) / JTJ_T * JTJ_T;
-    nsplit = (R + rps - 1) / rps;
+    const int R = ctx->Gb + E;
+    int nsplit = std::max(1, std::min(JTJ_MAXSPLIT, (R + 127) / 128));  // upper bound of the device-side split count (monotone in R)
     const int nt = (n1 + JTJ_T - 1) / JTJ_T;
     CK(ctx->d_jpart.ensure((size_t)nsplit * n1 * n1));
-    CK(cudaMemsetAsync(ctx->d_jpart.p, 0, (size_t)nsplit * n1 * n1 * sizeof(double), ctx->stream));
     dim3 grid(nt * (nt + 1) / 2, nsplit);
     ProfScope prof_(ctx, PROF_JTJ);
-    LAUNCH(k_jtj, grid, 256, 0, ctx->d_E.p, R, Vld, P, inv_h, rps, ctx->d_jpart.p);
-    LAUNCH(k_jtj_reduce, cdiv((size_t)n1 * n1, 256), 256, 0, ctx->d_jpart.p, nsplit, P, hg_dev);
+    LAUNCH(k_jtj, grid, 256, 0, ctx->d_E.p, li, E, Vld, P, inv_h, ctx->d_jpart.p);
+    LAUNCH(k_jtj_reduce, cdiv((size_t)n1 * n1, 256), 256, 0, ctx->d_jpart.p, li, E, P, hg_dev);
     CK(cudaGetLastError());
     return 0;
 }
@@ -904,7 +924,7 @@ int lineSearchDev(dmsa_b200_ctx* ctx, double* ls_dev) {
     if (rc) return rc;
     ProfScope prof_(ctx, PROF_COLSUM);
     CK(ctx->d_lspart.ensure(9 * COLSUM_PARTS));
-    LAUNCH(k_col_sumsq, dim3(9, COLSUM_PARTS), 256, 0, ctx->d_E.p, ctx->G + numExtra(ctx), ctx->curVld, ctx->d_lspart.p);
+    LAUNCH(k_col_sumsq, dim3(9, COLSUM_PARTS), 256, 0, ctx->d_E.p, ctx->d_linfo.p, numExtra(ctx), ctx->curVld, ctx->d_lspart.p);
     LAUNCH(k_col_sumsq_fin, 1, 32, 0, ctx->d_lspart.p, ls_dev);
     CK(cudaGetLastError());
     return 0;
@@ -919,56 +939,43 @@ int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) 
     return lineSearchDev(ctx, ls_dev);
 }
 
-// LM step on the device (kernels_solve.cuh): hg_dev = [H | g | err0] -> d_step (+ copy in step2), tail = [err0, nan flag]
+// LM step on the device (kernels_solve.cuh, P <= 128): hg_dev = [H | g | err0] -> d_step (+ copy in step2), tail = [err0, nan flag]
 int lmSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, const double* hg_dev, double* step2, double* tail) {
-    if (P > LM_SOLVE_T) ARGFAIL("lm_solve: more than 1024 parameters are not supported by the device solver");
-    if (P <= LU_TILE_N && !ctx->solveGeneral) {
-        // fast path: register-tiled LU (one block) -> inverse columns (one warp per 32 columns) -> step
-        const int lda = P | 1;
-        CK(ctx->d_solve.ensure(2 * (size_t)P * lda + P + 2));
-        double* LU = ctx->d_solve.p;
-        double* X = LU + (size_t)P * lda;
-        int* piv = reinterpret_cast<int*>(X + (size_t)P * lda);
-        const size_t smem = ((size_t)P * lda + (size_t)P * 33) * sizeof(double);
-        if (!ctx->solveAttr) {
-            CK(cudaFuncSetAttribute(k_inv_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-            CK(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-            ctx->solveAttr = true;
-        }
-        ProfScope prof_(ctx, PROF_LM_SOLVE);
-        LuTileArgs la{hg_dev, P, lda, (double)st->lambda_diag, LU, piv};
-        LAUNCH(k_lu_tile, 1, LU_TILE_T, 0, la);
-        InvColsArgs ia{LU, piv, P, lda, X};
-        LAUNCH(k_inv_cols, (P + 31) / 32, INV_T, smem, ia);
-        StepFinArgs fa{hg_dev, X, P, lda, st->step_length_optim, st->max_step, ctx->d_step.p, step2, tail};
-        LAUNCH(k_step_fin, 1, LU_TILE_N, 0, fa);
-        CK(cudaGetLastError());
-        return 0;
+    if (P > LM_DEV_MAXN) ARGFAIL("lm_solve: the device solver takes at most 128 parameters (larger systems: host solver)");
+    const int ld = pad32(P);
+    const size_t need = 2 * (size_t)P * ld + P + 2 * (size_t)P + 8;
+    if (need > ctx->d_solve.cap) {
+        CK(ctx->d_solve.ensure(need));
+        CK(cudaMemsetAsync(ctx->d_solve.p, 0, ctx->d_solve.cap * sizeof(double), ctx->stream));
     }
-    LmSolveArgs q;
-    q.hg = hg_dev;
-    q.P = P;
-    q.lda = P | 1;
-    q.lambda = (double)st->lambda_diag;
-    q.alpha = st->step_length_optim;
-    q.max_step = st->max_step;
-    const size_t bytes = 2 * (size_t)P * q.lda * sizeof(double) + (size_t)P * sizeof(int) + 16;
-    q.use_smem = bytes <= (size_t)227 * 1024 - 2048 ? 1 : 0;
-    q.scratch = nullptr;
-    if (!q.use_smem) {
-        CK(ctx->d_solve.ensure(2 * (size_t)P * q.lda + P + 2));
-        q.scratch = ctx->d_solve.p;
-    } else if (!ctx->solveAttr) {
-        CK(cudaFuncSetAttribute(k_inv_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
-        CK(cudaFuncSetAttribute(k_lm_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048));
+    double* LUT = ctx->d_solve.p;
+    double* XT = LUT + (size_t)P * ld;
+    double* rdiag = XT + (size_t)P * ld;
+    int* piv = reinterpret_cast<int*>(rdiag + P);
+    const size_t smem = ((size_t)P * ld + P) * sizeof(double);
+    if (!ctx->solveAttr) {
+        CK(cudaFuncSetAttribute(k_inv128, cudaFuncAttributeMaxDynamicSharedMemorySize, (LM_DEV_MAXN * LM_DEV_MAXN + LM_DEV_MAXN) * (int)sizeof(double)));
         ctx->solveAttr = true;
     }
-    q.step = ctx->d_step.p;
-    q.step2 = step2;
-    q.tail = tail;
-    q.clk = ctx->solveClk;
     ProfScope prof_(ctx, PROF_LM_SOLVE);
-    LAUNCH(k_lm_solve, 1, LM_SOLVE_T, q.use_smem ? bytes : 0, q);
+    Lu128Args la{hg_dev, P, ld, (double)st->lambda_diag, LUT, rdiag, piv};
+    static const bool luDbg = getenv("DMSA_B200_LU_CLK") != nullptr;
+    if (luDbg) {
+        LAUNCH(k_lu128<true>, 1, LU128_T, 0, la);
+        long long c[16];
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyFromSymbol(c, g_lu_clk, sizeof(c)));
+        fprintf(stderr, "k_lu128 step (panel 1, kk 3) cycles: argmax %lld | pivot row staging %lld | bookkeeping+div %lld | panel update %lld ; barrier wait of warp 2 %lld | its trailing update %lld\n",
+                c[1] - c[0], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[6] - c[5], c[7] - c[6]);
+        fprintf(stderr, "   trailing steps of warp 2, panel 1: %lld %lld %lld %lld %lld %lld %lld %lld ; barrier exit -> first step %lld\n", c[9] - c[8], c[10] - c[9], c[11] - c[10],
+                c[12] - c[11], c[13] - c[12], c[14] - c[13], c[15] - c[14], c[7] - c[15], c[8] - c[6]);
+    } else {
+        LAUNCH(k_lu128<false>, 1, LU128_T, 0, la);
+    }
+    Inv128Args ia{LUT, rdiag, piv, P, ld, XT};
+    LAUNCH(k_inv128, (P + INV128_WARPS - 1) / INV128_WARPS, INV128_WARPS * 32, smem, ia);
+    StepFinArgs fa{hg_dev, XT, P, ld, st->step_length_optim, st->max_step, ctx->d_step.p, step2, tail};
+    LAUNCH(k_step_fin, 1, LM_DEV_MAXN, 0, fa);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1030,6 +1037,28 @@ void staleGlobal(dmsa_b200_ctx* ctx, const double* p_last_eval, const double* p_
     ctx->poses.setParams(p_current);
 }
 
+// sum over the ranks of a row-sharded set, in place, on the context's stream; no-op without a communicator
+int allReduceSum(dmsa_b200_ctx* ctx, double* buf, size_t count) {
+    if (!ctx->comm) {
+        if (ctx->world > 1) ARGFAIL("the context is sharded (set_shard) but has no communicator: iteration / optimize need dmsa_b200_comm_init; "
+                                    "without one, combine the partial results of cost_jacobian_dev / line_search_costs_dev yourself");
+        return 0;
+    }
+    ncclResult_t r = nccl_api().AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) {
+        ctx->err = "ncclAllReduce: " + nccl_api().describe(r);
+        return DMSA_B200_ERR_CUDA;
+    }
+    ctx->collectives++;
+    return 0;
+}
+
+// One loop body of optimizeSet (DmsaOptimizer.h:69-144).  With the device LM solver (P <= 128) the whole body runs on the
+// device behind ONE read-back: [set counts / octree depths | 9 trial costs | step | e0^T e0 | NaN flag]; the host only picks
+// the line-search winner and keeps the pose bookkeeping of the reference (see staleGlobal).  Grid sizes that depend on the
+// number of sets come from the previous build of this context and are verified with the read-back (the rare miss redoes the
+// body with a synchronous build).  With the host solver (default, and always for P > 128) the body stops twice more: for
+// [H | g] before the solve and for the 9 trial costs.
 int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* stop, dmsa_b200_report* rep, double* step_out, double* ls_out) {
     const int P = 6 * (ctx->poses.n - 1);
     if (P <= 0) ARGFAIL("need at least two poses");
@@ -1045,59 +1074,101 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
             }
         }
     } wall_{ctx, PROF_HOST_ITER};
-    // getPoseParameters + updateGlobalPoints at the base pose (the forward-difference batch's vector 0)   :72-75
-    ctx->poses.relative2global();
-    CKRC(uploadParams(ctx));
-    std::vector<double> paramVec = ctx->h_p;
-    CKRC(prepareFdBatch(ctx));
-    CKRC(transformBase(ctx));
-    CKRC(buildSets(ctx, st));  // :78-86, :96
-    if (rep) {
-        rep->num_gaussians = ctx->G;
-        rep->num_extra = numExtra(ctx);
-    }
-    if (ctx->G < st->min_num_gaussians) {  // :89-93
-        *stop = DMSA_B200_STOP_FEW_GAUSSIANS;
-        return 0;
-    }
-    CKRC(runCost(ctx));  // e0 and the P perturbed evaluations in one batch   :99-104
+    const bool devSolve = ctx->solverMode == 0 && P <= LM_DEV_MAXN;  // larger systems: host solver
+    CKRC(ensurePinned(ctx, P));
     CK(ctx->d_hg.ensure((size_t)P * P + P + 1));
     CK(ctx->d_ls.ensure(16));
-    CKRC(jtjInto(ctx, ctx->d_hg.p));  // :107
-    std::vector<double> step;
-    int nanStep;
-    double error0;
+    CK(ctx->d_iter.ensure(16 + (size_t)P + 2));
+    std::vector<double> paramVec, step;
+    int nanStep = 0;
+    double error0 = 0;
     double ls[9];
-    const bool devSolve = ctx->solverMode == 0 && P <= LU_TILE_N;  // larger systems: the host solver is faster than one block
-    if (devSolve) {
-        // device-resident LM step: solve, line search and ONE read-back of [9 costs | step | err0 | NaN flag]
-        CK(ctx->d_iter.ensure(16 + (size_t)P + 2));
-        CKRC(lmSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
-        CKRC(lineSearchDev(ctx, ctx->d_iter.p));
-        CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_iter.p, (16 + (size_t)P + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        const double* r = pinHg(ctx);
-        std::copy(r, r + 9, ls);
-        step.assign(r + 16, r + 16 + P);
-        error0 = r[16 + P];
-        nanStep = r[16 + P + 1] != 0.0;
-        ctx->lastErr0 = error0;
-    } else {
-    ctx->h_hg.resize((size_t)P * P + P + 1);
-    CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    dmsa_host_solver_arm();  // the solve follows this read-back immediately: helper threads spin up while the host waits
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-        dmsa_host_solver_disarm();
-        ctx->err = "cudaStreamSynchronize failed before the LM solve";
-        return DMSA_B200_ERR_CUDA;
-    }
-    error0 = pinHg(ctx)[(size_t)P * P + P];
-    ctx->lastErr0 = error0;
-    {
-        WallTimer ws{ctx, PROF_HOST_SOLVE};
-        nanStep = solveStep(st, pinHg(ctx), P, step);
-    }
-    dmsa_host_solver_disarm();
+    bool tryDefer = devSolve;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // getPoseParameters + updateGlobalPoints at the base pose (the forward-difference batch's vector 0)   :72-75
+        ctx->poses.relative2global();
+        CKRC(uploadParams(ctx));
+        paramVec = ctx->h_p;
+        CKRC(prepareFdBatch(ctx));
+        CKRC(transformBase(ctx));
+        CKRC(buildSets(ctx, st, tryDefer));  // :78-86, :96
+        const bool deferred = ctx->G < 0;
+        if (!deferred) {
+            if (rep) {
+                rep->num_gaussians = ctx->G;
+                rep->num_extra = numExtra(ctx);
+            }
+            if (ctx->G < st->min_num_gaussians) {  // :89-93
+                *stop = DMSA_B200_STOP_FEW_GAUSSIANS;
+                return 0;
+            }
+        }
+        CKRC(runCost(ctx));  // e0 and the P perturbed evaluations in one batch   :99-104
+        CKRC(jtjInto(ctx, ctx->d_hg.p));  // :107
+        CKRC(allReduceSum(ctx, ctx->d_hg.p, (size_t)P * P + P + 1));
+        if (devSolve) {
+            // device-resident LM step: solve, line search and ONE read-back
+            CKRC(lmSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
+            CKRC(lineSearchDev(ctx, ctx->d_iter.p));
+            CKRC(allReduceSum(ctx, ctx->d_iter.p, 9));
+            CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_iter.p, (16 + (size_t)P + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (deferred) CK(cudaMemcpyAsync(pinLinfo(ctx, P), ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (deferred) {
+                // late verification of the two guesses the deferred build ran on: octree depth (sort key bits) and set count (grids)
+                memcpy(ctx->h_linfo, pinLinfo(ctx, P), 2 * sizeof(LevelInfo));
+                int G = 0;
+                bool miss = false;
+                for (int l = 0; l < 2; ++l) {
+                    if (!ctx->levelOn[l]) continue;
+                    if (ctx->h_linfo[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
+                    if (ctx->h_linfo[l].depth > ctx->cachedDepth[l]) miss = true;
+                    ctx->cachedDepth[l] = ctx->h_linfo[l].depth;
+                    G += ctx->h_linfo[l].G;
+                }
+                if (G > ctx->cellCap) ARGFAIL("build_sets: Gaussian store capacity exceeded");
+                if (G > ctx->Gb) miss = true;
+                ctx->Gguess = std::max(G, 1);
+                if (miss) {  // redo the body with a synchronous build (the state on the host has not been touched yet)
+                    if (ctx->profiling) profCollect(ctx);
+                    tryDefer = false;
+                    continue;
+                }
+                ctx->G = G;
+                if (rep) {
+                    rep->num_gaussians = G;
+                    rep->num_extra = numExtra(ctx);
+                }
+                if (G < st->min_num_gaussians) {  // :89-93 (the evaluations behind it ran on the device but change no state)
+                    if (ctx->profiling) profCollect(ctx);
+                    *stop = DMSA_B200_STOP_FEW_GAUSSIANS;
+                    return 0;
+                }
+            }
+            const double* r = pinHg(ctx);
+            std::copy(r, r + 9, ls);
+            step.assign(r + 16, r + 16 + P);
+            error0 = r[16 + P];
+            nanStep = r[16 + P + 1] != 0.0;
+            ctx->lastErr0 = error0;
+        } else {
+            ctx->h_hg.resize((size_t)P * P + P + 1);
+            CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_hg.p, ctx->h_hg.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            dmsa_host_solver_arm();  // the solve follows this read-back immediately: helper threads spin up while the host waits
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+                dmsa_host_solver_disarm();
+                ctx->err = "cudaStreamSynchronize failed before the LM solve";
+                return DMSA_B200_ERR_CUDA;
+            }
+            error0 = pinHg(ctx)[(size_t)P * P + P];
+            ctx->lastErr0 = error0;
+            {
+                WallTimer ws{ctx, PROF_HOST_SOLVE};
+                nanStep = solveStep(st, pinHg(ctx), P, step);
+            }
+            dmsa_host_solver_disarm();
+        }
+        break;
     }
     if (nanStep) {  // :113-122
         // the last cost evaluation of calcNumericJacobian was p + h e_{P-1}: its global poses stay behind (see staleGlobal)
@@ -1112,11 +1183,12 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
         return 0;
     }
     if (!devSolve) {
-    // adaptiveStepSize :152-182 — the 9 trial costs in one batch
-    CKRC(lineSearchInto(ctx, step.data(), ctx->d_ls.p));
-    CK(cudaMemcpyAsync(pinLs(ctx, P), ctx->d_ls.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    std::copy(pinLs(ctx, P), pinLs(ctx, P) + 9, ls);
+        // adaptiveStepSize :152-182 — the 9 trial costs in one batch
+        CKRC(lineSearchInto(ctx, step.data(), ctx->d_ls.p));
+        CKRC(allReduceSum(ctx, ctx->d_ls.p, 9));
+        CK(cudaMemcpyAsync(pinLs(ctx, P), ctx->d_ls.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        std::copy(pinLs(ctx, P), pinLs(ctx, P) + 9, ls);
     }
     if (ctx->profiling) profCollect(ctx);
     double minError = error0;
@@ -1191,6 +1263,10 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) {
+        nccl_api().CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
     if (ctx->stream2) {
         cudaStreamSynchronize(ctx->stream2);
         cudaStreamDestroy(ctx->stream2);
@@ -1866,11 +1942,11 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
     return 0;
 }
 
-// Which solver dmsa_b200_iteration / dmsa_b200_optimize use for the LM step: 1 (default) the host solver, 0 the device
-// kernels (no host round trip between the Jacobian pass and the line search; P <= 128, larger systems use the host
-// solver in either mode).  Same operation sequence, bit-identical steps.
+// Which solver dmsa_b200_iteration / dmsa_b200_optimize use for the LM step: 0 (default) the device kernels (P <= 128: the
+// loop body then runs behind one read-back; larger systems use the host solver in either mode), 1 the host solver.
+// Same operation sequence, bit-identical steps.
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode) {
-    if (mode != 0 && mode != 1) ARGFAIL("set_lm_solver: 1 (host, default) or 0 (device)");
+    if (mode != 0 && mode != 1) ARGFAIL("set_lm_solver: 0 (device, default) or 1 (host)");
     ctx->solverMode = mode;
     return 0;
 }
@@ -1882,11 +1958,12 @@ int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode) {
     return 0;
 }
 
-// The device LM step on a HOST copy of [H | g | err0] (any n_params <= 1024): upload, k_lm_solve, download.  Exists so
-// that the device solver can be checked against dmsa_b200_lm_solve (host) on arbitrary systems.
+// The device LM step on a HOST copy of [H | g | err0] (n_params <= 128): upload, the three solver kernels, download.
+// Exists so that the device solver can be checked against dmsa_b200_lm_solve (host) on arbitrary systems.
 int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step,
                               int32_t* has_nan) {
     if (!settings || !hg || !step || n_params <= 0) ARGFAIL("lm_solve_device: bad arguments");
+    if (n_params > LM_DEV_MAXN) ARGFAIL("lm_solve_device: the device solver takes at most 128 parameters (larger systems: host solver)");
     CK(cudaSetDevice(ctx->device));
     const int P = n_params;
     const size_t nhg = (size_t)P * P + P + 1;
@@ -1894,17 +1971,7 @@ int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* sett
     CK(ctx->d_step.ensure(P));
     CK(ctx->d_iter.ensure(16 + (size_t)P + 2));
     CK(cudaMemcpyAsync(ctx->d_hg.p, hg, nhg * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ctx->solveGeneral = getenv("DMSA_B200_SOLVE_GENERAL") != nullptr;
-    const bool dbg = getenv("DMSA_B200_SOLVE_CLK") != nullptr;
-    if (dbg && !ctx->solveClk) CK(cudaMalloc((void**)&ctx->solveClk, 8 * sizeof(long long)));
     CKRC(lmSolveDev(ctx, settings, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
-    if (dbg) {
-        long long c[8];
-        CK(cudaMemcpyAsync(c, ctx->solveClk, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        fprintf(stderr, "k_lm_solve P=%d cycles: load %lld | LU %lld | forward %lld | backward %lld | matvec %lld\n", P, 0LL, c[1] - c[0], c[2] - c[1], c[3] - c[2],
-                c[4] - c[3]);
-    }
     std::vector<double> r((size_t)P + 2);
     CK(cudaMemcpyAsync(r.data(), ctx->d_iter.p + 16, r.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -2002,6 +2069,46 @@ int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world) {
     ctx->world = world;
     return 0;
 }
+// ---- NCCL communicator of a row-sharded context (one process per GPU; NCCL is bound at run time, nccl_dyn.h) ----
+int dmsa_b200_comm_unique_id(void* id128) {
+    if (!id128) return DMSA_B200_ERR_ARG;
+    if (!nccl_api().load()) return DMSA_B200_ERR_UNSUPPORTED;
+    ncclUniqueId id;
+    if (nccl_api().GetUniqueId(&id) != ncclSuccess) return DMSA_B200_ERR_CUDA;
+    memcpy(id128, id.internal, sizeof(id.internal));
+    return 0;
+}
+int dmsa_b200_comm_init(dmsa_b200_ctx* ctx, const void* id128, int32_t rank, int32_t world) {
+    if (!id128 || world < 1 || rank < 0 || rank >= world) ARGFAIL("comm_init: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (!nccl_api().load()) {
+        ctx->err = "comm_init: " + nccl_api().err;
+        return DMSA_B200_ERR_UNSUPPORTED;
+    }
+    if (ctx->comm) {
+        nccl_api().CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ncclUniqueId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    ncclResult_t r = nccl_api().CommInitRank(&ctx->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        ctx->comm = nullptr;
+        ctx->err = "ncclCommInitRank: " + nccl_api().describe(r);
+        return DMSA_B200_ERR_CUDA;
+    }
+    return dmsa_b200_set_shard(ctx, rank, world);
+}
+int dmsa_b200_comm_destroy(dmsa_b200_ctx* ctx) {
+    if (ctx->comm) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        nccl_api().CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    return dmsa_b200_set_shard(ctx, 0, 1);
+}
+int64_t dmsa_b200_collective_count(const dmsa_b200_ctx* ctx) { return ctx ? ctx->collectives : 0; }
+
 int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->G <= 0) ARGFAIL("cost_jacobian_dev: build_sets first");

@@ -49,7 +49,12 @@ DMSA_CLONES static void lu_factor_impl(std::vector<double>& a, std::vector<int>&
         }
     }
 }
-// forward + back substitution of the right-hand-side columns [c0, c1) (independent of every other column)
+// forward + back substitution of the right-hand-side columns [c0, c1) (independent of every other column).
+// Forward: x_i -= l_ij x_j with ascending j.  Backward, column-oriented: x_j *= 1 / u_jj once every row below has been
+// applied, then x_i -= u_ij x_j for the rows above, descending j (Eigen's triangular matrix solver, the path inverse() takes,
+// also scales by the reciprocal diagonal; neither order can be pinned against Eigen here).  This is the order in which
+// a column's dependency chain is 2 n steps long, so the device solver (kernels_solve.cuh) runs the same sequence with one
+// warp per column.
 DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n, int ldx, int c0, int c1) {
     for (int i = 0; i < n; ++i) {  // forward substitution, unit lower triangle
         double* __restrict__ xi = &inv[(size_t)i * ldx];
@@ -60,16 +65,15 @@ DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n,
             for (int c = c0; c < c1; ++c) xi[c] -= l * xj[c];
         }
     }
-    for (int i = n - 1; i >= 0; --i) {  // back substitution
-        double* __restrict__ xi = &inv[(size_t)i * ldx];
-        const double* ai = &a[(size_t)i * n];
-        for (int j = i + 1; j < n; ++j) {
-            const double u = ai[j];
-            const double* __restrict__ xj = &inv[(size_t)j * ldx];
+    for (int j = n - 1; j >= 0; --j) {  // back substitution
+        double* __restrict__ xj = &inv[(size_t)j * ldx];
+        const double rdiag = 1.0 / a[(size_t)j * n + j];
+        for (int c = c0; c < c1; ++c) xj[c] = xj[c] * rdiag;
+        for (int i = 0; i < j; ++i) {
+            const double u = a[(size_t)i * n + j];
+            double* __restrict__ xi = &inv[(size_t)i * ldx];
             for (int c = c0; c < c1; ++c) xi[c] -= u * xj[c];
         }
-        const double dinv = ai[i];
-        for (int c = c0; c < c1; ++c) xi[c] = xi[c] / dinv;
     }
 }
 

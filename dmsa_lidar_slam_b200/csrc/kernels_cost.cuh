@@ -44,6 +44,7 @@ struct CostArgs {
     int* done1;              // [g] same for pass 1 (sets with more than MEAN_INLINE_MAX chunks only)
     double* Q;               // partial quadratic forms [c * Vld + v]
     double* E;               // residuals      [g * Vld + v]
+    const LevelInfo* li;     // the set count lives on the device (total_sets): grids are sized from a host-side bound
 };
 
 __device__ __forceinline__ void xform(const float4& m0, const float4& m1, const float4& m2, const float4& r, float& X, float& Y, float& Z) {
@@ -217,11 +218,11 @@ __device__ __forceinline__ double pass_quad(const CostArgs& a, const float4* __r
 // on them.  Blocks are issued longest-set-first (a.order) so that the kernel does not end on a long block.
 // Also zero-fills the rows of sets owned by other ranks.
 template <bool PACKED, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ double ex[PACKED_WARPS][16];
-    if ((int)blockIdx.x >= G) return;
+    if ((int)blockIdx.x >= total_sets(a.li)) return;
     const int g = a.order[blockIdx.x];
     const int kind = a.cell_kind[g];
     if (kind == 2) return;
@@ -250,10 +251,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a, int G) {
 // in tiles).  Slow on the big sets of un-downsampled clouds (a dependent float-add chain as long as the set) and
 // therefore not the default; it exists to show that the only arithmetic difference between the fast path and the
 // reference's operation order is that one reduction (DESIGN.md §3 "mean").
-__global__ void __launch_bounds__(1024) k_cost_seq(CostArgs a, int G) {
+__global__ void __launch_bounds__(1024) k_cost_seq(CostArgs a) {
     __shared__ __align__(16) float4 srec[COST_CHUNK];
     const int g = blockIdx.x;
-    if (g >= G) return;
+    if (g >= total_sets(a.li)) return;
     const int kind = a.cell_kind[g];
     const int v = min((int)threadIdx.x, a.V - 1);
     const bool active = (int)threadIdx.x < a.V;
@@ -628,10 +629,10 @@ __device__ __forceinline__ PairMap pair_map(const CostArgs& a) {
 }
 
 template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k_cost_fused2(CostArgs a, int G) {
+__global__ void __launch_bounds__(MAXT, MINB) k_cost_fused2(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
-    if ((int)blockIdx.x >= G) return;
+    if ((int)blockIdx.x >= total_sets(a.li)) return;
     const int g = a.order[blockIdx.x];
     const int kind = a.cell_kind[g];
     if (kind == 2) return;
@@ -742,8 +743,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad2(CostArgs a) {
 
 // per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): COLSUM_PARTS row slices per vector, fixed reduction order
 #define COLSUM_PARTS 16
-__global__ void k_col_sumsq(const double* __restrict__ E, int R, int Vld, double* __restrict__ part /*[9][COLSUM_PARTS]*/) {
+__global__ void k_col_sumsq(const double* __restrict__ E, const LevelInfo* __restrict__ li, int n_extra, int Vld, double* __restrict__ part /*[9][COLSUM_PARTS]*/) {
     __shared__ double red[256];
+    const int R = total_sets(li) + n_extra;
     const int v = blockIdx.x, y = blockIdx.y;
     const int per = (R + COLSUM_PARTS - 1) / COLSUM_PARTS;
     const int r0 = y * per, r1 = min(R, r0 + per);
@@ -768,13 +770,40 @@ __global__ void k_col_sumsq_fin(const double* __restrict__ part, double* __restr
     out[v] = s;
 }
 
+// additional residual rows (IMU / gravity / odometry) behind the set rows: E[G + r][v] = extra[r][v]   (DmsaOptimizer.h:271-272)
+__global__ void k_append_extra(double* __restrict__ E, const LevelInfo* __restrict__ li, const double* __restrict__ extra, int n_extra, int Vld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_extra * Vld) return;
+    E[(size_t)total_sets(li) * Vld + i] = extra[i];
+}
+
+// Row partition of the J^T J kernels, computed on the device from the actual row count (the summation order, and with it
+// every bit of H, depends on the partition: it must not depend on the host's grid-size guess).
+#define JD_ROWS 32
+#define JD_MAXBLK 148
+__device__ __forceinline__ void jd_partition(int R, int& nblk, int& rpb) {
+    nblk = max(1, min(JD_MAXBLK, (R + JD_ROWS - 1) / JD_ROWS));
+    rpb = max(JD_ROWS, ((R + nblk - 1) / nblk + JD_ROWS - 1) / JD_ROWS * JD_ROWS);
+    nblk = max(1, (R + rpb - 1) / rpb);
+}
+#define JTJ_T 32
+#define JTJ_MAXSPLIT 64
+__device__ __forceinline__ void jtj_partition(int R, int& nsplit, int& rps) {
+    nsplit = max(1, min(JTJ_MAXSPLIT, (R + 127) / 128));
+    rps = max(JTJ_T, ((R + nsplit - 1) / nsplit + JTJ_T - 1) / JTJ_T * JTJ_T);
+    nsplit = max(1, (R + rps - 1) / rps);
+}
+
 // ---- [J e0]^T [J e0] : H = J^T J, g = J^T e0, err0 = e0^T e0 in one symmetric product ---------------------------
 // Column c < P of the augmented matrix is the forward-difference column (E[:,c+1] - E[:,0]) / h (DmsaOptimizer.h:227),
 // column P is e0.  Upper-triangular 32x32 tiles, split over row ranges; partials are reduced in fixed order.
-#define JTJ_T 32
-__global__ void __launch_bounds__(256) k_jtj(const double* __restrict__ E, int R, int Vld, int P, double inv_h, int rows_per_split,
+__global__ void __launch_bounds__(256) k_jtj(const double* __restrict__ E, const LevelInfo* __restrict__ li, int n_extra, int Vld, int P, double inv_h,
                                              double* __restrict__ part /*[split][(P+1)*(P+1)]*/) {
     __shared__ double A[JTJ_T][JTJ_T + 1], B[JTJ_T][JTJ_T + 1];
+    const int R = total_sets(li) + n_extra;
+    int nsplit, rows_per_split;
+    jtj_partition(R, nsplit, rows_per_split);
+    if ((int)blockIdx.y >= nsplit) return;
     const int nt = (P + 1 + JTJ_T - 1) / JTJ_T;
     // decode upper-triangular tile index
     int t = blockIdx.x, ta = 0;
@@ -829,8 +858,10 @@ __global__ void __launch_bounds__(256) k_jtj(const double* __restrict__ E, int R
     if (i0 + 1 < n1 && j0 + 1 < n1) out[(size_t)(i0 + 1) * n1 + j0 + 1] = acc11;
 }
 // out = [H (P*P row-major) | g (P) | err0]
-__global__ void k_jtj_reduce(const double* __restrict__ part, int nsplit, int P, double* __restrict__ out) {
+__global__ void k_jtj_reduce(const double* __restrict__ part, const LevelInfo* __restrict__ li, int n_extra, int P, double* __restrict__ out) {
     const int n1 = P + 1;
+    int nsplit, rps_;
+    jtj_partition(total_sets(li) + n_extra, nsplit, rps_);
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n1 * n1) return;
     int i = q / n1, j = q % n1;
@@ -855,14 +886,17 @@ __global__ void k_jtj_reduce(const double* __restrict__ part, int nsplit, int P,
 // t = lane % 4): both are the same shared-memory access pattern.  A block owns a row range, stages 32-row panels of A in
 // shared memory (row stride 132 doubles: conflict-free 8-byte fragment loads) and keeps ALL upper-triangular 8 x 8 output
 // tiles in registers (<= 8 tiles per warp, 16 warps); per-block partials are reduced in fixed order by k_jtj_reduce8.
-#define JD_ROWS 32
 #define JD_LD 132
 #define JD_T 512
 #define JD_MAXN 128
-__global__ void __launch_bounds__(JD_T, 1) k_jtj_dmma(const double* __restrict__ E, int R, int Vld, int P, double inv_h, int rows_per_block,
+__global__ void __launch_bounds__(JD_T, 1) k_jtj_dmma(const double* __restrict__ E, const LevelInfo* __restrict__ li, int n_extra, int Vld, int P, double inv_h,
                                                        double* __restrict__ part /*[block][n1*n1]*/) {
     __shared__ __align__(16) double As[JD_ROWS * JD_LD];
     __shared__ unsigned char tij[JD_MAXN / 8 * (JD_MAXN / 8 + 1) / 2][2];
+    const int R = total_sets(li) + n_extra;
+    int nblk_, rows_per_block;
+    jd_partition(R, nblk_, rows_per_block);
+    if ((int)blockIdx.x >= nblk_) return;
     const int n1 = P + 1, nt = (n1 + 7) >> 3, ntile = nt * (nt + 1) / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     for (int q = threadIdx.x; q < ntile; q += JD_T) {  // upper-triangular tile list, row by row
@@ -920,9 +954,12 @@ __global__ void __launch_bounds__(JD_T, 1) k_jtj_dmma(const double* __restrict__
 // out = [H (P*P row-major) | g (P) | err0] from the per-block partials of k_jtj_dmma (8 x 8 tiles, lower tiles mirrored).
 // blockDim = (32, 8): 32 consecutive output elements x 8 interleaved partial streams (partial k goes to stream k % 8,
 // ascending k), the streams are combined in ascending order: fixed summation order, coalesced 256-byte reads.
-__global__ void __launch_bounds__(256) k_jtj_reduce8(const double* __restrict__ part, int nsplit, int P, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_jtj_reduce8(const double* __restrict__ part, const LevelInfo* __restrict__ li, int n_extra, int P,
+                                                     double* __restrict__ out) {
     __shared__ double red[8][33];
     const int n1 = P + 1;
+    int nsplit, rpb_;
+    jd_partition(total_sets(li) + n_extra, nsplit, rpb_);
     const int q = blockIdx.x * 32 + threadIdx.x;
     const bool ok = q < n1 * n1;
     const int i = ok ? q / n1 : 0, j = ok ? q % n1 : 0;

@@ -38,7 +38,14 @@ struct LevelInfo {
     int G;            // accepted sets of this level
     int gbase;        // first set index of this level in the store
     int error;        // 1: depth > 21
+    int bound;        // most sets the consumers of this build may touch (grids / row buffers were sized for it)
 };
+
+// number of accepted sets of both levels (a level that is switched off keeps the zeroed record of the per-build memset):
+// the kernels behind the set build read it from the device so that the host does not have to wait for it
+// (clamped to the bound the host sized its buffers for: a deferred build whose guess was too small must stay in bounds;
+// the host sees the unclamped counts in the read-back and redoes the iteration)
+__device__ __forceinline__ int total_sets(const LevelInfo* __restrict__ li) { return min(li[0].G + li[1].G, max(li[0].bound, li[1].bound)); }
 
 // ---- anchor (one thread) ---------------------------------------------------------------------
 struct LevelPlan {  // the resolution levels built in this pass (DmsaOptimizer.h:81-86: a factor <= FLT_MIN disables a level)
@@ -46,9 +53,10 @@ struct LevelPlan {  // the resolution levels built in this pass (DmsaOptimizer.h
     int level[2];
     float res[2];
 };
-__global__ void k_anchor(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* infos) {
+__global__ void k_anchor(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* infos, int bound) {
     if (blockIdx.x != 0 || (int)threadIdx.x >= plan.n) return;
     LevelInfo* info = infos + plan.level[threadIdx.x];
+    info->bound = bound;
     const double res = (double)plan.res[threadIdx.x];  // OctreePointCloud(const double resolution)
     const double minValue = 1.1920928955078125e-07;  // std::numeric_limits<float>::epsilon()
     int i = 0;
@@ -711,10 +719,10 @@ __device__ inline void gaussian_finish(CellStore cs, int g, int n, const double 
 // One warp per accepted set with n <= GAUSS_WARP_MAX members (larger sets: k_gaussian_big over the compact list of
 // k_gauss_list): centred second moments -> mom[g][6]; k_gaussian_fin turns them into information matrices.  The member loops are unrolled so that the loads of four strides are in flight together; every
 // thread still adds its terms in ascending member order.
-__global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G, double* __restrict__ mom) {
+__global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, const LevelInfo* __restrict__ li, double* __restrict__ mom) {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (g >= G) return;
+    if (g >= total_sets(li)) return;
     const int s = cs.start[g], n = cs.n[g];
     if (n > GAUSS_WARP_MAX) return;
     // colwise().mean(): exactly-rounded sum, float division
@@ -750,9 +758,9 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, int G,
         for (int k = 0; k < 6; ++k) mom[6 * (size_t)g + k] = a[k];
 }
 // compact list of the sets with n > GAUSS_WARP_MAX (order irrelevant: every set's result depends on the set alone)
-__global__ void k_gauss_list(CellStore cs, int G, int* __restrict__ list, int* __restrict__ count) {
+__global__ void k_gauss_list(CellStore cs, const LevelInfo* __restrict__ li, int* __restrict__ list, int* __restrict__ count) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    if (g >= total_sets(li)) return;
     if (cs.n[g] > GAUSS_WARP_MAX) list[atomicAdd(count, 1)] = g;
 }
 #define GAUSS_BIG_T 1024
@@ -822,9 +830,9 @@ __global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __re
 }
 // Eigen clamp + information matrix + observation weight of every set from its centred second moments: one THREAD per
 // set (the 3x3 Jacobi sweeps are long dependent FP64 chains; with one lane per warp they cost 32x the issue slots).
-__global__ void k_gaussian_fin(CellStore cs, int G, const double* __restrict__ mom) {
+__global__ void k_gaussian_fin(CellStore cs, const LevelInfo* __restrict__ li, const double* __restrict__ mom) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    if (g >= total_sets(li)) return;
     double a[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) a[k] = mom[6 * (size_t)g + k];
@@ -833,8 +841,9 @@ __global__ void k_gaussian_fin(CellStore cs, int G, const double* __restrict__ m
 
 // Gaussians.h:172-177: w0 = (1 / n) * observation weight (1, OptimizablePointSet.h:52), w = w0 / mean(w0)   (one block;
 // deterministic double reduction, one rounding).  Depends on the set sizes only, so it runs beside the set statistics.
-__global__ void k_weights(CellStore cs, int G) {
+__global__ void k_weights(CellStore cs, const LevelInfo* __restrict__ li) {
     __shared__ double part[1024];
+    const int G = total_sets(li);
     double s = 0;
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         const float w0 = fmul_(fdiv_(1.0f, (float)cs.n[g]), 1.0f);
@@ -858,10 +867,10 @@ __global__ void k_weights(CellStore cs, int G) {
 struct Chunk {
     int cell, start, count, first;  // first: index of the set's first chunk
 };
-__global__ void k_cell_plan(CellStore cs, int G, int CH, int fuse_max, int rank, int world, int* __restrict__ kind, int* __restrict__ nchunk,
-                            int* __restrict__ okey, int* __restrict__ oval) {
+__global__ void k_cell_plan(CellStore cs, const LevelInfo* __restrict__ li, int CH, int fuse_max, int rank, int world, int* __restrict__ kind,
+                            int* __restrict__ nchunk, int* __restrict__ okey, int* __restrict__ oval) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    if (g >= total_sets(li)) return;
     const int n = cs.n[g];
     const int k = (g % world == rank) ? (n <= fuse_max ? 1 : 2) : 0;
     kind[g] = k;
@@ -873,7 +882,7 @@ __global__ void k_cell_plan(CellStore cs, int G, int CH, int fuse_max, int rank,
 }
 // order[] = set indices grouped by size class, longest class first.  The position inside a class comes from an atomic
 // cursor: the order is a scheduling hint only and does not influence any result.
-__global__ void k_cell_order(int G, const int* __restrict__ okey, int* __restrict__ hist_cursor, int* __restrict__ order) {
+__global__ void k_cell_order(const LevelInfo* __restrict__ li, const int* __restrict__ okey, int* __restrict__ hist_cursor, int* __restrict__ order) {
     __shared__ int base[ORDER_CLASSES];
     if (threadIdx.x == 0) {
         int acc = 0;
@@ -884,15 +893,16 @@ __global__ void k_cell_order(int G, const int* __restrict__ okey, int* __restric
     }
     __syncthreads();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    if (g >= total_sets(li)) return;
     const int c = okey[g];
     const int pos = atomicAdd(&hist_cursor[ORDER_CLASSES + c], 1);
     order[base[c] + pos] = g;
 }
 // chunk_off = exclusive scan of nchunk (G+1 entries, last = total)
-__global__ void k_chunk_fill(CellStore cs, int G, int CH, const int* __restrict__ nchunk, const int* __restrict__ chunk_off, Chunk* __restrict__ chunks) {
+__global__ void k_chunk_fill(CellStore cs, const LevelInfo* __restrict__ li, int CH, const int* __restrict__ nchunk, const int* __restrict__ chunk_off,
+                             Chunk* __restrict__ chunks) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
+    if (g >= total_sets(li)) return;
     const int nc = nchunk[g], o = chunk_off[g], s = cs.start[g], n = cs.n[g];
     for (int c = 0; c < nc; ++c) {
         Chunk ch;

@@ -201,6 +201,16 @@ int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev);
 /* 9 partial line-search costs for step (host P doubles) into ls_dev[9] (device) */
 int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, double* ls_dev);
 
+/* In-library exchange for dmsa_b200_iteration / dmsa_b200_optimize on a sharded context: one process per GPU, every rank
+ * stages the SAME set and calls the same sequence; an iteration then all-reduces [H | g | err0] (P*P + P + 1 doubles) and the
+ * 9 line-search costs with NCCL on the context's stream (intra-node NVLink / NVSwitch), and every rank takes the same step.
+ * NCCL is bound at run time (dlopen of libnccl.so.2: inside a PyTorch process that is torch's own copy).
+ * Rank 0 creates the 128-byte id and hands it to the other ranks by any means (e.g. torch.distributed.broadcast over gloo). */
+int dmsa_b200_comm_unique_id(void* id128);
+int dmsa_b200_comm_init(dmsa_b200_ctx* ctx, const void* id128, int32_t rank, int32_t world); /* implies set_shard(rank, world) */
+int dmsa_b200_comm_destroy(dmsa_b200_ctx* ctx);                                              /* back to set_shard(0, 1) */
+int64_t dmsa_b200_collective_count(const dmsa_b200_ctx* ctx); /* NCCL all-reduces issued by this context */
+
 /* Host-side LM step (DmsaOptimizer.h:107-128) on a host copy of the (all-reduced) [H | g | err0] buffer; no context needed.
  * explicit_inverse = 1: the reference's arithmetic, (-alpha * H.inverse()) * g with an LU inverse (what dmsa_b200_iteration uses);
  * explicit_inverse = 2: the same arithmetic with the inverse's columns spread over a few helper threads (bit-identical; what
@@ -210,9 +220,9 @@ int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, doub
 int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, int32_t explicit_inverse, double* step,
                        int32_t* has_nan);
 
-/* Solver of the LM step inside dmsa_b200_iteration / dmsa_b200_optimize (DmsaOptimizer.h:107-128): 1 (default) = host
- * solver, 0 = device kernels for P <= 128 (the iteration then has no host round trip between the Jacobian pass and the
- * line search; larger systems use the host solver in either mode).
+/* Solver of the LM step inside dmsa_b200_iteration / dmsa_b200_optimize (DmsaOptimizer.h:107-128): 0 (default) = device
+ * kernels for P <= 128 (the whole loop body then runs behind ONE read-back; larger systems use the host solver in either
+ * mode), 1 = host solver.
  * Both run the same operation sequence (LU with partial pivoting, explicit inverse, ascending accumulation): bit-identical. */
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode);
 /* Cost kernels of the forward-difference batch (V = P + 1 vectors): 1 (default) = two vectors per thread with Blackwell's

@@ -494,30 +494,37 @@ def test_call_order_is_checked():
         ContinuousTrajectory().initTraj(0.0, 1.0, 2)  # barycentric_rational of order 2 needs >= 3 poses
 
 
-@pytest.mark.parametrize("n", [12, 18, 31, 33, 64, 114, 116, 117, 128, 129, 234])
+@pytest.mark.parametrize("n", [3, 12, 18, 31, 32, 33, 64, 84, 96, 97, 114, 116, 117, 128])
 def test_device_lm_solve_is_bit_identical_to_the_host_solver(n):
-    """k_lm_solve (kernels_solve.cuh) runs the operation sequence of the host solver (DmsaOptimizer.h:107-128 with Eigen's
-    PartialPivLU inverse): the clamped steps are bit-identical, in shared memory (n <= 116) and in global scratch."""
+    """The device LM step (kernels_solve.cuh: k_lu128 / k_inv128 / k_step_fin) runs the operation sequence of the host solver
+    (DmsaOptimizer.h:107-128 with an LU inverse): the clamped steps are bit-identical."""
+    from dmsa_lidar_slam_b200 import DmsaError
     from dmsa_lidar_slam_b200.api import lm_solve
 
     traj = ContinuousTrajectory()
     rng = np.random.default_rng(1000 + n)
-    for trial in range(3):
+    for trial in range(4):
         J = rng.standard_normal((3 * n, n)) * np.logspace(0, -3, n)[None, :]  # ill-conditioned like lambda = 1e-5 systems
         if trial == 2:
             J[:, n // 2] = 0.0  # a zero column: the lambda diagonal alone keeps the pivot alive
+        if trial == 3:
+            J = J[:, rng.permutation(n)] * rng.choice([1e-3, 1.0, 1e3], n)[None, :]  # forces row exchanges
         r = rng.standard_normal(3 * n)
         hg = np.concatenate([(J.T @ J).ravel(), J.T @ r, [float(r @ r)]])
+        if trial == 3:  # an unsymmetric perturbation: partial pivoting leaves the diagonal
+            H = hg[:n * n].reshape(n, n)
+            H += rng.standard_normal((n, n)) * np.abs(H).mean()
         s = DmsaOptimSettings(step_length_optim=0.2, max_step=0.3 if trial else 1e9, lambda_diag=1e-5)
         a, nan_a = lm_solve(s, hg, n, 1)
-        for general in (False, True):  # n <= 128: register-tiled three-kernel path; forced general one-block kernel
-            os.environ.pop("DMSA_B200_SOLVE_GENERAL", None)
-            if general:
-                os.environ["DMSA_B200_SOLVE_GENERAL"] = "1"
-            b, nan_b = traj.lmSolveDevice(s, hg, n)
-            os.environ.pop("DMSA_B200_SOLVE_GENERAL", None)
-            assert nan_a == nan_b == 0
-            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), f"n={n} trial={trial} general={general}: max |diff| {np.abs(a - b).max():.3e}"
+        a2, _ = lm_solve(s, hg, n, 2)  # helper threads: same arithmetic
+        assert np.array_equal(a.view(np.uint64), a2.view(np.uint64))
+        b, nan_b = traj.lmSolveDevice(s, hg, n)
+        assert nan_a == nan_b == 0
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), f"n={n} trial={trial}: max |diff| {np.abs(a - b).max():.3e}"
+        if trial == 0:  # and it is the solution: (H + lambda I) step = -alpha g
+            H = hg[:n * n].reshape(n, n) + 1e-5 * np.eye(n)
+            ref = -0.2 * np.linalg.solve(H, hg[n * n:n * n + n])
+            assert np.linalg.norm(a - ref) <= 1e-6 * np.linalg.norm(ref)
     hg = np.zeros(n * n + n + 1)
     hg[0] = np.nan
     _, nan_h = lm_solve(DmsaOptimSettings(), hg, n, 1)
@@ -528,6 +535,8 @@ def test_device_lm_solve_is_bit_identical_to_the_host_solver(n):
     _, nan_h = lm_solve(s0, hg, n, 1)
     _, nan_d = traj.lmSolveDevice(s0, hg, n)
     assert nan_h == nan_d == 1
+    with pytest.raises(DmsaError, match="at most 128"):  # larger systems are solved on the host
+        traj.lmSolveDevice(DmsaOptimSettings(), np.zeros(129 * 129 + 130), 129)
 
 
 @pytest.mark.parametrize("name", ["tiny", "cfg1", "cfg2"])
