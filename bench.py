@@ -51,6 +51,14 @@ def emit(line):
 SETTINGS = dict(num_iter=1, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10, min_num_gaussians=30)
 METRIC = "DMSA iterations/sec"
 UNIT = "iterations/s"
+PRODUCTION_NUM_ITER = 10  # config/slam_settings.yaml:22 (num_iter of the sliding-window optimizeSet)
+
+
+def workload_string(config, win, P, world):
+    """The same string in both arms (the driver compares `config` of the two lines)."""
+    return (f"{config}: sliding-window DMSA iteration (DmsaOptimizer.h:69-144), {len(win['scans'])} scans x {len(win['scans'][0])} pts + "
+            f"{len(win['static'])} static, {win['n_poses']} control poses, P={P}, {P + 10} cost evaluations/step; "
+            + ("1 window" if world == 1 else f"{world} identical windows, one per rank (replicas, no collective)"))
 
 
 def load_peaks():
@@ -131,12 +139,14 @@ def best_thread_count(win):
     return best
 
 
-def oracle_cpu_baseline(win, threads, iters=2):
-    """The CPU path (oracle port of the reference arithmetic, oracle/dmsa_oracle.cpp) timed on the host cores."""
+def oracle_cpu_baseline(win, threads, iters=2, opt="O2"):
+    """The CPU path (oracle port of the reference arithmetic, oracle/dmsa_oracle.cpp) timed on the host cores.
+    opt="O1", threads=1: the "reference-faithful" build (CMakeLists.txt:15 -O1; the reference's cost loops are serial,
+    DmsaOptimizer.h:56-57 only gives Eigen's J^T J product 4 threads)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
 
-    m = ob.OracleModel.from_window(win)
+    m = ob.OracleModel.from_window(win, opt=opt)
     m.set_threads(threads)
     m.set_mode(0)
     m.centralize()
@@ -150,6 +160,24 @@ def oracle_cpu_baseline(win, threads, iters=2):
         ts.append(t)
     s = m.sets()
     return dict(seconds_per_iteration=float(np.median(ts)), M=int(s["M"]), G=int(s["G"]), status=status, threads=threads)
+
+
+def keyframe_cpu_baseline(sm, n_bundles, settings):
+    """The CPU path (oracle port) on ONE bundle of the same submap, scaled by the number of bundles (bounded sample)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from dmsa_lidar_slam_b200.distributed import bundle_ranges
+
+    f, l = bundle_ranges(sm["n_keyframes"], 15, 8)[0]
+    sub = dict(n_keyframes=l - f + 1, clouds=sm["clouds"][f:l + 1], rings=sm["rings"][f:l + 1], grid_sizes=sm["grid_sizes"][f:l + 1],
+               rel_orient=sm["rel_orient"][:, f:l + 1].copy(), rel_transl=sm["rel_transl"][:, f:l + 1].copy())
+    m = ob.OracleModel.from_submap(sub)
+    threads = os.cpu_count() or 1
+    m.set_threads(threads)
+    m.set_mode(0)
+    t, status = m.time_iteration(ob.settings(**settings))
+    return {"value": 1.0 / (t * n_bundles), "unit": "iterations/s", "cores": threads, "kind": "port",
+            "sample": f"one iteration of one of the {n_bundles} bundles (15 keyframes) by oracle/dmsa_oracle.cpp, faithful arithmetic; time x {n_bundles}"}
 
 
 def run_reference(args):
@@ -173,7 +201,7 @@ def run_reference(args):
         m.set_params(p0)
         m.time_iteration(st)
     t_total = 0.0
-    steps = min(args.steps, 10)  # bounded: each step is one full CPU iteration of the same workload
+    steps = args.steps  # each step is one full CPU iteration of the same workload (~0.3 s at cfg2 on 16 threads)
     for _ in range(steps):
         m.set_params(p0)
         t, _ = m.time_iteration(st)
@@ -181,14 +209,16 @@ def run_reference(args):
     s = m.sets()
     P = m.P
     val = steps / t_total
+    world = max(1, args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: sliding-window DMSA iteration, N={m.N} points, {win['n_poses']} control poses (P={P}), {P + 10} cost evaluations/step",
-                   "M": int(s["M"]), "G": int(s["G"])},
+        "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 point arithmetic / f64 pose chain, sums, J^T J (the reference's types)", "data": "synthetic",
+        "config": {"workload": workload_string(args.config, win, P, world), "N": int(m.N), "M": int(s["M"]), "G": int(s["G"]),
+                   "l2": "flushed between timed steps (256 MiB write, untimed)", "settings": SETTINGS},
         "point_jacobians_per_s": val * int(s["M"]),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{steps} full iterations; oracle/dmsa_oracle.cpp -O2 -fopenmp (the reference needs Eigen/PCL/Boost: unbuildable here)"},
+                         "sample": f"{steps} full iterations of one window; oracle/dmsa_oracle.cpp -O2 -fopenmp (the reference needs Eigen/PCL/Boost: unbuildable here)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -217,7 +247,7 @@ def run_sliding(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    win = synth.make_config(args.config, seed=None if world == 1 else 100 + rank)
+    win = synth.make_config(args.config)  # every rank gets the same window: per-N values compare like with like
     torch.cuda.set_stream(torch.cuda.Stream(dev))  # a real (non-default) stream: the library launches on it, torch events see it
     stream = torch.cuda.current_stream().cuda_stream
     assert stream != 0
@@ -246,6 +276,8 @@ def run_sliding(args):
         last = traj.iteration(s)
     G, M = traj.buildSets(s)  # sizes of the first iteration's sets (reported with every figure)
     sets = traj.getSets()
+    C_FUSE = traj.L.dmsa_b200_fuse_threshold()
+    N_points = int(traj.numPoints)
     reset_poses()
     traj.profileEnable(True)
     clocks = ClockSampler(local)
@@ -277,38 +309,65 @@ def run_sliding(args):
     d2h = 4 * rel_o.nbytes + 64
     e2e_steps = max(3, min(args.steps, 10))
 
-    def e2e_step():
+    from dmsa_lidar_slam_b200 import DmsaOptimizer
+
+    def stage_window():
         traj.initTraj(win["t_min"], win["t_max"], win["n_poses"], False, win["dt_res"])
         traj.registerPcBuffer([p[1] for p in pinned], win["grid_sizes"])
         traj.addStaticPoints(pstat[1])
         traj.setRelativePoses(rel_o, rel_t)
+
+    def e2e_step():  # one iteration per uploaded window (the conservative definition of round 1)
+        stage_window()
         traj.centralize()
         d = traj.iteration(s)
         poses = traj.getPoses()  # result read-back
-        return d, poses
+        return 1
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        ev2[k][0].record()
-        e2e_step()
-        ev2[k][1].record()
-    barrier()
-    wall_e2e = time.perf_counter() - t0
-    ms_e2e = sum(a.elapsed_time(b) for a, b in ev2)
-    t = torch.tensor([max(ms_e2e, 1e3 * wall_e2e)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps / (float(t.item()) * 1e-3)
+    s_prod = DmsaOptimSettings(**dict(SETTINGS, num_iter=PRODUCTION_NUM_ITER))
+    opt = DmsaOptimizer()
+
+    def e2e_optimize():  # the call a user of the reference makes: optimizeSet on a freshly staged window (DmsaSlam.h:150-166)
+        stage_window()
+        rep = opt.optimizeSet(traj, s_prod)
+        poses = traj.getPoses()
+        return rep["iterations"]
+
+    def time_e2e(fn, reps):
+        for _ in range(2):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        t0 = time.perf_counter()
+        iters = 0
+        for k in range(reps):
+            evs[k][0].record()
+            iters += fn()
+            evs[k][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([max(ms, 1e3 * wall)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return world * iters / (float(t.item()) * 1e-3), iters / reps
+
+    e2e_single, _ = time_e2e(e2e_step, e2e_steps)
+    e2e_value, e2e_iters = time_e2e(e2e_optimize, max(3, min(args.steps // 2, 6)))
     clk = clocks.stop()
+    keyframe = None
+    if args.keyframe:
+        from dmsa_lidar_slam_b200 import distributed
+
+        del traj
+        keyframe = distributed.measure_keyframe(max(3, min(args.steps, 10)), args.warmup, rank, world, local,
+                                                cpu_baseline_fn=keyframe_cpu_baseline if world == 1 else None)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    T = C_FUSE
     # ---------------- roofline of the dominant kernel ----------------
     peak, peak_src = load_peaks()
     # the dominant single kernel: the fused evaluation of the forward-difference batch over the sets that fit one block (the
@@ -316,7 +375,6 @@ def run_sliding(args):
     dom = "k_cost_fused_fd" if prof.get("k_cost_fused_fd", (0, 0))[1] else max((k for k in prof if k.startswith("k_cost")), key=lambda k: prof[k][0])
     dom_ms, dom_n = prof[dom]
     V = P + 1 if dom.endswith("_fd") else 9
-    T = traj.L.dmsa_b200_fuse_threshold()
     n_per_set = np.diff(sets["offs"])
     small = n_per_set <= T
     if "fused" in dom:
@@ -342,15 +400,19 @@ def run_sliding(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 point arithmetic / f64 pose chain, sums, J^T J (the reference's types)", "data": "synthetic",
-        "config": {"workload": f"{args.config}: sliding-window DMSA iteration (DmsaOptimizer.h:69-144), {len(win['scans'])} scans x {len(win['scans'][0])} pts + "
-                               f"{len(win['static'])} static, {win['n_poses']} control poses, P={P}, {P + 10} cost evaluations/step; "
-                               + ("1 window" if world == 1 else f"{world} independent windows (replicas, no collective)"),
-                   "N": int(traj.numPoints), "M": int(M), "G": int(G), "l2": "flushed between timed steps (256 MiB write, untimed)",
+        "config": {"workload": workload_string(args.config, win, P, world),
+                   "N": N_points, "M": int(M), "G": int(G), "l2": "flushed between timed steps (256 MiB write, untimed)",
                    "settings": SETTINGS},
         "point_jacobians_per_s": value * M,
         "membership_evals_per_s": value * M * (P + 10),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                "what": "traj_init (timing tables recomputed and uploaded every step: table reuse switched off) + register_scans + add_static_points (pinned host AoS PointStampId) + set poses + centralize + 1 iteration + pose read-back"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e2e_iters), "d2h_bytes_per_step": int(d2h / e2e_iters),
+                "iterations_per_window": e2e_iters, "h2d_bytes_per_window": int(h2d), "d2h_bytes_per_window": int(d2h),
+                "what": f"the reference's call on a new window, timed whole: traj_init (timing tables recomputed and uploaded: table reuse switched off) + "
+                        f"register_scans + add_static_points (pinned host AoS PointStampId) + set poses + optimizeSet(num_iter = {PRODUCTION_NUM_ITER}, the "
+                        "production setting of config/slam_settings.yaml:22: centralize, iterations, decentralize, final updateGlobalPoints) + pose read-back; "
+                        "value = iterations run / time",
+                "single_iteration_per_upload": {"value": e2e_single, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                                                "what": "round-1 definition: one iteration per uploaded window (upload + centralize + 1 iteration + pose read-back)"}},
         "gpu_launches": int(launches),
         "gpu_launches_note": "hand-written kernels only (CUB radix-sort/scan launches inside the set build are not counted)",
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
@@ -363,11 +425,17 @@ def run_sliding(args):
         "clocks": clk,
         "last_step": {"G": last["num_gaussians"], "error0": last["error0"], "best_step": last["best_step"], "stop": last["stop"]},
     }
+    if keyframe is not None:
+        line["keyframe"] = keyframe
     if world == 1:
         threads = best_thread_count(win)
         cb = oracle_cpu_baseline(win, threads)
         line["cpu_baseline"] = {"value": 1.0 / cb["seconds_per_iteration"], "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "median of 2 full iterations of the same workload; oracle/dmsa_oracle.cpp -O2 -fopenmp, faithful arithmetic"}
+        # the reference's own build and threading: -O1 (CMakeLists.txt:15), serial cost loops (DmsaOptimizer.h:56-57 only feeds Eigen's GEMM)
+        cf = oracle_cpu_baseline(win, 1, iters=1, opt="O1")
+        line["cpu_baseline"]["reference_faithful"] = {"value": 1.0 / cf["seconds_per_iteration"], "unit": UNIT, "cores": 1, "kind": "port",
+                                                      "sample": "1 full iteration; oracle/dmsa_oracle.cpp -O1, one thread (the reference's cost loops are serial)"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -381,6 +449,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sliding", choices=["sliding", "keyframe"])
     ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--keyframe", type=int, default=1, help="1: also measure BASELINE config 4 (keyframe bundles, NCCL all-reduce) -> `keyframe` object")
     args = ap.parse_args()
     global RESULT_OUT
     RESULT_OUT = _claim_stdout()

@@ -81,6 +81,12 @@ def load_library():
         "dmsa_b200_synchronize": (i32, [vp]),
         "dmsa_b200_traj_init": (i32, [vp, f64, f64, i32, i32, f64]),
         "dmsa_b200_traj_init_window": (i32, [vp, f64, f64, i32, i32, f64]),
+        "dmsa_b200_spd_solve_dev": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, vp]),
+        "dmsa_b200_spd_solve": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
+        "dmsa_b200_bundle_jacobian": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, i32]),
+        "dmsa_b200_bundle_line_search": (i32, [vp, vp, vp, vp]),
+        "dmsa_b200_bundle_verify": (i32, [vp, P(i32), P(i32)]),
+        "dmsa_b200_all_reduce": (i32, [vp, vp, i64]),
         "dmsa_b200_comm_unique_id": (i32, [vp]),
         "dmsa_b200_comm_init": (i32, [vp, vp, i32, i32]),
         "dmsa_b200_comm_destroy": (i32, [vp]),
@@ -151,7 +157,8 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode",
     "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
-    "dmsa_b200_comm_unique_id", "dmsa_b200_comm_init", "dmsa_b200_comm_destroy", "dmsa_b200_collective_count",
+    "dmsa_b200_spd_solve_dev", "dmsa_b200_spd_solve", "dmsa_b200_bundle_jacobian", "dmsa_b200_bundle_line_search", "dmsa_b200_bundle_verify",
+    "dmsa_b200_all_reduce", "dmsa_b200_comm_unique_id", "dmsa_b200_comm_init", "dmsa_b200_comm_destroy", "dmsa_b200_collective_count",
 ]
 
 
@@ -358,6 +365,34 @@ class OptimizablePointSet:
         nan = C.c_int32(0)
         self.ctx._ck(self.L.dmsa_b200_lm_solve_device(self.h, C.byref(settings), _p(hg), int(n_params), _p(step), C.byref(nan)))
         return step, int(nan.value)
+
+    def spdSolve(self, settings, hg, n_params):
+        """Device Cholesky LM step of the bundle extension on a host [H | g | err0] buffer: (step, flag 0 ok / 1 NaN / 2 not SPD)."""
+        hg = np.ascontiguousarray(hg, dtype=np.float64)
+        step = np.zeros(int(n_params))
+        flag = C.c_int32(0)
+        self.ctx._ck(self.L.dmsa_b200_spd_solve(self.h, C.byref(settings), _p(hg), int(n_params), _p(step), C.byref(flag)))
+        return step, int(flag.value)
+
+    def spdSolveDev(self, settings, hg_dev_ptr, n_params, step_dev_ptr, tail_dev_ptr):
+        self.ctx._ck(self.L.dmsa_b200_spd_solve_dev(self.h, C.byref(settings), C.c_void_p(hg_dev_ptr), int(n_params), C.c_void_p(step_dev_ptr),
+                                                    C.c_void_p(tail_dev_ptr)))
+
+    def bundleJacobian(self, settings, idx_dev_ptr, P_global, ghg_dev_ptr, sync_build=False):
+        self.ctx._ck(self.L.dmsa_b200_bundle_jacobian(self.h, C.byref(settings), C.c_void_p(idx_dev_ptr), int(P_global), C.c_void_p(ghg_dev_ptr),
+                                                      int(bool(sync_build))))
+
+    def bundleLineSearch(self, gstep_dev_ptr, idx_dev_ptr, gls_dev_ptr):
+        self.ctx._ck(self.L.dmsa_b200_bundle_line_search(self.h, C.c_void_p(gstep_dev_ptr), C.c_void_p(idx_dev_ptr), C.c_void_p(gls_dev_ptr)))
+
+    def bundleVerify(self):
+        G, redo = C.c_int32(0), C.c_int32(0)
+        self.ctx._ck(self.L.dmsa_b200_bundle_verify(self.h, C.byref(G), C.byref(redo)))
+        self._G = G.value
+        return G.value, bool(redo.value)
+
+    def allReduce(self, dev_ptr, count):
+        self.ctx._ck(self.L.dmsa_b200_all_reduce(self.h, C.c_void_p(dev_ptr), int(count)))
 
     def profileEnable(self, on=True):
         self.ctx._ck(self.L.dmsa_b200_profile_enable(self.h, int(bool(on))))

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/dmsa_b200.h"
+#include "kernels_chol.cuh"
 #include "kernels_cost.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_knn.cuh"
@@ -210,7 +211,7 @@ struct dmsa_b200_ctx {
     DBuf<int> d_gidx, d_gsidx, d_gcount;
     DBuf<float4> d_gpts, d_gquery;
     DBuf<unsigned char> d_gsel;
-    DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart, d_solve, d_iter;
+    DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart, d_solve, d_iter, d_chol;
     bool solveAttr = false;
     DBuf<int> d_biglist;  // sets with more than GAUSS_WARP_MAX members (+ the count at [cellCap])
     DBuf<int> d_done;  // per-set completion counters of k_cost_quad [0, cap] and k_cost_sum [cap + 1, 2 cap + 1] (zeroed by the set build, self-resetting)
@@ -379,6 +380,35 @@ __global__ void k_shift_static(float4* __restrict__ local, float4* __restrict__ 
     }
     world[off + i] = p;
     local[off + i] = p;
+}
+
+// ---- keyframe-bundle extension: a bundle's [H_b | g_b | err0_b] scattered into the global system (parameters are RELATIVE
+// poses, so bundle-local parameter i is global parameter idx[i]); the bundles of a rank run on one stream, one after the
+// other, so plain read-modify-write is race-free and the summation order is fixed
+__global__ void k_bundle_scatter(const double* __restrict__ hg, int Pl, const int* __restrict__ idx, int Pg, const LevelInfo* __restrict__ li,
+                                 int depth0, int depth1, double* __restrict__ ghg) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nH = Pl * Pl;
+    if (e < nH) {
+        const int i = e / Pl, j = e - i * Pl;
+        ghg[(size_t)idx[i] * Pg + idx[j]] += hg[e];
+    } else if (e < nH + Pl) {
+        ghg[(size_t)Pg * Pg + idx[e - nH]] += hg[e];
+    } else if (e == nH + Pl) {
+        ghg[(size_t)Pg * Pg + Pg] += hg[e];                           // e0^T e0
+        ghg[(size_t)Pg * Pg + Pg + 1] += (double)total_sets(li);      // number of Gaussian sets (DmsaOptimizer.h:89)
+        // a deferred build that ran on a wrong guess (more sets than the grids were sized for, or a deeper octree than the
+        // sort keys covered) is counted here, so that after the all-reduce EVERY rank knows the iteration must be repeated
+        const bool miss = li[0].G + li[1].G > max(li[0].bound, li[1].bound) || li[0].depth > depth0 || li[1].depth > depth1 || li[0].error || li[1].error;
+        if (miss) ghg[(size_t)Pg * Pg + Pg + 2] += 1.0;
+    }
+}
+__global__ void k_bundle_gather_step(const double* __restrict__ gstep, const int* __restrict__ idx, int Pl, double* __restrict__ step) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Pl) step[i] = gstep[idx[i]];
+}
+__global__ void k_add9(const double* __restrict__ src, double* __restrict__ dst) {
+    if (threadIdx.x < 9) dst[threadIdx.x] += src[threadIdx.x];
 }
 
 int64_t numPoints(const dmsa_b200_ctx* ctx) { return ctx->n_scan + ctx->n_static; }
@@ -1281,7 +1311,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
     REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_gkeys); REL(d_gskeys); REL(d_gidx); REL(d_gsidx); REL(d_gcount); REL(d_gpts); REL(d_gquery); REL(d_gsel); REL(d_mom); REL(d_solve); REL(d_iter);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_gkeys); REL(d_gskeys); REL(d_gidx); REL(d_gsidx); REL(d_gcount); REL(d_gpts); REL(d_gquery); REL(d_gsel); REL(d_mom); REL(d_solve); REL(d_iter); REL(d_chol);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
@@ -2069,6 +2099,122 @@ int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world) {
     ctx->world = world;
     return 0;
 }
+// ---- SPD solve of the keyframe-bundle extension (kernels_chol.cuh): device in, device out ----
+int dmsa_b200_spd_solve_dev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, const double* hg_dev, int32_t n, double* step_dev, double* tail_dev) {
+    if (!st || !hg_dev || !step_dev || !tail_dev || n <= 0 || n > CHOL_MAXN) ARGFAIL("spd_solve_dev: bad arguments (1 <= n <= 1024)");
+    CK(cudaSetDevice(ctx->device));
+    const int ld = pad32(n);
+    CK(ctx->d_chol.ensure((size_t)(n + 1) * ld + 8));
+    CholArgs q;
+    q.hg = hg_dev;
+    q.n = n;
+    q.ld = ld;
+    q.lambda = (double)st->lambda_diag;
+    q.alpha = st->step_length_optim;
+    q.max_step = st->max_step;
+    q.W = ctx->d_chol.p;
+    q.step = step_dev;
+    q.step2 = nullptr;
+    q.tail = tail_dev;
+    q.flag = reinterpret_cast<int*>(ctx->d_chol.p + (size_t)(n + 1) * ld);
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int tiles = ((n + 31) / 32) * ((n + 31) / 32 + 1) / 2;
+    const unsigned grid = (unsigned)std::max(1, std::min(std::min(nsm, 64), tiles));
+    void* args[] = {&q};
+    ProfScope prof_(ctx, PROF_LM_SOLVE);
+    CK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_T), args, 0, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+// the same on host buffers (validation): step[n], *flag = 0 ok / 1 NaN / 2 not positive definite
+int dmsa_b200_spd_solve(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, const double* hg, int32_t n, double* step, int32_t* flag) {
+    if (!st || !hg || !step || n <= 0 || n > CHOL_MAXN) ARGFAIL("spd_solve: bad arguments (1 <= n <= 1024)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nhg = (size_t)n * n + n + 1;
+    CK(ctx->d_hg.ensure(nhg));
+    CK(ctx->d_iter.ensure(16 + (size_t)n + 2));
+    CK(cudaMemcpyAsync(ctx->d_hg.p, hg, nhg * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CKRC(dmsa_b200_spd_solve_dev(ctx, st, ctx->d_hg.p, n, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + n));
+    std::vector<double> r((size_t)n + 2);
+    CK(cudaMemcpyAsync(r.data(), ctx->d_iter.p + 16, r.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::copy(r.begin(), r.begin() + n, step);
+    if (flag) *flag = (int)r[(size_t)n + 1];
+    return 0;
+}
+
+// ---- keyframe-bundle extension (BASELINE config 4): one context per bundle, the orchestration of an iteration is
+//      jacobian (every bundle) -> all_reduce -> spd_solve_dev -> line_search (every bundle) -> all_reduce -> ONE read-back
+//      -> verify (every bundle).  Nothing in between touches the host.
+int dmsa_b200_bundle_jacobian(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, const int32_t* idx_dev, int32_t P_global, double* ghg_dev, int32_t sync_build) {
+    if (!st || !idx_dev || !ghg_dev) ARGFAIL("bundle_jacobian: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->model == MODEL_NONE) ARGFAIL("bundle_jacobian: no model staged");
+    const int P = 6 * (ctx->poses.n - 1);
+    if (P <= 0 || P > P_global) ARGFAIL("bundle_jacobian: bad parameter counts");
+    ctx->poses.relative2global();
+    CKRC(uploadParams(ctx));
+    CKRC(prepareFdBatch(ctx));
+    CKRC(transformBase(ctx));
+    CKRC(buildSets(ctx, st, sync_build == 0));
+    CKRC(runCost(ctx));
+    CK(ctx->d_hg.ensure((size_t)P * P + P + 1));
+    CK(ctx->d_ls.ensure(16));
+    CKRC(jtjInto(ctx, ctx->d_hg.p));
+    LAUNCH(k_bundle_scatter, cdiv((size_t)P * P + P + 1, 256), 256, 0, ctx->d_hg.p, P, idx_dev, P_global, ctx->d_linfo.p,
+           ctx->levelOn[0] ? ctx->cachedDepth[0] : 1 << 30, ctx->levelOn[1] ? ctx->cachedDepth[1] : 1 << 30, ghg_dev);
+    CKRC(ensurePinned(ctx, P));
+    CK(cudaMemcpyAsync(pinLinfo(ctx, P), ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+int dmsa_b200_bundle_line_search(dmsa_b200_ctx* ctx, const double* gstep_dev, const int32_t* idx_dev, double* gls_dev) {
+    if (!gstep_dev || !idx_dev || !gls_dev) ARGFAIL("bundle_line_search: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int P = 6 * (ctx->poses.n - 1);
+    LAUNCH(k_bundle_gather_step, cdiv(P, 128), 128, 0, gstep_dev, idx_dev, P, ctx->d_step.p);
+    CKRC(lineSearchDev(ctx, ctx->d_ls.p));
+    LAUNCH(k_add9, 1, 32, 0, ctx->d_ls.p, gls_dev);
+    CK(cudaGetLastError());
+    return 0;
+}
+// after the caller synchronised the stream: the set count of the last bundle_jacobian and whether its deferred build ran on
+// a wrong guess (octree depth grew / more sets than the grids were sized for) -> *redo = 1: repeat the iteration with sync_build = 1
+int dmsa_b200_bundle_verify(dmsa_b200_ctx* ctx, int32_t* num_gaussians, int32_t* redo) {
+    const int P = 6 * (ctx->poses.n - 1);
+    if (!ctx->pin) ARGFAIL("bundle_verify: no bundle_jacobian before");
+    if (ctx->profiling) profCollect(ctx);
+    int G = 0;
+    bool miss = false;
+    if (ctx->G < 0) {
+        memcpy(ctx->h_linfo, pinLinfo(ctx, P), 2 * sizeof(LevelInfo));
+        for (int l = 0; l < 2; ++l) {
+            if (!ctx->levelOn[l]) continue;
+            if (ctx->h_linfo[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
+            if (ctx->h_linfo[l].depth > ctx->cachedDepth[l]) miss = true;
+            ctx->cachedDepth[l] = ctx->h_linfo[l].depth;
+            G += ctx->h_linfo[l].G;
+        }
+        if (G > ctx->cellCap) ARGFAIL("build_sets: Gaussian store capacity exceeded");
+        if (G > ctx->Gb) miss = true;
+        ctx->Gguess = std::max(G, 1);
+        if (!miss) ctx->G = G;
+    } else {
+        G = ctx->G;
+    }
+    if (num_gaussians) *num_gaussians = G;
+    if (redo) *redo = miss ? 1 : 0;
+    return 0;
+}
+// sum over the ranks of the communicator, in place, on the context's stream (device memory of the caller)
+int dmsa_b200_all_reduce(dmsa_b200_ctx* ctx, double* dev, int64_t count) {
+    if (!dev || count <= 0) ARGFAIL("all_reduce: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->comm && ctx->world == 1) return 0;
+    return allReduceSum(ctx, dev, (size_t)count);
+}
+
 // ---- NCCL communicator of a row-sharded context (one process per GPU; NCCL is bound at run time, nccl_dyn.h) ----
 int dmsa_b200_comm_unique_id(void* id128) {
     if (!id128) return DMSA_B200_ERR_ARG;

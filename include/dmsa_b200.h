@@ -201,6 +201,29 @@ int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev);
 /* 9 partial line-search costs for step (host P doubles) into ls_dev[9] (device) */
 int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, double* ls_dev);
 
+/* LM step of the keyframe-BUNDLE extension (BASELINE config 4): the all-reduced global system of the bundles is symmetric
+ * positive definite and has no reference arithmetic to mirror, so step = -alpha (H + lambda I)^-1 g comes from a blocked
+ * Cholesky factorisation on the device (one cooperative kernel), followed by the NaN guard and the infinity-norm clamp of
+ * DmsaOptimizer.h:113-128.  hg = [H | g | err0]; tail[0] = err0, tail[1] = 0 ok / 1 NaN step / 2 not positive definite. */
+int dmsa_b200_spd_solve_dev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg_dev, int32_t n_params, double* step_dev,
+                            double* tail_dev);
+int dmsa_b200_spd_solve(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step, int32_t* flag);
+
+/* Building blocks of one iteration over keyframe bundles (one context per bundle; every call is asynchronous on the
+ * context's stream; all contexts of a rank must share ONE stream):
+ *   bundle_jacobian   base transform, set build (deferred: no host wait), cost / forward-difference batch, J^T J, and the
+ *                     scatter-add of [H_b | g_b | err0_b | #sets | #missed guesses] into the global buffer ghg_dev
+ *                     (P_global^2 + P_global + 3 doubles) through idx_dev (P_local global parameter indices, device int32)
+ *   all_reduce        NCCL sum over the ranks (communicator of dmsa_b200_comm_init)
+ *   spd_solve_dev     the global LM step (above)
+ *   bundle_line_search  9 trial costs of the bundle for the global step, added into gls_dev[9]
+ *   bundle_verify     after the caller synchronised: set count, and whether a deferred build must be repeated (sync_build = 1) */
+int dmsa_b200_bundle_jacobian(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const int32_t* idx_dev, int32_t P_global, double* ghg_dev,
+                              int32_t sync_build);
+int dmsa_b200_bundle_line_search(dmsa_b200_ctx* ctx, const double* gstep_dev, const int32_t* idx_dev, double* gls_dev);
+int dmsa_b200_bundle_verify(dmsa_b200_ctx* ctx, int32_t* num_gaussians, int32_t* redo);
+int dmsa_b200_all_reduce(dmsa_b200_ctx* ctx, double* dev, int64_t count);
+
 /* In-library exchange for dmsa_b200_iteration / dmsa_b200_optimize on a sharded context: one process per GPU, every rank
  * stages the SAME set and calls the same sequence; an iteration then all-reduces [H | g | err0] (P*P + P + 1 doubles) and the
  * 9 line-search costs with NCCL on the context's stream (intra-node NVLink / NVSwitch), and every rank takes the same step.

@@ -44,8 +44,27 @@ if rank == 0:
     ok = same and out["G"] == out["G_ref"] and out["best"] == out["best_ref"] and max(out["err0_rel"]) < 1e-12 and max(out["ls_rel"]) < 1e-10 \
         and out["params_rel"] < 1e-7 and out["collectives"] == 6
     out["ok"] = bool(ok)
-    print(json.dumps(out))
 kf.commDestroy()
+del kf
+# ---- bundle mode (BASELINE config 4 shape, small): bundles round-robin over the ranks vs all bundles on one GPU ----
+from dmsa_lidar_slam_b200.distributed import KeyframeBundleOptimizer  # noqa: E402
+
+sm2 = synth.make_keyframe_submap(n_keyframes=12, n_points=n_pts, seed=6)
+opt = KeyframeBundleOptimizer(sm2, s, 5, 3, rank, world, local, None)
+rb = [opt.iteration() for _ in range(3)]
+allp = [None] * world
+dist.all_gather_object(allp, opt.p.tobytes())
+if rank == 0:
+    one = KeyframeBundleOptimizer(sm2, s, 5, 3, 0, 1, local, None)
+    r1 = [one.iteration() for _ in range(3)]
+    out["bundles"] = dict(n_bundles=len(opt.ranges), ranks_identical=bool(all(a == allp[0] for a in allp)),
+                          err0_rel=[abs(a["error0"] - b["error0"]) / b["error0"] for a, b in zip(rb, r1)],
+                          best=[a["best_step"] for a in rb], best_1gpu=[b["best_step"] for b in r1], params_rel=rel(opt.p, one.p),
+                          collectives=opt.collective_count())
+    okb = out["bundles"]["ranks_identical"] and max(out["bundles"]["err0_rel"]) < 1e-9 and out["bundles"]["best"] == out["bundles"]["best_1gpu"] \
+        and out["bundles"]["params_rel"] < 1e-7
+    out["ok"] = bool(out["ok"] and okb)
+    print(json.dumps(out))
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0 and not out["ok"]:

@@ -762,3 +762,101 @@ def test_keyframe_bundle_cfg4_scale_against_the_oracle():
     tr = om.last_trace()
     assert d["best_step"] == tr["best_k"] and rel(d["ls_cost"], tr["ls_cost"]) < 1e-8
     assert rel(kf.getPoseParameters(), om.get_params()) < 1e-6
+
+
+# ---- keyframe bundles / multi-GPU building blocks ------------------------------------------------------------
+@pytest.mark.parametrize("n", [5, 33, 84, 378])
+def test_device_cholesky_lm_step_of_the_bundle_extension(n):
+    """kernels_chol.cuh: step = -alpha (H + lambda I)^-1 g with NaN guard and clamp, against LAPACK and the host solver."""
+    from dmsa_lidar_slam_b200.api import lm_solve
+
+    kf = MapManagement(2)
+    rng = np.random.default_rng(n)
+    J = rng.standard_normal((3 * n, n)) * np.logspace(0, -2, n)[None, :]
+    r = rng.standard_normal(3 * n)
+    hg = np.concatenate([(J.T @ J).ravel(), J.T @ r, [float(r @ r)]])
+    for max_step in (1e9, 0.3):
+        s = DmsaOptimSettings(step_length_optim=0.2, max_step=max_step, lambda_diag=1e-5)
+        step, flag = kf.spdSolve(s, hg, n)
+        assert flag == 0
+        ref, nan = lm_solve(s, hg, n, 0)  # host Cholesky
+        assert not nan and rel(step, ref) < 1e-8
+        if max_step > 1:
+            H = hg[:n * n].reshape(n, n) + float(np.float32(1e-5)) * np.eye(n)
+            assert rel(step, -0.2 * np.linalg.solve(H, hg[n * n:n * n + n])) < 1e-7
+        else:
+            assert abs(np.abs(step).max() - 0.3) < 1e-12
+        step2, _ = kf.spdSolve(s, hg, n)
+        assert np.array_equal(step, step2)  # deterministic: every rank computes the same bits
+    hg_bad = hg.copy()
+    hg_bad[:n * n] = -hg[:n * n]  # negative definite
+    assert kf.spdSolve(DmsaOptimSettings(), hg_bad, n)[1] == 2
+    hg_nan = hg.copy()
+    hg_nan[n * n] = np.nan
+    assert kf.spdSolve(DmsaOptimSettings(), hg_nan, n)[1] == 1
+
+
+def test_keyframe_bundle_optimizer_single_bundle_is_the_reference_iteration():
+    """One bundle covering every keyframe == MapManagement.iteration (the reference's keyframe pass), bit for bit."""
+    from dmsa_lidar_slam_b200.distributed import KeyframeBundleOptimizer
+
+    sm = synth.make_keyframe_submap(n_keyframes=5, n_points=6000, seed=9)
+    st = dict(num_iter=2, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=6, min_num_gaussians=10, gauss_split=1, epsilon=1e-7)
+    s = DmsaOptimSettings(**st)
+    opt = KeyframeBundleOptimizer(sm, s, bundle_size=5, overlap=2)
+    assert opt.single
+    kf = MapManagement.from_submap(sm)
+    for _ in range(3):
+        a, b = opt.iteration(), kf.iteration(s)
+        assert a["stop"] == b["stop"] and a["best_step"] == b["best_step"] and a["error0"] == b["error0"] and a["num_sets"] == b["num_gaussians"]
+        assert np.array_equal(a["step"], b["step"]) and np.array_equal(a["ls"], b["ls_cost"])
+    assert np.array_equal(opt.p, kf.getPoseParameters())
+
+
+def test_keyframe_bundles_partial_systems_add_up_and_iterate():
+    """Bundle extension: the global [H | g | err0 | #sets] is the scatter-sum of the bundles' systems; two emulated ranks add up
+    to the single-rank buffer; an iteration lowers the cost and is reproducible."""
+    from dmsa_lidar_slam_b200.distributed import KeyframeBundleOptimizer, bundle_param_index, bundle_ranges
+
+    sm = synth.make_keyframe_submap(n_keyframes=9, n_points=5000, seed=6)
+    st = dict(num_iter=1, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=6, min_num_gaussians=10, gauss_split=1, epsilon=1e-7)
+    s = DmsaOptimSettings(**st)
+    n, P = 9, 48
+    whole = KeyframeBundleOptimizer(sm, s, bundle_size=5, overlap=3)
+    assert len(whole.ranges) == 3 and not whole.single
+    for sync_build in (True, False):  # synchronous builds, then deferred builds (grid sizes from the previous build)
+        whole.jacobian_phase(sync_build)
+        ghg = whole.ghg.cpu().numpy()
+        assert ghg[P * P + P + 2] == 0  # no missed guess
+        # independent composition: every bundle as its own submap through the plain step-by-step API
+        ref = np.zeros(P * P + P + 2)
+        rel_o, rel_t = sm["rel_orient"], sm["rel_transl"]
+        from dmsa_lidar_slam_b200.distributed import relative2global
+        go, gt = relative2global(rel_o, rel_t)
+        for (f, l) in bundle_ranges(n, 5, 3):
+            sub = dict(n_keyframes=l - f + 1, clouds=sm["clouds"][f:l + 1], rings=sm["rings"][f:l + 1], grid_sizes=sm["grid_sizes"][f:l + 1],
+                       rel_orient=rel_o[:, f:l + 1].copy(), rel_transl=rel_t[:, f:l + 1].copy())
+            sub["rel_orient"][:, 0], sub["rel_transl"][:, 0] = go[:, f], gt[:, f]
+            b = MapManagement.from_submap(sub)
+            b.updateGlobalPoints()
+            G, _ = b.buildSets(s)
+            cj = b.costJacobian()
+            idx = bundle_param_index(n, f, l)
+            ref[:P * P].reshape(P, P)[np.ix_(idx, idx)] += cj["H"]
+            ref[P * P + idx] += cj["g"]
+            ref[P * P + P] += cj["err0"]
+            ref[P * P + P + 1] += G
+        assert rel(ghg[:P * P + P + 2], ref) < 1e-13 and ghg[P * P + P + 1] == ref[P * P + P + 1]
+    parts = []
+    for r in range(2):
+        o = KeyframeBundleOptimizer(sm, s, bundle_size=5, overlap=3, rank=r, world=2, emulate=True)
+        o.jacobian_phase(True)
+        parts.append(o.ghg.cpu().numpy())
+    tot = parts[0] + parts[1]
+    assert rel(tot[:P * P], ghg[:P * P]) < 1e-12 and abs(tot[P * P + P] - ghg[P * P + P]) < 1e-13 * ghg[P * P + P]
+    assert tot[P * P + P + 1] == ghg[P * P + P + 1]
+    d1 = whole.iteration()
+    assert d1["stop"] in ("max_iter", "epsilon") and d1["best_step"] >= 1 and d1["ls"][d1["best_step"] - 1] < d1["error0"]
+    again = KeyframeBundleOptimizer(sm, s, bundle_size=5, overlap=3)
+    d2 = again.iteration()
+    assert d2["error0"] == d1["error0"] and np.array_equal(d1["step"], d2["step"]) and np.array_equal(again.p, whole.p)
