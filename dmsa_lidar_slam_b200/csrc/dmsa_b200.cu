@@ -189,6 +189,7 @@ struct dmsa_b200_ctx {
         d_best_ij, d_scratch;
     DBuf<SplitTile> d_tiles;
     DBuf<float> d_best_v;
+    DBuf<int> d_split_search, d_split_nbox;
     DBuf<unsigned long long> d_code, d_scode;
     DBuf<unsigned char> d_cub;
     DBuf<float4> d_rec, d_wrec;
@@ -599,6 +600,8 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
         CK(ctx->d_best_v.ensure(2 * tileBound));
         CK(ctx->d_best_ij.ensure(4 * tileBound));
         CK(ctx->d_scratch.ensure((size_t)2 * N));
+        CK(ctx->d_split_nbox.ensure(12 * N2));
+        CK(ctx->d_split_search.ensure(2 * N2));
     }
     CK(ctx->d_rec.ensure((size_t)2 * N));
     CK(ctx->d_wrec.ensure((size_t)2 * N));
@@ -718,7 +721,12 @@ phase2:
             int* best_i = ctx->d_best_ij.p + 2 * tileBound * l;
             int* best_j = best_i + tileBound;
             int* scratch = ctx->d_scratch.p + (size_t)N * l;
-            LAUNCH_ON(strm, k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, raw_start, acc_flag, li, ntile);
+            int* nbox = ctx->d_split_nbox.p + 6 * N2 * l;
+            int* search = ctx->d_split_search.p + N2 * l;
+            LAUNCH_ON(strm, k_split_nbox_init, cdiv(N2, 256), 256, 0, nbox, search, (int)N2);
+            LAUNCH_ON(strm, k_split_nbox, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox);
+            LAUNCH_ON(strm, k_split_prefilter, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox, search);
+            LAUNCH_ON(strm, k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, raw_start, acc_flag, search, li, ntile);
             CK(cub::DeviceScan::ExclusiveSum(cubTmp, cubBytes, ntile, tile_off, N + 1, strm));
             LAUNCH_ON(strm, k_split_tile_fill, cdiv(N, 256), 256, 0, ntile, tile_off, li, tiles);
             LAUNCH_ON(strm, k_split_pairs, (unsigned)tileBound, 256, 0, tiles, tile_off, li, raw_start, sidx, ctx->d_normal_w.p, best_v, best_i, best_j);
@@ -1309,7 +1317,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
     REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_dense); REL(d_Mtab); REL(d_Mpair);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
-    REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
+    REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_split_nbox); REL(d_split_search); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
     REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_gkeys); REL(d_gskeys); REL(d_gidx); REL(d_gsidx); REL(d_gcount); REL(d_gpts); REL(d_gquery); REL(d_gsel); REL(d_mom); REL(d_solve); REL(d_iter); REL(d_chol);
 #undef REL

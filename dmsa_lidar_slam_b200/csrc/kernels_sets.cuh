@@ -386,12 +386,89 @@ __global__ void k_accept(const int* __restrict__ raw_start, const int* __restric
 struct SplitTile {
     int cell, i1_start;
 };
-__global__ void k_split_tile_counts(const int* __restrict__ raw_start, const int* __restrict__ acc_flag, const LevelInfo* __restrict__ info,
-                                    int* __restrict__ ntile) {
+// Pre-filter of the O(n^2) pair search (exact, not a heuristic): for ANY vector r with |r| <= 1,
+//     ||n_a + n_b|| >= (n_a + n_b) . r >= 2 min_j (n_j . r),
+// so a leaf whose normals all satisfy n_j . r > 0.3 has min ||n_a + n_b|| > 0.6 > 0.5 and splitSet leaves it unsplit
+// (Gaussians.h:54) whatever the arg-min pair is.  r = the centre of the leaf's normal bounding box, normalised (rounded
+// down in length): independent of how many points each surface contributes, so walls meeting at a corner pass.  Only the
+// leaves that fail (surfaces seen from both sides, the ones that really split) run the pair search.
+__device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> int
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__global__ void k_split_nbox(const int* __restrict__ idx, const int* __restrict__ scan, const int* __restrict__ acc_flag, const LevelInfo* __restrict__ info,
+                             const float4* __restrict__ normal_w, int* __restrict__ nbox /*[R][6]: ordered-int min xyz, max xyz*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in = i < info->n_valid;
+    const int c = in ? scan[i] - 1 : -1 - lane;  // (distinct negative ids: never merged)
+    const bool act = in && acc_flag[c];
+    int mn[3] = {2147483647, 2147483647, 2147483647}, mx[3] = {-2147483647 - 1, -2147483647 - 1, -2147483647 - 1};
+    if (act) {
+        const float4 n = normal_w[idx[i]];
+        mn[0] = mx[0] = f2ord(n.x);
+        mn[1] = mx[1] = f2ord(n.y);
+        mn[2] = mx[2] = f2ord(n.z);
+    }
+    // segmented min / max over the contiguous runs of equal leaf id inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int c2 = __shfl_down_sync(0xffffffffu, c, o);
+        const bool take = lane + o < 32 && c2 == c;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int m2 = __shfl_down_sync(0xffffffffu, mn[a], o), x2 = __shfl_down_sync(0xffffffffu, mx[a], o);
+            if (take) {
+                mn[a] = min(mn[a], m2);
+                mx[a] = max(mx[a], x2);
+            }
+        }
+    }
+    const int cprev = __shfl_up_sync(0xffffffffu, c, 1);
+    if (act && (lane == 0 || cprev != c)) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(nbox + 6 * (size_t)c + a, mn[a]);
+            atomicMax(nbox + 6 * (size_t)c + 3 + a, mx[a]);
+        }
+    }
+}
+__global__ void k_split_prefilter(const int* __restrict__ idx, const int* __restrict__ scan, const int* __restrict__ acc_flag, const LevelInfo* __restrict__ info,
+                                  const float4* __restrict__ normal_w, const int* __restrict__ nbox, int* __restrict__ search /*[R]: 1 = run the pair search*/) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= info->n_valid) return;
+    const int c = scan[i] - 1;
+    if (!acc_flag[c]) return;
+    const int* __restrict__ b = nbox + 6 * (size_t)c;
+    const float sx = 0.5f * (ord2f(b[0]) + ord2f(b[3])), sy = 0.5f * (ord2f(b[1]) + ord2f(b[4])), sz = 0.5f * (ord2f(b[2]) + ord2f(b[5]));
+    const float len = sqrtf(sx * sx + sy * sy + sz * sz);
+    bool ok = false;
+    if (len > 1e-3f && len < 3.0e38f) {
+        const float inv = 1.0f / (len * 1.00001f);  // |r| < 1
+        const float4 n = normal_w[idx[i]];
+        const float d = (n.x * sx + n.y * sy + n.z * sz) * inv;
+        ok = d > 0.3f;  // (NaN compares false -> searched)
+    }
+    if (!ok) search[c] = 1;
+}
+// nbox initial values: min slots = INT_MAX, max slots = INT_MIN
+__global__ void k_split_nbox_init(int* __restrict__ nbox, int* __restrict__ search, int n_cells) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        nbox[6 * (size_t)c + a] = 2147483647;
+        nbox[6 * (size_t)c + 3 + a] = -2147483647 - 1;
+    }
+    search[c] = 0;
+}
+__global__ void k_split_tile_counts(const int* __restrict__ raw_start, const int* __restrict__ acc_flag, const int* __restrict__ search,
+                                    const LevelInfo* __restrict__ info, int* __restrict__ ntile) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int R = info->R;
     if (c > R) return;
-    ntile[c] = (c < R && acc_flag[c]) ? (raw_start[c + 1] - raw_start[c] + 255) / 256 : 0;
+    ntile[c] = (c < R && acc_flag[c] && search[c]) ? (raw_start[c + 1] - raw_start[c] + 255) / 256 : 0;
 }
 __global__ void k_split_tile_fill(const int* __restrict__ ntile, const int* __restrict__ tile_off, const LevelInfo* __restrict__ info,
                                   SplitTile* __restrict__ tiles) {

@@ -209,13 +209,15 @@ class KeyframeBundleOptimizer:
                     ls=d["ls_cost"], step=d["step"])
 
     def jacobian_phase(self, sync_build=False):
-        """This rank's partial [H | g | err0 | #sets | #misses] in self.ghg (before the all-reduce)."""
+        """This rank's partial [H | g | err0 | #sets | #misses] in self.ghg (before the all-reduce).  Everything is enqueued on
+        self.stream (torch's zero_ included); a caller outside iteration() synchronises before reading self.ghg."""
         s, P = self.settings, self.P
-        self._push_poses()
-        self.ghg.zero_()
-        self.out.zero_()
-        for c, idx in zip(self.ctx, self.idx_dev):
-            c.bundleJacobian(s, idx.data_ptr(), P, self.ghg.data_ptr(), sync_build)
+        with self.torch.cuda.stream(self.stream):
+            self._push_poses()
+            self.ghg.zero_()
+            self.out.zero_()
+            for c, idx in zip(self.ctx, self.idx_dev):
+                c.bundleJacobian(s, idx.data_ptr(), P, self.ghg.data_ptr(), sync_build)
 
     def _iteration_bundles(self, sync_build):
         s, P = self.settings, self.P

@@ -826,6 +826,7 @@ def test_keyframe_bundles_partial_systems_add_up_and_iterate():
     assert len(whole.ranges) == 3 and not whole.single
     for sync_build in (True, False):  # synchronous builds, then deferred builds (grid sizes from the previous build)
         whole.jacobian_phase(sync_build)
+        whole.stream.synchronize()
         ghg = whole.ghg.cpu().numpy()
         assert ghg[P * P + P + 2] == 0  # no missed guess
         # independent composition: every bundle as its own submap through the plain step-by-step API
@@ -851,6 +852,7 @@ def test_keyframe_bundles_partial_systems_add_up_and_iterate():
     for r in range(2):
         o = KeyframeBundleOptimizer(sm, s, bundle_size=5, overlap=3, rank=r, world=2, emulate=True)
         o.jacobian_phase(True)
+        o.stream.synchronize()
         parts.append(o.ghg.cpu().numpy())
     tot = parts[0] + parts[1]
     assert rel(tot[:P * P], ghg[:P * P]) < 1e-12 and abs(tot[P * P + P] - ghg[P * P + P]) < 1e-13 * ghg[P * P + P]
