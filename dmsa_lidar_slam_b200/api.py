@@ -132,6 +132,7 @@ def load_library():
         "dmsa_b200_lm_solve": (i32, [P(DmsaOptimSettings), vp, i32, i32, vp, P(i32)]),
         "dmsa_b200_set_lm_solver": (i32, [vp, i32]),
         "dmsa_b200_set_pair_mode": (i32, [vp, i32]),
+        "dmsa_b200_get_batch_tables": (i32, [vp, vp, vp]),
         "dmsa_b200_select_static_points": (i32, [vp, vp, i64, vp, C.c_float, vp, P(i64)]),
         "dmsa_b200_overlap": (i32, [vp, vp, i64, C.c_float, P(C.c_float)]),
         "dmsa_b200_lm_solve_device": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
@@ -155,7 +156,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_get_voxel_keys", "dmsa_b200_eval_cost", "dmsa_b200_cost_jacobian", "dmsa_b200_iteration", "dmsa_b200_optimize",
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
-    "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode",
+    "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode", "dmsa_b200_get_batch_tables",
     "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
     "dmsa_b200_spd_solve_dev", "dmsa_b200_spd_solve", "dmsa_b200_bundle_jacobian", "dmsa_b200_bundle_line_search", "dmsa_b200_bundle_verify",
     "dmsa_b200_all_reduce", "dmsa_b200_comm_unique_id", "dmsa_b200_comm_init", "dmsa_b200_comm_destroy", "dmsa_b200_collective_count",
@@ -349,6 +350,14 @@ class OptimizablePointSet:
         out = C.c_float(0.0)
         self.ctx._ck(self.L.dmsa_b200_overlap(self.h, _p(a), len(a), float(max_dist), C.byref(out)))
         return float(out.value)
+
+    def batchTables(self):
+        """The float transform table of the batch evaluated last: (rows + 1, V, 12)."""
+        dims = np.zeros(2, dtype=np.int32)
+        self.ctx._ck(self.L.dmsa_b200_get_batch_tables(self.h, None, _p(dims)))
+        out = np.zeros((int(dims[0]), int(dims[1]), 12), dtype=np.float32)
+        self.ctx._ck(self.L.dmsa_b200_get_batch_tables(self.h, _p(out), _p(dims)))
+        return out
 
     def setPairMode(self, mode):
         """1: pair-packed FP32x2 cost kernels for the forward-difference batch (default); 0: scalar kernels (bit-identical)."""

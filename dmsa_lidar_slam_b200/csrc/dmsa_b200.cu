@@ -179,8 +179,10 @@ struct dmsa_b200_ctx {
     // pose batches
     DBuf<double> d_p, d_step, d_batch, d_globO, d_globT, d_quat, d_extra, d_dense;
     DBuf<float> d_Mtab, d_Mpair;
-    int pairMode = 1;  // 1: pair-packed cost kernels (FMUL2/FADD2) for the forward-difference batch, 0: scalar kernels; bit-identical
+    int pairMode = 1;  // 1: pair-packed cost kernels (FMUL2/FADD2) with the shared-rotation fast path for the translation vectors of the
+                       // forward-difference batch, 2: pair-packed without the fast path, 0: scalar kernels; all bit-identical
     int curV = 0, curVld = 0;
+    bool fdBatch = false;  // the tables hold the forward-difference batch [p, p + h e_0, ..]: vectors beyond 3 (n - 1) perturb translations only
 
     // set construction
     DBuf<LevelInfo> d_linfo;
@@ -458,6 +460,7 @@ int runPoseTables(dmsa_b200_ctx* ctx, int V) {
     KfFactors kf;
     memset(&kf, 0, sizeof(kf));
     const size_t smem = (size_t)n * 24 * sizeof(double);
+    ctx->fdBatch = false;
     ProfScope prof_(ctx, ctx->phase ? PROF_POSE_LS : PROF_POSE_FD);
     if (ctx->model == MODEL_TRAJ) {
         if (E > 0) {
@@ -616,7 +619,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
     CK(ctx->d_cell_w.ensure(cap));
     CK(ctx->d_nchunk.ensure((size_t)cap + 1));
     CK(ctx->d_chunk_off.ensure((size_t)cap + 1));
-    CK(ctx->d_done.ensure(2 * ((size_t)cap + 1)));
+    CK(ctx->d_done.ensure(4 * ((size_t)cap + 1)));
     CKRC(ensureCub(ctx, N, cap));
     CellStore cs;
     cs.start = ctx->d_cell_start.p;
@@ -808,7 +811,7 @@ phase2:
         CK(cudaEventRecord(ctx->evJoin, s2));
         LAUNCH(k_gaussian, cdiv((size_t)Gb * 32, 256), 256, 0, ctx->d_wrec.p, cs, li, ctx->d_mom.p);
         CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_done.p, 0, 2 * ((size_t)cap + 1) * sizeof(int), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_done.p, 0, 4 * ((size_t)cap + 1) * sizeof(int), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_nchunk.p, 0, ((size_t)Gb + 1) * sizeof(int), ctx->stream));  // entries behind the last set stay 0
         LAUNCH(k_cell_plan, cdiv(Gb, 256), 256, 0, cs, li, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
         LAUNCH(k_cell_order, cdiv(Gb, 256), 256, 0, li, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
@@ -877,12 +880,31 @@ int runCost(dmsa_b200_ctx* ctx) {
         default: LAUNCH((KERN<false, 1024, 1>), GRID, Vld, 0, __VA_ARGS__); break;         \
     }
     const bool pair = !packed && ctx->pairMode;  // two parameter vectors per thread, packed FP32x2 (kernels_cost.cuh)
+    // shared-rotation fast path (kernels_cost.cuh): two blocks per set / chunk, one for the vector pairs that carry a rotation of
+    // their own, one for the pairs that perturb a translation only
+    int pairT = Vld / 2, mult = 1;
+    a.split = 0;
+    a.ns = pairT;
+    a.done_f = ctx->d_done.p + 2 * ((size_t)ctx->cellCap + 1);
+    a.done1_f = ctx->d_done.p + 3 * ((size_t)ctx->cellCap + 1);
+    if (pair && ctx->pairMode == 1 && ctx->fdBatch) {
+        const int vT = 1 + 3 * (ctx->poses.n - 1);  // first vector that perturbs a translation: p + h e_{3 (n - 1)}
+        const int ns = (vT + 1) / 2, nf = (V + 1) / 2 - ns;
+        if (nf > 0) {
+            a.split = 1;
+            a.ns = ns;
+            pairT = pad32(std::max(ns, nf));
+            mult = 2;
+        }
+    }
+    const int cls2 = pairT <= 32 ? 0 : (pairT <= 64 ? 1 : (pairT <= 128 ? 2 : (pairT <= 256 ? 3 : 4)));
 #define DISPATCH2(KERN, GRID, ...)                                                         \
-    switch (cls) {                                                                         \
-        case 1: LAUNCH((KERN<64, 12>), GRID, Vld / 2, 0, __VA_ARGS__); break;              \
-        case 2: LAUNCH((KERN<128, 6>), GRID, Vld / 2, 0, __VA_ARGS__); break;              \
-        case 3: LAUNCH((KERN<256, 3>), GRID, Vld / 2, 0, __VA_ARGS__); break;              \
-        default: LAUNCH((KERN<512, 1>), GRID, Vld / 2, 0, __VA_ARGS__); break;             \
+    switch (cls2) {                                                                        \
+        case 0: LAUNCH((KERN<32, 24>), (GRID) * mult, pairT, 0, __VA_ARGS__); break;       \
+        case 1: LAUNCH((KERN<64, 12>), (GRID) * mult, pairT, 0, __VA_ARGS__); break;       \
+        case 2: LAUNCH((KERN<128, 6>), (GRID) * mult, pairT, 0, __VA_ARGS__); break;       \
+        case 3: LAUNCH((KERN<256, 3>), (GRID) * mult, pairT, 0, __VA_ARGS__); break;       \
+        default: LAUNCH((KERN<512, 1>), (GRID) * mult, pairT, 0, __VA_ARGS__); break;      \
     }
     {
         ProfScope p_(ctx, PROF_FUSED_FD + ph);
@@ -921,7 +943,9 @@ int prepareFdBatch(dmsa_b200_ctx* ctx) {
     // `1.0 * sqrt(std::numeric_limits<float>::epsilon())` resolves to sqrt(float)       DmsaOptimizer.h:209
     const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
     LAUNCH(k_make_fd_batch, cdiv((size_t)(P + 1) * P, 256), 256, 0, ctx->d_p.p, P, h, ctx->d_batch.p);
-    return runPoseTables(ctx, P + 1);
+    CKRC(runPoseTables(ctx, P + 1));
+    ctx->fdBatch = true;
+    return 0;
 }
 
 int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
@@ -1767,6 +1791,22 @@ int dmsa_b200_traj_get_dense_tforms(dmsa_b200_ctx* ctx, float* out) {
     return 0;
 }
 
+// validation surface: the transform table of the batch evaluated last, [rows + 1][V][12] floats (the last row is the identity
+// used by static points); dims = {rows + 1, V}.  out may be NULL (dimensions only).
+int dmsa_b200_get_batch_tables(dmsa_b200_ctx* ctx, float* out, int32_t* dims) {
+    if (ctx->model == MODEL_NONE || ctx->curVld == 0) ARGFAIL("get_batch_tables: no batch evaluated yet");
+    CK(cudaSetDevice(ctx->device));
+    const int rows1 = numTableRows(ctx) + 1, V = ctx->curV, Vld = ctx->curVld;
+    if (dims) {
+        dims[0] = rows1;
+        dims[1] = V;
+    }
+    if (!out) return 0;
+    CK(cudaMemcpy2DAsync(out, (size_t)V * 48, ctx->d_Mtab.p, (size_t)Vld * 48, (size_t)V * 48, rows1, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // denseGlobalPoses of the current parameters (ContinuousTrajectory.h:194-218): 3 x n_total column-major doubles each
 int dmsa_b200_traj_get_dense_poses(dmsa_b200_ctx* ctx, double* orient, double* transl) {
     if (ctx->model != MODEL_TRAJ || ctx->curVld == 0) ARGFAIL("get_dense_poses: call update_global_points first");
@@ -1991,7 +2031,7 @@ int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode) {
 
 // Cost kernels of the forward-difference batch: 1 (default) pair-packed FP32x2 kernels, 0 scalar kernels (bit-identical).
 int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode) {
-    if (mode != 0 && mode != 1) ARGFAIL("set_pair_mode: 1 (pair-packed, default) or 0 (scalar)");
+    if (mode < 0 || mode > 2) ARGFAIL("set_pair_mode: 1 (pair-packed with the shared-rotation fast path, default), 2 (pair-packed, every vector in full) or 0 (scalar)");
     ctx->pairMode = mode;
     return 0;
 }

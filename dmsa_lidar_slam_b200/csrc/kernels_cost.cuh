@@ -45,6 +45,13 @@ struct CostArgs {
     double* Q;               // partial quadratic forms [c * Vld + v]
     double* E;               // residuals      [g * Vld + v]
     const LevelInfo* li;     // the set count lives on the device (total_sets): grids are sized from a host-side bound
+    // pair kernels, forward-difference batch with the shared-rotation fast path (split = 1): every work unit (set / chunk) is
+    // evaluated by TWO independent blocks, blockIdx.x = 2 unit + role.  Role 0 owns the vector pairs [0, ns), which carry a
+    // rotation of their own; role 1 owns the pairs [ns, ..), which perturb a translation only and share the rotated member
+    // coordinates of vector 0.  split = 0: one block per unit evaluates every pair in full.
+    int split, ns;
+    int* done_f;             // completion counters of role 1 (k_cost_quad2) [g]
+    int* done1_f;            // ... and of k_cost_sum2
 };
 
 __device__ __forceinline__ void xform(const float4& m0, const float4& m1, const float4& m2, const float4& r, float& X, float& Y, float& Z) {
@@ -530,9 +537,58 @@ __device__ __forceinline__ u64 mul2s(u64 a, float s) { return mul2(a, pk2(s, s))
         OUTB = fadd_(b0_, fadd_(b1_, b2_));                                                                             \
     }
 
+// ---- shared-rotation fast path ------------------------------------------------------------------------------------
+// Half of the forward-difference vectors perturb a TRANSLATION parameter (parameter layout [w_1..w_{n-1} | t_1..t_{n-1}],
+// Poses.h:64-76).  The rotation block of every table row of such a vector is bit-identical to vector 0's: the pose-chain
+// and dense-table kernels compute it from the rotation parameters alone, by the same instruction sequence
+// (tests/test_gpu_parity.py::test_translation_vectors_share_the_base_rotation_bitwise checks the tables).  The first three
+// terms of Eigen's Matrix4f * Vector4f product, q = (m0 x + m1 y) + m2 z, are therefore the same floats for vector 0 and
+// for every translation vector; a block of translation pairs computes q once per member (stage_partials) and its threads
+// only add their own translation: X = q + m3 — 3 packed adds instead of 9 packed multiplies + 12 adds + 3 packed adds.
+// The two kinds of pairs run in separate blocks (CostArgs::split): the kernels are bound by the latency of each warp's
+// dependent chain, not by issue slots, so a block that mixes a full-cost warp with a cheap one would hold its slot on the SM
+// for the full-cost duration and gain nothing (measured); separate blocks free their slots as soon as they finish.
+#define DMSA_ROW_UPDATE2F(t)                                                                                             \
+    if ((t) != tprev) {                                                                                                 \
+        const u64* Mp = reinterpret_cast<const u64*>(Mv + (size_t)(unsigned)(t) * (size_t)rowbytes);                    \
+        m[3] = __ldg(Mp + 3);                                                                                           \
+        m[7] = __ldg(Mp + 7);                                                                                           \
+        m[11] = __ldg(Mp + 11);                                                                                         \
+        tprev = (t);                                                                                                    \
+    }
+// world coordinates of member record r for the vector pair (FAST: r holds the rotated coordinates q)
+#define DMSA_XFORM2(r, X, Y, Z)                 \
+    if constexpr (FAST) {                       \
+        DMSA_ROW_UPDATE2F(t)                    \
+        X = add2(pk2((r).x, (r).x), m[3]);      \
+        Y = add2(pk2((r).y, (r).y), m[7]);      \
+        Z = add2(pk2((r).z, (r).z), m[11]);     \
+    } else {                                    \
+        DMSA_ROW_UPDATE2(t)                     \
+        DMSA_XROW2(0, r, X)                     \
+        DMSA_XROW2(4, r, Y)                     \
+        DMSA_XROW2(8, r, Z)                     \
+    }
+// q_j = (m0 x + m1 y) + m2 z with vector 0's rotation for `count` member records (coalesced 16-byte loads); sq[j] = (q, table row)
+__device__ __forceinline__ void stage_partials(const CostArgs& a, const float4* __restrict__ rec, float4* __restrict__ sq, int count) {
+    for (int j = threadIdx.x; j < count; j += blockDim.x) {
+        const float4 r = __ldg(rec + j);
+        const float4* __restrict__ Mp = a.Mtab + (size_t)(unsigned)__float_as_int(r.w) * (size_t)a.Vld * 3;
+        const float4 m0 = __ldg(Mp), m1 = __ldg(Mp + 1), m2 = __ldg(Mp + 2);
+        float4 q;
+        q.x = fadd_(fadd_(fmul_(m0.x, r.x), fmul_(m0.y, r.y)), fmul_(m0.z, r.z));
+        q.y = fadd_(fadd_(fmul_(m1.x, r.x), fmul_(m1.y, r.y)), fmul_(m1.z, r.z));
+        q.z = fadd_(fadd_(fmul_(m2.x, r.x), fmul_(m2.y, r.y)), fmul_(m2.z, r.z));
+        q.w = r.w;
+        sq[j] = q;
+    }
+    __syncthreads();
+}
+
 struct PairSums {
     double x0, y0, z0, x1, y1, z1;
 };
+template <bool FAST>
 __device__ __forceinline__ void pass_sum2(const CostArgs& a, const float4* __restrict__ srec, int count, int tp, PairSums& S) {
     S.x0 = S.y0 = S.z0 = S.x1 = S.y1 = S.z1 = 0.0;
     int tprev = -1;
@@ -545,11 +601,8 @@ __device__ __forceinline__ void pass_sum2(const CostArgs& a, const float4* __res
     {                                        \
         const float4 r = srec[(jj)];         \
         const int t = __float_as_int(r.w);   \
-        DMSA_ROW_UPDATE2(t)                  \
         u64 X, Y, Z;                         \
-        DMSA_XROW2(0, r, X)                  \
-        DMSA_XROW2(4, r, Y)                  \
-        DMSA_XROW2(8, r, Z)                  \
+        DMSA_XFORM2(r, X, Y, Z)              \
         float lo, hi;                        \
         upk2(X, lo, hi);                     \
         S.x0 += (double)lo;                  \
@@ -571,6 +624,7 @@ __device__ __forceinline__ void pass_sum2(const CostArgs& a, const float4* __res
     for (; j < count; ++j) DMSA_SUM_BODY2(j)
 #undef DMSA_SUM_BODY2
 }
+template <bool FAST>
 __device__ __forceinline__ void pass_quad2(const CostArgs& a, const float4* __restrict__ srec, int count, int tp, int g, u64 MX, u64 MY, u64 MZ,
                                            double& acc0, double& acc1) {
     const float* __restrict__ I = a.info + 9 * (size_t)g;
@@ -588,11 +642,8 @@ __device__ __forceinline__ void pass_quad2(const CostArgs& a, const float4* __re
     {                                                                                        \
         const float4 r = srec[(jj)];                                                         \
         const int t = __float_as_int(r.w);                                                   \
-        DMSA_ROW_UPDATE2(t)                                                                  \
         u64 X, Y, Z;                                                                         \
-        DMSA_XROW2(0, r, X)                                                                  \
-        DMSA_XROW2(4, r, Y)                                                                  \
-        DMSA_XROW2(8, r, Z)                                                                  \
+        DMSA_XFORM2(r, X, Y, Z)                                                              \
         const u64 d0 = sub2(X, MX), d1 = sub2(Y, MY), d2 = sub2(Z, MZ);                      \
         const u64 t0 = mul2s(d0, wk), t1 = mul2s(d1, wk), t2 = mul2s(d2, wk);                \
         float r0a, r0b, r1a, r1b, r2a, r2b, sa, sb;                                          \
@@ -616,15 +667,20 @@ __device__ __forceinline__ void pass_quad2(const CostArgs& a, const float4* __re
 
 // thread -> vector pair; threads beyond the last pair keep a valid table column and process no members
 struct PairMap {
+    int unit;  // set position / chunk index of this block
     int tp;
-    bool has0, has1;
+    bool has0, has1, fast;  // fast is block-uniform
 };
 __device__ __forceinline__ PairMap pair_map(const CostArgs& a) {
     PairMap pm;
-    pm.tp = threadIdx.x;
-    pm.has0 = 2 * pm.tp < a.V;
-    pm.has1 = 2 * pm.tp + 1 < a.V;
-    if (!pm.has0) pm.tp = (a.V - 1) >> 1;
+    const int tid = threadIdx.x;
+    pm.unit = a.split ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    pm.fast = a.split && (blockIdx.x & 1);
+    pm.tp = pm.fast ? a.ns + tid : tid;
+    const bool mine = pm.fast || !a.split || tid < a.ns;
+    pm.has0 = mine && 2 * pm.tp < a.V;
+    pm.has1 = mine && 2 * pm.tp + 1 < a.V;
+    if (!pm.has0) pm.tp = pm.fast ? (a.V - 1) >> 1 : 0;
     return pm;
 }
 
@@ -632,28 +688,37 @@ template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused2(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
-    if ((int)blockIdx.x >= total_sets(a.li)) return;
-    const int g = a.order[blockIdx.x];
+    const PairMap pm = pair_map(a);
+    if (pm.unit >= total_sets(a.li)) return;
+    const int g = a.order[pm.unit];
     const int kind = a.cell_kind[g];
     if (kind == 2) return;
-    const PairMap pm = pair_map(a);
-    double* __restrict__ Eg = a.E + (size_t)g * a.Vld + 2 * threadIdx.x;
+    double* __restrict__ Eg = a.E + (size_t)g * a.Vld + 2 * pm.tp;
     if (kind == 0) {
         if (pm.has0) Eg[0] = 0.0;
         if (pm.has1) Eg[1] = 0.0;
         return;
     }
     const int n = a.cell_n[g];
-    stage_records(srec, a.rec + a.cell_start[g], n, &bar);
+    if (pm.fast)
+        stage_partials(a, a.rec + a.cell_start[g], srec, n);
+    else
+        stage_records(srec, a.rec + a.cell_start[g], n, &bar);
     const int cnt = pm.has0 ? n : 0;
     PairSums S;
-    pass_sum2(a, srec, cnt, pm.tp, S);
+    if (pm.fast)
+        pass_sum2<true>(a, srec, cnt, pm.tp, S);
+    else
+        pass_sum2<false>(a, srec, cnt, pm.tp, S);
     const float nf = (float)n;
     const u64 MX = pk2(fdiv_((float)S.x0, nf), fdiv_((float)S.x1, nf));  // DmsaOptimizer.h:254
     const u64 MY = pk2(fdiv_((float)S.y0, nf), fdiv_((float)S.y1, nf));
     const u64 MZ = pk2(fdiv_((float)S.z0, nf), fdiv_((float)S.z1, nf));
     double q0, q1;
-    pass_quad2(a, srec, cnt, pm.tp, g, MX, MY, MZ, q0, q1);
+    if (pm.fast)
+        pass_quad2<true>(a, srec, cnt, pm.tp, g, MX, MY, MZ, q0, q1);
+    else
+        pass_quad2<false>(a, srec, cnt, pm.tp, g, MX, MY, MZ, q0, q1);
     if (pm.has0) Eg[0] = sqrt(fabs(q0));  // :267
     if (pm.has1) Eg[1] = sqrt(fabs(q1));
 }
@@ -663,14 +728,19 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_last;
-    const int c = blockIdx.x;
-    if (c >= *a.n_chunks) return;
     const PairMap pm = pair_map(a);
+    const int c = pm.unit;
+    if (c >= *a.n_chunks) return;
     const Chunk ch = a.chunks[c];
-    stage_records(srec, a.rec + ch.start, ch.count, &bar);
     PairSums S;
-    pass_sum2(a, srec, pm.has0 ? ch.count : 0, pm.tp, S);
-    double* __restrict__ Sp = a.S_part + (size_t)c * 3 * a.Vld + 2 * threadIdx.x;
+    if (pm.fast) {
+        stage_partials(a, a.rec + ch.start, srec, ch.count);
+        pass_sum2<true>(a, srec, pm.has0 ? ch.count : 0, pm.tp, S);
+    } else {
+        stage_records(srec, a.rec + ch.start, ch.count, &bar);
+        pass_sum2<false>(a, srec, pm.has0 ? ch.count : 0, pm.tp, S);
+    }
+    double* __restrict__ Sp = a.S_part + (size_t)c * 3 * a.Vld + 2 * pm.tp;
     if (pm.has0) {
         Sp[0] = S.x0;
         Sp[a.Vld] = S.y0;
@@ -683,7 +753,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
     }
     const int g = ch.cell, nc = a.nchunk[g];
     if (nc <= MEAN_INLINE_MAX) return;
-    if (!last_block_of_set(a.done1 + g, nc, &s_last)) return;
+    int* const cnt1 = (pm.fast ? a.done1_f : a.done1) + g;  // the chunk blocks of one role reduce that role's vectors
+    if (!last_block_of_set(cnt1, nc, &s_last)) return;
     if (pm.has0) {  // (an odd V: the second half of the last pair lands on a padding slot)
         const float nf = (float)a.cell_n[g];
         const size_t st3 = (size_t)3 * a.Vld;
@@ -697,7 +768,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
         mu[2 * (size_t)a.Vld] = fdiv_((float)sz.x, nf);
         mu[2 * (size_t)a.Vld + 1] = fdiv_((float)sz.y, nf);
     }
-    if (threadIdx.x == 0) a.done1[g] = 0;
+    if (threadIdx.x == 0) *cnt1 = 0;
 }
 
 template <int MAXT, int MINB>
@@ -705,12 +776,15 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad2(CostArgs a) {
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_last;
-    const int c = blockIdx.x;
-    if (c >= *a.n_chunks) return;
     const PairMap pm = pair_map(a);
+    const int c = pm.unit;
+    if (c >= *a.n_chunks) return;
     const Chunk ch = a.chunks[c];
     const int g = ch.cell;
-    stage_records(srec, a.rec + ch.start, ch.count, &bar);
+    if (pm.fast)
+        stage_partials(a, a.rec + ch.start, srec, ch.count);
+    else
+        stage_records(srec, a.rec + ch.start, ch.count, &bar);
     const int nc = a.nchunk[g], o = ch.first;
     const float nf = (float)a.cell_n[g];
     const size_t st3 = (size_t)3 * a.Vld;
@@ -729,16 +803,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad2(CostArgs a) {
         MZ = mu2[2 * (size_t)a.Vp];
     }
     double q0, q1;
-    pass_quad2(a, srec, pm.has0 ? ch.count : 0, pm.tp, g, MX, MY, MZ, q0, q1);
-    double* __restrict__ Qc = a.Q + (size_t)c * a.Vld + 2 * threadIdx.x;
+    if (pm.fast)
+        pass_quad2<true>(a, srec, pm.has0 ? ch.count : 0, pm.tp, g, MX, MY, MZ, q0, q1);
+    else
+        pass_quad2<false>(a, srec, pm.has0 ? ch.count : 0, pm.tp, g, MX, MY, MZ, q0, q1);
+    double* __restrict__ Qc = a.Q + (size_t)c * a.Vld + 2 * pm.tp;
     if (pm.has0) Qc[0] = q0;
     if (pm.has1) Qc[1] = q1;
-    if (!last_block_of_set(a.done + g, nc, &s_last)) return;
-    double* __restrict__ Eg = a.E + (size_t)g * a.Vld + 2 * threadIdx.x;
+    int* const cnt2 = (pm.fast ? a.done_f : a.done) + g;
+    if (!last_block_of_set(cnt2, nc, &s_last)) return;
+    double* __restrict__ Eg = a.E + (size_t)g * a.Vld + 2 * pm.tp;
     const double2 qs = reduce_chunks2(a.Q + (size_t)o * a.Vld + 2 * pm.tp, nc, (size_t)a.Vld);
     if (pm.has0) Eg[0] = sqrt(fabs(qs.x));
     if (pm.has1) Eg[1] = sqrt(fabs(qs.y));
-    if (threadIdx.x == 0) a.done[g] = 0;
+    if (threadIdx.x == 0) *cnt2 = 0;
 }
 
 // per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): COLSUM_PARTS row slices per vector, fixed reduction order

@@ -153,6 +153,10 @@ int64_t dmsa_b200_num_points(const dmsa_b200_ctx* ctx);
 int dmsa_b200_get_global_points(dmsa_b200_ctx* ctx, float* xyzw, float* normals);
 /* dense local->global transforms of the current parameters: n_total x 12 floats (rows 0..2 of Matrix4f) */
 int dmsa_b200_traj_get_dense_tforms(dmsa_b200_ctx* ctx, float* out);
+/* validation surface: the float transform table of the batch evaluated last (after cost_jacobian: the forward-difference
+ * batch [p, p + h e_0, ..]), (rows + 1) x V x 12 floats, row = dense sample / keyframe, the last row = identity (static
+ * points); dims[2] = {rows + 1, V}.  out may be NULL (dimensions only). */
+int dmsa_b200_get_batch_tables(dmsa_b200_ctx* ctx, float* out, int32_t* dims);
 /* denseGlobalPoses of the current parameters (ContinuousTrajectory.h:29, 194-218): orientations (axis-angle) and
  * translations, 3 x n_total column-major doubles each (either may be NULL) */
 int dmsa_b200_traj_get_dense_poses(dmsa_b200_ctx* ctx, double* orient, double* transl);
@@ -249,8 +253,10 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
  * Both run the same operation sequence (LU with partial pivoting, explicit inverse, ascending accumulation): bit-identical. */
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode);
 /* Cost kernels of the forward-difference batch (V = P + 1 vectors): 1 (default) = two vectors per thread with Blackwell's
- * packed FP32x2 instructions (FMUL2 / FADD2; every multiply->add edge keeps a scalar side, so nothing is fused), 0 = one
- * vector per thread.  Same rounding sequence per value: bit-identical results. */
+ * packed FP32x2 instructions (FMUL2 / FADD2; every multiply->add edge keeps a scalar side, so nothing is fused) and the
+ * shared-rotation fast path (the vectors that perturb a translation parameter reuse vector 0's rotated member coordinates:
+ * their table rows carry the same rotation bits), 2 = pair-packed, every vector evaluated in full, 0 = one vector per
+ * thread.  Same rounding sequence per value: bit-identical results in all three modes. */
 int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode);
 /* The device LM step on a HOST copy of [H | g | err0] (n_params <= 1024); validation twin of dmsa_b200_lm_solve(.., 1, ..). */
 int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step,

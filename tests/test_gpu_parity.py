@@ -561,7 +561,7 @@ def test_pair_packed_cost_kernels_equal_the_scalar_kernels_bitwise(name):
     no fused multiply-add: every multiply->add edge keeps a scalar side).  Same rounding sequence per value as the
     one-vector-per-thread kernels: e0, J, H, g and whole iterations are bit-identical."""
     res = []
-    for mode in (1, 0):
+    for mode in (1, 2, 0):  # pair-packed + shared-rotation fast path (default), pair-packed in full, scalar
         win, traj, om, s, so = make_pair(name)
         traj.setPairMode(mode)
         traj.centralize()
@@ -574,14 +574,41 @@ def test_pair_packed_cost_kernels_equal_the_scalar_kernels_bitwise(name):
         e = traj.evalCost(batch)
         it = [traj.iteration(s) for _ in range(2)]
         res.append((cj, e, it, traj.getPoseParameters()))
-    a, b = res
-    for k in ("e0", "J", "H", "g"):
-        assert np.array_equal(a[0][k], b[0][k]), k
-    assert np.array_equal(a[1], b[1])
-    for x, y in zip(a[2], b[2]):
-        assert x["error0"] == y["error0"] and x["best_step"] == y["best_step"]
-        assert np.array_equal(x["step"], y["step"]) and np.array_equal(x["ls_cost"], y["ls_cost"])
-    assert np.array_equal(a[3], b[3])
+    for a, b in ((res[0], res[2]), (res[1], res[2])):
+        for k in ("e0", "J", "H", "g"):
+            assert np.array_equal(a[0][k], b[0][k]), k
+        assert np.array_equal(a[1], b[1])
+        for x, y in zip(a[2], b[2]):
+            assert x["error0"] == y["error0"] and x["best_step"] == y["best_step"]
+            assert np.array_equal(x["step"], y["step"]) and np.array_equal(x["ls_cost"], y["ls_cost"])
+        assert np.array_equal(a[3], b[3])
+
+
+@pytest.mark.parametrize("model", ["trajectory", "keyframes"])
+def test_translation_vectors_share_the_base_rotation_bitwise(model):
+    """Premise of the shared-rotation fast path of the pair kernels (kernels_cost.cuh): in the forward-difference batch the
+    vectors p + h e_k with k >= 3 (n - 1) perturb a translation parameter (Poses.h:64-76), and every row of their transform
+    table carries the very rotation bits of vector 0 (the base pose), while the translation column differs somewhere."""
+    if model == "trajectory":
+        win, obj, om, s, so = make_pair("cfg1")
+        obj.centralize()
+    else:
+        sm = synth.make_keyframe_submap(n_keyframes=6, n_points=3000, seed=3)
+        obj = MapManagement.from_submap(sm)
+        s = DmsaOptimSettings(num_iter=1, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=6, min_num_gaussians=10, gauss_split=0, epsilon=1e-4)
+    obj.updateGlobalPoints()
+    obj.buildSets(s)
+    obj.costJacobian()
+    T = obj.batchTables()  # (rows + 1, V, 12)
+    P = obj.numParams
+    assert T.shape[1] == P + 1
+    rot = [0, 1, 2, 4, 5, 6, 8, 9, 10]
+    vT = 1 + P // 2
+    bits = T.view(np.uint32)
+    assert np.array_equal(bits[:, vT:, :][:, :, rot], np.broadcast_to(bits[:, :1, :][:, :, rot], bits[:, vT:, :][:, :, rot].shape))
+    assert not np.array_equal(bits[:, vT:, :][:, :, [3, 7, 11]], np.broadcast_to(bits[:, :1, :][:, :, [3, 7, 11]], bits[:, vT:, :][:, :, [3, 7, 11]].shape))
+    # ... and the rotation vectors do differ from the base (the fast path must not cover them)
+    assert all((bits[:, v, :][:, rot] != bits[:, 0, :][:, rot]).any() for v in range(1, vT))
 
 
 def test_many_poses_wide_batch_pair_kernels_and_fma_jtj():
@@ -592,17 +619,17 @@ def test_many_poses_wide_batch_pair_kernels_and_fma_jtj():
     st = dict(num_iter=1, step_length_optim=0.2, max_step=0.3, min_num_points_per_set=10, min_num_gaussians=30)
     s, so = DmsaOptimSettings(**st), ob.settings(**st)
     out = []
-    for mode in (1, 0):
+    for mode in (1, 2, 0):
         traj = ContinuousTrajectory.from_window(win)
         traj.setPairMode(mode)
         traj.centralize()
         traj.updateGlobalPoints()
         G, _ = traj.buildSets(s)
         out.append((traj.costJacobian(with_rows=True), G))
-    (a, Ga), (b, Gb) = out
-    assert Ga == Gb and a["J"].shape[1] == 138
+    (a, Ga), (c, Gc), (b, Gb) = out
+    assert Ga == Gb == Gc and a["J"].shape[1] == 138
     for k in ("e0", "J", "H", "g"):
-        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(a[k], b[k]) and np.array_equal(c[k], b[k]), k
     om = ob.OracleModel.from_window(win)
     om.set_threads(os.cpu_count() or 8)
     om.set_mode(2)
