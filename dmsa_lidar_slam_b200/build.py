@@ -9,13 +9,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "dmsa_b200.cu")
 HOST_SRC = os.path.join(_HERE, "csrc", "host_solve.cpp")
 HOST_OBJ = os.path.join(_HERE, "lib", "host_solve.o")
-DEPS = [os.path.join(_HERE, "csrc", f) for f in ("host_solve.cpp", "dmsa_b200.cu", "kernels_cost.cuh", "kernels_pose.cuh", "kernels_sets.cuh", "kernels_solve.cuh", "kernels_knn.cuh", "se3_math.cuh")] + [
+DEPS = [os.path.join(_HERE, "csrc", f) for f in ("host_solve.cpp", "dmsa_b200.cu", "kernels_cost.cuh", "kernels_pose.cuh", "kernels_sets.cuh", "kernels_solve.cuh", "kernels_sort.cuh", "kernels_chol.cuh", "kernels_knn.cuh", "se3_math.cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", "dmsa_b200.h")]
 OUT = os.path.join(_HERE, "lib", "libdmsa_b200.so")
 
 # -fmad=false: the reference's float arithmetic has no FMA contraction (CMakeLists.txt:13-17, baseline x86-64);
 # the kernels use explicit fma() where fusion is wanted (J^T J) and explicit *_rn intrinsics on the parity-critical path.
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-shared",
+NVCC_FLAGS = (["-DDMSA_TIMELINE=" + os.environ["DMSA_TIMELINE"]] if os.environ.get("DMSA_TIMELINE") else []) + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC", "-shared",
               # host side (LM solve): AVX2 vector loops, still no FMA contraction so results equal the scalar sequence
               "-Xcompiler", "-O3,-mavx2,-ffp-contract=off"]
 

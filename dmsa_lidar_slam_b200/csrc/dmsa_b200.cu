@@ -23,6 +23,7 @@
 #include "kernels_knn.cuh"
 #include "kernels_pose.cuh"
 #include "kernels_sets.cuh"
+#include "kernels_sort.cuh"
 #include "nccl_dyn.h"
 #include "se3_math.cuh"
 
@@ -194,6 +195,8 @@ struct dmsa_b200_ctx {
     DBuf<int> d_split_search, d_split_nbox;
     DBuf<unsigned long long> d_code, d_scode;
     DBuf<unsigned char> d_cub;
+    DBuf<unsigned char> d_ctl;  // tickets, digit histograms and look-back status words of the hand-written sort / scans (zeroed per build)
+    bool sortAttr = false;
     DBuf<float4> d_rec, d_wrec;
     DBuf<int> d_cell_start, d_cell_n, d_cell_level, d_cell_key, d_cell_sub, d_cell_kind, d_nchunk, d_chunk_off, d_okey, d_oval;
     DBuf<float> d_cell_info, d_cell_w0, d_cell_w;
@@ -332,6 +335,7 @@ __global__ void k_unpack_psi(const unsigned char* __restrict__ raw, int n, int o
     const double stamp = *reinterpret_cast<const double*>(raw + 32 * (size_t)i + 16);
     const int id = *reinterpret_cast<const int*>(raw + 32 * (size_t)i + 24);
     if (p.w != 1.0f) atomicOr(flag, 1);
+    if ((unsigned)id > 65535u) atomicOr(flag + 1, 1);  // sticky: the set build then takes its ring ids by gather (kernels_sort.cuh ring_packed)
     const int o = out_off + i;
     local[o] = p;
     ring[o] = id;
@@ -364,6 +368,7 @@ __global__ void k_unpack_pn(const unsigned char* __restrict__ raw, const int* __
     local[o] = p;
     normal[o] = r[1];
     ring[o] = rings[i];
+    if ((unsigned)rings[i] > 65535u) atomicOr(flag + 1, 1);
     tid[o] = kf;
 }
 
@@ -561,6 +566,49 @@ int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
     return 0;
 }
 
+// control block of the hand-written sort / chained scans of one set build (kernels_sort.cuh); one memset zeroes all of it
+struct CtlLayout {
+    size_t tickets = 0, gbready = 0, hist = 0, look = 0, segStatus = 0, emitStatus = 0, scanStatus[3] = {0, 0, 0}, bytes = 0;
+    int tilesSort = 0, tilesScan = 0;
+    static size_t al(size_t x) { return (x + 15) / 16 * 16; }
+    CtlLayout(int N, int npass, int cells) {
+        tilesSort = (N + RS_TILE - 1) / RS_TILE;
+        tilesScan = (std::max(N, cells) + 1 + CS_TILE - 1) / CS_TILE;
+        const int tilesEmit = (N + EM_TILE - 1) / EM_TILE + 1;
+        size_t o = 0;
+        tickets = o;  // 16 ints: [0, 8) sort passes, 8 segment, 9 emit, 10..12 scans
+        o = al(o + 16 * sizeof(int));
+        gbready = o;
+        o = al(o + RS_MAXSEG * sizeof(int));
+        hist = o;
+        o = al(o + (size_t)RS_MAXSEG * RS_MAXPASS * RS_BINS * sizeof(u32_t));
+        look = o;
+        o = al(o + (size_t)npass * RS_MAXSEG * tilesSort * RS_BINS * sizeof(u32_t));
+        segStatus = o;
+        o = al(o + (size_t)RS_MAXSEG * tilesScan * sizeof(u64_t));
+        emitStatus = o;
+        o = al(o + (size_t)RS_MAXSEG * tilesEmit * sizeof(u64_t));
+        for (int k = 0; k < 3; ++k) {
+            scanStatus[k] = o;
+            o = al(o + (size_t)tilesScan * sizeof(u64_t));
+        }
+        bytes = o;
+    }
+};
+// out[i] = in[0] + .. + in[i - 1], i < n (single-pass chained scan; slot selects the ticket / status area of the control block)
+int scanExclusive(dmsa_b200_ctx* ctx, cudaStream_t strm, const CtlLayout& cl, int slot, const int* in, int* out, int n) {
+    ScanArgs sa;
+    sa.in = in;
+    sa.out = out;
+    sa.n = n;
+    sa.tiles = (n + CS_TILE - 1) / CS_TILE;
+    sa.status = reinterpret_cast<u64_t*>(ctx->d_ctl.p + cl.scanStatus[slot]);
+    sa.ticket = reinterpret_cast<int*>(ctx->d_ctl.p + cl.tickets) + 10 + slot;
+    if (sa.tiles > cl.tilesScan) ARGFAIL("scanExclusive: more tiles than the control block was sized for");
+    LAUNCH_ON(strm, k_scan_excl, sa.tiles, CS_T, 0, sa);
+    return 0;
+}
+
 // reset + both createGaussianSets + updateRebalancingWeights + work decomposition   DmsaOptimizer.h:78-96
 // defer = true (inside an iteration, when a previous build gives a grid-size guess): no host synchronisation at all; the
 // set count stays on the device (LevelInfo::G), the kernels behind the build read it there, and the caller verifies the
@@ -620,7 +668,6 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
     CK(ctx->d_nchunk.ensure((size_t)cap + 1));
     CK(ctx->d_chunk_off.ensure((size_t)cap + 1));
     CK(ctx->d_done.ensure(4 * ((size_t)cap + 1)));
-    CKRC(ensureCub(ctx, N, cap));
     CellStore cs;
     cs.start = ctx->d_cell_start.p;
     cs.n = ctx->d_cell_n.p;
@@ -659,8 +706,7 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
     // The radix sort needs the number of key bits (3 * octree depth + 1) on the host.  The depth of the previous build of
     // this context is a safe guess (more bits than needed are harmless); it is verified after phase 2 and the phase is
     // redone in the rare case the tree grew.  Without a guess: one synchronisation here.
-    size_t cubBytes = ctx->cubPer;
-    int prev = -1;
+
     int depthUsed[2] = {ctx->cachedDepth[0], ctx->cachedDepth[1]};
     bool haveGuess = true;
     for (int l = 0; l < 2; ++l)
@@ -677,77 +723,147 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
         }
     }
 phase2:
-    // phase 2: sort, segment, accept, gather.  The two levels are independent up to the set numbering (level 1's sets
-    // follow level 0's): level 0 runs on the context's stream, level 1 on stream2; level 1's emission waits for level 0's.
-    prev = -1;
+    // phase 2: sort, segment, accept, emit, gather — both resolution levels in the SAME launches (kernels_sort.cuh): one
+    // Morton + histogram kernel, one kernel per 8-bit digit, one chained scan for run heads / leaf starts / ring test, one for
+    // acceptance / set numbering / emission (level 1's sets follow level 0's: one scan chain over both levels), one gather.
+
+    int npass = 1;
+    for (int l = 0; l < 2; ++l)
+        if (ctx->levelOn[l]) npass = std::max(npass, (std::min(64, 3 * depthUsed[l] + 1) + 7) / 8);
+    const CtlLayout cl(N, npass, cap);
+    CK(ctx->d_ctl.ensure(cl.bytes));
     {
     ProfScope prof_(ctx, PROF_SETS_SORT);
-    const bool fork = ctx->levelOn[0] && ctx->levelOn[1];
-    if (fork) {
-        CK(cudaEventRecord(ctx->evFork, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->stream2, ctx->evFork, 0));
+    cudaStream_t strm = ctx->stream;
+    if (!ctx->sortAttr) {
+        CK(cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+        ctx->sortAttr = true;
     }
+    CK(cudaMemsetAsync(ctx->d_ctl.p, 0, cl.bytes, strm));
+    CK(cudaMemsetAsync(ctx->d_raw_diff.p, 0, 2 * N2 * sizeof(int), strm));
+    SortArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    PrepArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    SegmentArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    EmitArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    GatherArgs gt;
+    memset(&gt, 0, sizeof(gt));
+    int nseg = 0;
+    // pass p reads A / writes B for even p: the buffers are assigned so that the last pass always lands in d_scode / d_sidx
+    const bool odd = (npass & 1) != 0;
     for (int l = 0; l < 2; ++l) {
         if (!ctx->levelOn[l]) continue;
-        cudaStream_t strm = (fork && l == 1) ? ctx->stream2 : ctx->stream;
-        LevelInfo* li = ctx->d_linfo.p + l;
-        int* keys = ctx->d_keys.p + (size_t)3 * N * l;
-        int* sidx = ctx->d_sidx.p + (size_t)N * l;
-        unsigned long long* code = ctx->d_code.p + (size_t)N * l;
-        unsigned long long* scode = ctx->d_scode.p + (size_t)N * l;
-        int* idx = ctx->d_idx.p + (size_t)N * l;
-        int* flagA = ctx->d_flagA.p + (size_t)N * l;
-        int* scanA = ctx->d_scanA.p + (size_t)N * l;
-        int* raw_start = ctx->d_raw_start.p + N2 * l;
-        int* raw_diff = ctx->d_raw_diff.p + N2 * l;
-        int* acc_flag = ctx->d_acc_flag.p + N2 * l;
-        int* acc_scan = ctx->d_acc_scan.p + N2 * l;
-        int* out_cnt = ctx->d_out_cnt.p + N2 * l;
-        unsigned char* cubTmp = ctx->d_cub.p + ctx->cubPer * l;
-        LAUNCH_ON(strm, k_morton, cdiv(N, 256), 256, 0, keys, N, li, code, idx);
-        const int end_bit = std::min(64, 3 * depthUsed[l] + 1);
-        CK(cub::DeviceRadixSort::SortPairs(cubTmp, cubBytes, code, scode, idx, sidx, N, 0, end_bit, strm));
-        LAUNCH_ON(strm, k_heads, cdiv(N, 256), 256, 0, scode, N, li, flagA);
-        CK(cub::DeviceScan::InclusiveSum(cubTmp, cubBytes, flagA, scanA, N, strm));
-        CK(cudaMemsetAsync(raw_diff, 0, N2 * sizeof(int), strm));
-        LAUNCH_ON(strm, k_raw_starts, cdiv(N, 256), 256, 0, scode, flagA, scanA, N, li, raw_start);
-        LAUNCH_ON(strm, k_ring_diff, cdiv(N, 256), 256, 0, sidx, scanA, raw_start, ctx->d_ring.p, li, raw_diff);
-        int* sub_start = ctx->d_sub.p + 6 * N2 * l;
-        int* sub_n = sub_start + 2 * N2;
-        int* sub_code = sub_n + 2 * N2;
-        LAUNCH_ON(strm, k_accept, cdiv(N, 256), 256, 0, raw_start, raw_diff, li, minPts, acc_flag, out_cnt, sub_start, sub_n, sub_code);
-        if (split) {  // Gaussians.h:27-85 on every accepted leaf
-            int* ntile = ctx->d_ntile.p + N2 * l;
-            int* tile_off = ctx->d_tile_off.p + N2 * l;
-            SplitTile* tiles = ctx->d_tiles.p + tileBound * l;
-            float* best_v = ctx->d_best_v.p + tileBound * l;
-            int* best_i = ctx->d_best_ij.p + 2 * tileBound * l;
-            int* best_j = best_i + tileBound;
-            int* scratch = ctx->d_scratch.p + (size_t)N * l;
-            int* nbox = ctx->d_split_nbox.p + 6 * N2 * l;
-            int* search = ctx->d_split_search.p + N2 * l;
-            LAUNCH_ON(strm, k_split_nbox_init, cdiv(N2, 256), 256, 0, nbox, search, (int)N2);
-            LAUNCH_ON(strm, k_split_nbox, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox);
-            LAUNCH_ON(strm, k_split_prefilter, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox, search);
-            LAUNCH_ON(strm, k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, raw_start, acc_flag, search, li, ntile);
-            CK(cub::DeviceScan::ExclusiveSum(cubTmp, cubBytes, ntile, tile_off, N + 1, strm));
-            LAUNCH_ON(strm, k_split_tile_fill, cdiv(N, 256), 256, 0, ntile, tile_off, li, tiles);
-            LAUNCH_ON(strm, k_split_pairs, (unsigned)tileBound, 256, 0, tiles, tile_off, li, raw_start, sidx, ctx->d_normal_w.p, best_v, best_i, best_j);
-            LAUNCH_ON(strm, k_split_decide, 148 * 8, 256, 0, acc_flag, ntile, tile_off, li, raw_start, sidx, scratch, ctx->d_normal_w.p, ctx->d_ring.p, best_v,
-                      best_i, best_j, minPts, out_cnt, sub_start, sub_n, sub_code);
-        }
-        CK(cub::DeviceScan::ExclusiveSum(cubTmp, cubBytes, out_cnt, acc_scan, N, strm));
-        if (fork && l == 1) CK(cudaStreamWaitEvent(strm, ctx->evLevel0, 0));  // gbase of level 1 = sets emitted by level 0
-        LAUNCH_ON(strm, k_emit_cells, cdiv(N, 256), 256, 0, raw_start, out_cnt, acc_scan, sub_start, sub_n, sub_code, sidx, keys, li,
-                  prev >= 0 ? ctx->d_linfo.p + prev : nullptr, l, l * N, cs, cap);
-        if (fork && l == 0) CK(cudaEventRecord(ctx->evLevel0, strm));
-        LAUNCH_ON(strm, k_gather, cdiv(N, 256), 256, 0, sidx, li, ctx->d_local.p, ctx->d_tid.p, numTableRows(ctx), ctx->d_world.p,
-                  ctx->d_rec.p + (size_t)N * l, ctx->d_wrec.p + (size_t)N * l);
-        prev = l;
+        const int s_ = nseg++;
+        u64_t* const code0 = ctx->d_code.p + (size_t)N * l;
+        u64_t* const code1 = ctx->d_scode.p + (size_t)N * l;
+        u32_t* const idx0 = reinterpret_cast<u32_t*>(ctx->d_idx.p + (size_t)N * l);
+        u32_t* const idx1 = reinterpret_cast<u32_t*>(ctx->d_sidx.p + (size_t)N * l);
+        sa.seg[s_].keyA = odd ? code0 : code1;
+        sa.seg[s_].keyB = odd ? code1 : code0;
+        sa.seg[s_].valA = odd ? idx0 : idx1;
+        sa.seg[s_].valB = odd ? idx1 : idx0;
+        pa.level[s_] = l;
+        const u64_t* scode = code1;
+        u32_t* sidx = idx1;
+        ga.code[s_] = scode;
+        ga.idx[s_] = sidx;
+        ga.scan[s_] = ctx->d_scanA.p + (size_t)N * l;
+        ga.raw_start[s_] = ctx->d_raw_start.p + N2 * l;
+        ga.raw_diff[s_] = ctx->d_raw_diff.p + N2 * l;
+        ga.level[s_] = l;
+        ea.raw_start[s_] = ga.raw_start[s_];
+        ea.raw_diff[s_] = ga.raw_diff[s_];
+        ea.out_cnt[s_] = ctx->d_out_cnt.p + N2 * l;
+        ea.sub_start[s_] = ctx->d_sub.p + 6 * N2 * l;
+        ea.sub_n[s_] = ea.sub_start[s_] + 2 * N2;
+        ea.sub_code[s_] = ea.sub_n[s_] + 2 * N2;
+        ea.idx[s_] = sidx;
+        ea.keys[s_] = ctx->d_keys.p + (size_t)3 * N * l;
+        ea.mbase[s_] = l * N;
+        ea.level[s_] = l;
+        gt.idx[s_] = sidx;
+        gt.rec[s_] = ctx->d_rec.p + (size_t)N * l;
+        gt.wrec[s_] = ctx->d_wrec.p + (size_t)N * l;
+        gt.level[s_] = l;
     }
-    if (fork) {
-        CK(cudaEventRecord(ctx->evJoin, ctx->stream2));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+    if (nseg > 0) {
+        sa.nseg = nseg;
+        sa.n = N;
+        sa.tiles = cl.tilesSort;
+        sa.npass = npass;
+        sa.iota = 1;
+        sa.hist = reinterpret_cast<u32_t*>(ctx->d_ctl.p + cl.hist);
+        sa.look = reinterpret_cast<u32_t*>(ctx->d_ctl.p + cl.look);
+        sa.ticket = reinterpret_cast<int*>(ctx->d_ctl.p + cl.tickets);
+        pa.keys_all = ctx->d_keys.p;
+        pa.infos = ctx->d_linfo.p;
+        pa.ring = ctx->d_ring.p;
+        pa.flags = ctx->d_flag.p;
+        LAUNCH_ON(strm, k_sort_prepare, dim3(cl.tilesSort, nseg), RS_T, 0, sa, pa);
+        for (int p_ = 0; p_ < npass; ++p_) {
+            sa.pass = p_;
+            LAUNCH_ON(strm, k_sort_pass, cl.tilesSort * nseg, RS_T, RS_SMEM, sa);
+        }
+        const int tilesSeg = (N + SG_TILE - 1) / SG_TILE, tilesEmit = (N + EM_TILE - 1) / EM_TILE;
+        ga.infos = ctx->d_linfo.p;
+        ga.ring = ctx->d_ring.p;
+        ga.flags = ctx->d_flag.p;
+        ga.n = N;
+        ga.tiles = tilesSeg;
+        ga.status = reinterpret_cast<u64_t*>(ctx->d_ctl.p + cl.segStatus);
+        ga.ticket = reinterpret_cast<int*>(ctx->d_ctl.p + cl.tickets) + 8;
+        LAUNCH_ON(strm, k_segment, tilesSeg * nseg, SG_T, 0, ga);
+        ea.infos = ctx->d_linfo.p;
+        ea.nseg = nseg;
+        ea.n = N;
+        ea.tiles = tilesEmit;
+        ea.minPts = minPts;
+        ea.cap = cap;
+        ea.cs = cs;
+        ea.status = reinterpret_cast<u64_t*>(ctx->d_ctl.p + cl.emitStatus);
+        ea.ticket = reinterpret_cast<int*>(ctx->d_ctl.p + cl.tickets) + 9;
+        ea.gbase_ready = reinterpret_cast<int*>(ctx->d_ctl.p + cl.gbready);
+        if (split) {  // Gaussians.h:27-85 on every accepted leaf, then emission from the plan
+            for (int s_ = 0; s_ < nseg; ++s_) {
+                const int l = ea.level[s_];
+                LevelInfo* li = ctx->d_linfo.p + l;
+                int* sidx = reinterpret_cast<int*>(const_cast<u32_t*>(ea.idx[s_]));
+                int* scanA = ga.scan[s_];
+                int* raw_start = ga.raw_start[s_];
+                int* acc_flag = ctx->d_acc_flag.p + N2 * l;
+                int* out_cnt = ctx->d_out_cnt.p + N2 * l;
+                int* sub_start = ctx->d_sub.p + 6 * N2 * l;
+                int* sub_n = sub_start + 2 * N2;
+                int* sub_code = sub_n + 2 * N2;
+                int* ntile = ctx->d_ntile.p + N2 * l;
+                int* tile_off = ctx->d_tile_off.p + N2 * l;
+                SplitTile* tiles = ctx->d_tiles.p + tileBound * l;
+                float* best_v = ctx->d_best_v.p + tileBound * l;
+                int* best_i = ctx->d_best_ij.p + 2 * tileBound * l;
+                int* best_j = best_i + tileBound;
+                int* scratch = ctx->d_scratch.p + (size_t)N * l;
+                int* nbox = ctx->d_split_nbox.p + 6 * N2 * l;
+                int* search = ctx->d_split_search.p + N2 * l;
+                LAUNCH_ON(strm, k_accept, cdiv(N, 256), 256, 0, raw_start, ga.raw_diff[s_], li, minPts, acc_flag, out_cnt, sub_start, sub_n, sub_code);
+                LAUNCH_ON(strm, k_split_nbox_init, cdiv(N2, 256), 256, 0, nbox, search, (int)N2);
+                LAUNCH_ON(strm, k_split_nbox, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox);
+                LAUNCH_ON(strm, k_split_prefilter, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox, search);
+                LAUNCH_ON(strm, k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, raw_start, acc_flag, search, li, ntile);
+                CKRC(scanExclusive(ctx, strm, cl, 1 + s_, ntile, tile_off, N + 1));
+                LAUNCH_ON(strm, k_split_tile_fill, cdiv(N, 256), 256, 0, ntile, tile_off, li, tiles);
+                LAUNCH_ON(strm, k_split_pairs, (unsigned)tileBound, 256, 0, tiles, tile_off, li, raw_start, sidx, ctx->d_normal_w.p, best_v, best_i, best_j);
+                LAUNCH_ON(strm, k_split_decide, 148 * 8, 256, 0, acc_flag, ntile, tile_off, li, raw_start, sidx, scratch, ctx->d_normal_w.p, ctx->d_ring.p, best_v,
+                          best_i, best_j, minPts, out_cnt, sub_start, sub_n, sub_code);
+            }
+            LAUNCH_ON(strm, k_emit<true>, std::min(tilesEmit * nseg, 148 * 4), EM_T, 0, ea);
+        } else {
+            LAUNCH_ON(strm, k_emit<false>, std::min(tilesEmit * nseg, 148 * 4), EM_T, 0, ea);
+        }
+        gt.infos = ctx->d_linfo.p;
+        LAUNCH_ON(strm, k_gather2, dim3(cdiv(N, 256), nseg), 256, 0, gt, ctx->d_local.p, ctx->d_tid.p, numTableRows(ctx), ctx->d_world.p);
     }
     }
     int Gb = 0;
@@ -770,7 +886,6 @@ phase2:
             ctx->cachedDepth[l] = ctx->h_linfo[l].depth;
         }
         if (redo) {
-            prev = -1;
             goto phase2;
         }
     }
@@ -815,7 +930,7 @@ phase2:
         CK(cudaMemsetAsync(ctx->d_nchunk.p, 0, ((size_t)Gb + 1) * sizeof(int), ctx->stream));  // entries behind the last set stay 0
         LAUNCH(k_cell_plan, cdiv(Gb, 256), 256, 0, cs, li, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
         LAUNCH(k_cell_order, cdiv(Gb, 256), 256, 0, li, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
-        CK(cub::DeviceScan::ExclusiveSum(ctx->d_cub.p, cubBytes, ctx->d_nchunk.p, ctx->d_chunk_off.p, Gb + 1, ctx->stream));  // [Gb] = total
+        CKRC(scanExclusive(ctx, ctx->stream, cl, 0, ctx->d_nchunk.p, ctx->d_chunk_off.p, Gb + 1));  // [Gb] = total
         LAUNCH(k_chunk_fill, cdiv(Gb, 256), 256, 0, cs, li, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);
         CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
         LAUNCH(k_gaussian_fin, cdiv(Gb, 128), 128, 0, cs, li, ctx->d_mom.p);
@@ -1289,6 +1404,9 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
 // ============================================================================================
 extern "C" {
 
+#ifdef DMSA_TIMELINE
+int dmsa_b200_dbg_times(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, g_dbg_t, 16384 * 8); }
+#endif
 int dmsa_b200_version(void) { return 101; }
 int32_t dmsa_b200_fuse_threshold(void) { return FUSE_MAX; }
 
@@ -1341,7 +1459,7 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
     REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_dense); REL(d_Mtab); REL(d_Mpair);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
-    REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_split_nbox); REL(d_split_search); REL(d_code); REL(d_scode); REL(d_cub); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
+    REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_split_nbox); REL(d_split_search); REL(d_code); REL(d_scode); REL(d_cub); REL(d_ctl); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
     REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_gkeys); REL(d_gskeys); REL(d_gidx); REL(d_gsidx); REL(d_gcount); REL(d_gpts); REL(d_gquery); REL(d_gsel); REL(d_mom); REL(d_solve); REL(d_iter); REL(d_chol);
 #undef REL
