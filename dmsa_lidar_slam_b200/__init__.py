@@ -5,4 +5,4 @@ Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C-ABI of in
 (deterministic synthetic windows of the BASELINE shapes) and `build.py` (in-tree nvcc build).
 """
 from .api import (ContinuousTrajectory, DmsaError, DmsaOptimizer, DmsaOptimSettings, MapManagement,  # noqa: F401
-                  OptimizablePointSet, load_library)
+                  OptimizablePointSet, PreProcessor, PreprocessConfig, load_library, rand_sequence)

@@ -58,6 +58,16 @@ class Report(C.Structure):
         return d
 
 
+class PreprocessConfig(C.Structure):
+    """The fields of Config (Config.h:24-58) that preProcess reads (DmsaSlam.h:570-634); defaults are the reference's."""
+
+    _fields_ = [("max_num_points_per_scan", C.c_int32), ("min_dist_ds", C.c_float), ("min_dist", C.c_float), ("lidar_to_imu", C.c_float * 16)]
+
+    def __init__(self, max_num_points_per_scan=3000, minDistDS=30.0, min_dist=0.0, lidarToImuTform=None):
+        T = np.eye(4, dtype=np.float32) if lidarToImuTform is None else np.asarray(lidarToImuTform, dtype=np.float32).reshape(4, 4)
+        super().__init__(int(max_num_points_per_scan), float(minDistDS), float(min_dist), (C.c_float * 16)(*T.T.ravel()))  # column-major
+
+
 _lib = None
 
 
@@ -133,6 +143,11 @@ def load_library():
         "dmsa_b200_set_lm_solver": (i32, [vp, i32]),
         "dmsa_b200_set_pair_mode": (i32, [vp, i32]),
         "dmsa_b200_get_batch_tables": (i32, [vp, vp, vp]),
+        "dmsa_b200_rand_sequence": (i32, [C.c_uint32, i64, vp]),
+        "dmsa_b200_grid_downsample": (i32, [vp, vp, i64, i32, C.c_float, C.c_uint32, vp, P(i64)]),
+        "dmsa_b200_downsample_global_points": (i32, [vp, C.c_float, C.c_uint32, vp, P(i64)]),
+        "dmsa_b200_preprocess_scan": (i32, [vp, vp, i64, P(PreprocessConfig), C.c_uint32, vp, P(i64), P(C.c_float)]),
+        "dmsa_b200_estimate_normals": (i32, [vp, vp, i64, vp, C.c_float, vp]),
         "dmsa_b200_select_static_points": (i32, [vp, vp, i64, vp, C.c_float, vp, P(i64)]),
         "dmsa_b200_overlap": (i32, [vp, vp, i64, C.c_float, P(C.c_float)]),
         "dmsa_b200_lm_solve_device": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
@@ -157,6 +172,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode", "dmsa_b200_get_batch_tables",
+    "dmsa_b200_rand_sequence", "dmsa_b200_grid_downsample", "dmsa_b200_downsample_global_points", "dmsa_b200_preprocess_scan", "dmsa_b200_estimate_normals",
     "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
     "dmsa_b200_spd_solve_dev", "dmsa_b200_spd_solve", "dmsa_b200_bundle_jacobian", "dmsa_b200_bundle_line_search", "dmsa_b200_bundle_verify",
     "dmsa_b200_all_reduce", "dmsa_b200_comm_unique_id", "dmsa_b200_comm_init", "dmsa_b200_comm_destroy", "dmsa_b200_collective_count",
@@ -588,3 +604,47 @@ def lm_solve(settings, hg, n_params, explicit_inverse=True):
     if rc != 0:
         raise DmsaError(f"dmsa_b200_lm_solve failed ({rc})")
     return step, bool(nan.value)
+
+
+# ---- pre-processing and normal estimation (helpers.h:67-182, DmsaSlam.h:557-634) ----------------------
+def rand_sequence(seed, n):
+    """The first n values of rand() after srand(seed) (glibc), as the library generates them."""
+    L = load_library()
+    out = np.zeros(int(n), dtype=np.int32)
+    rc = L.dmsa_b200_rand_sequence(int(seed) & 0xFFFFFFFF, int(n), _p(out))
+    if rc:
+        raise DmsaError("rand_sequence failed")
+    return out
+
+
+class PreProcessor:
+    """randomGridDownsampling / preProcess / updateNormals of DmsaSlam on the device (own context unless one is passed)."""
+
+    def __init__(self, ctx=None, device=0, stream=None):
+        self.ctx = ctx if ctx is not None else _Context(device, stream)
+        self.L, self.h = self.ctx.L, self.ctx.h
+
+    def randomGridDownsampling(self, cloud, gridSize, seed):
+        """cloud: structured array (PointStampId or pcl::PointNormal layout) -> (filtered cloud, picked indices)."""
+        cloud = np.ascontiguousarray(cloud)
+        idx = np.zeros(len(cloud), dtype=np.int32)
+        n_out = C.c_int64(0)
+        self.ctx._ck(self.L.dmsa_b200_grid_downsample(self.h, _p(cloud), len(cloud), cloud.dtype.itemsize, float(gridSize), int(seed) & 0xFFFFFFFF, _p(idx), C.byref(n_out)))
+        idx = idx[: n_out.value]
+        return cloud[idx], idx
+
+    def preProcess(self, rawPc, config: PreprocessConfig, seed):
+        """-> (filteredPc as PointStampId array, gridSize)."""
+        rawPc = np.ascontiguousarray(rawPc, dtype=POINT_STAMP_ID)
+        out = np.zeros(len(rawPc), dtype=POINT_STAMP_ID)
+        n_out, gs = C.c_int64(0), C.c_float(0.0)
+        self.ctx._ck(self.L.dmsa_b200_preprocess_scan(self.h, _p(rawPc), len(rawPc), C.byref(config), int(seed) & 0xFFFFFFFF, _p(out), C.byref(n_out), C.byref(gs)))
+        return out[: n_out.value], float(gs.value)
+
+    def updateNormals(self, cloud, origin=(0.0, 0.0, 0.0), cell_size=0.3, with_neighbours=False):
+        """cloud: pcl::PointNormal structured array; returns the cloud with normals / curvature (and the n x 6 neighbour indices)."""
+        cloud = np.ascontiguousarray(cloud, dtype=POINT_NORMAL).copy()
+        vp = np.asarray(origin, dtype=np.float32)
+        nn = np.zeros((len(cloud), 6), dtype=np.int32) if with_neighbours else None
+        self.ctx._ck(self.L.dmsa_b200_estimate_normals(self.h, _p(cloud), len(cloud), _p(vp), float(cell_size), _p(nn) if with_neighbours else None))
+        return (cloud, nn) if with_neighbours else cloud

@@ -11,7 +11,6 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <cub/cub.cuh>
 #include <limits>
 #include <string>
 #include <vector>
@@ -22,6 +21,7 @@
 #include "kernels_solve.cuh"
 #include "kernels_knn.cuh"
 #include "kernels_pose.cuh"
+#include "kernels_pre.cuh"
 #include "kernels_sets.cuh"
 #include "kernels_sort.cuh"
 #include "nccl_dyn.h"
@@ -194,7 +194,6 @@ struct dmsa_b200_ctx {
     DBuf<float> d_best_v;
     DBuf<int> d_split_search, d_split_nbox;
     DBuf<unsigned long long> d_code, d_scode;
-    DBuf<unsigned char> d_cub;
     DBuf<unsigned char> d_ctl;  // tickets, digit histograms and look-back status words of the hand-written sort / scans (zeroed per build)
     bool sortAttr = false;
     DBuf<float4> d_rec, d_wrec;
@@ -208,15 +207,25 @@ struct dmsa_b200_ctx {
     bool levelOn[2] = {false, false};
     int cachedDepth[2] = {0, 0};
     int cellCap = 0;
-    size_t cubPer = 0;  // bytes of CUB temporary storage per resolution level
 
     // cost
     DBuf<double> d_mom;  // centred second moments of every set [g][6]
     // uniform grids for the radius queries of addStaticPoints / getOverlap
-    DBuf<unsigned long long> d_gkeys, d_gskeys;
-    DBuf<int> d_gidx, d_gsidx, d_gcount;
+    DBuf<int> d_gbucket, d_gstart, d_gcursor, d_gcount;
     DBuf<float4> d_gpts, d_gquery;
-    DBuf<unsigned char> d_gsel;
+    DBuf<unsigned char> d_gsel, d_gctl;
+    // the window grid of addStaticPoints is kept across the keyframe clouds of one call (DmsaSlam.h:296-339: one kd-tree)
+    uint64_t worldEpoch = 0, gridEpoch = ~0ull;
+    float gridRadius = -1.0f;
+    int gridN = 0, gridB = 0;
+    double gridH = 0;
+    // buffers of the pre-processing / normal estimation entry points (dmsa_b200_pre.inl)
+    DBuf<LevelInfo> p_linfo;
+    DBuf<int> p_keys, p_bb, p_idx, p_sidx, p_scan, p_raw_start, p_raw_diff, p_pick, p_flag, p_pos, p_rand, p_nn;
+    DBuf<unsigned long long> p_code, p_scode;
+    DBuf<unsigned char> p_ctl, p_raw, p_out;
+    DBuf<float4> p_pts, p_cloud;
+    DBuf<float> p_range;
     DBuf<double> d_S, d_Q, d_E, d_jpart, d_hg, d_ls, d_lspart, d_solve, d_iter, d_chol;
     bool solveAttr = false;
     DBuf<int> d_biglist;  // sets with more than GAUSS_WARP_MAX members (+ the count at [cellCap])
@@ -547,22 +556,7 @@ int transformBase(dmsa_b200_ctx* ctx) {
            ctx->curVld, 0, ctx->d_world.p, kfm ? ctx->d_normal_l.p : nullptr, kfm ? ctx->d_normal_w.p : nullptr);
     CK(cudaGetLastError());
     ctx->worldValid = true;
-    return 0;
-}
-
-int ensureCub(dmsa_b200_ctx* ctx, int N, int cells) {
-    size_t need = 0, b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, N, 0, 64);
-    need = std::max(need, b);
-    cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, std::max(N, cells + 1));
-    need = std::max(need, b);
-    cub::DeviceScan::ExclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, std::max(N, cells + 1));
-    need = std::max(need, b);
-    cub::DeviceRadixSort::SortPairsDescending(nullptr, b, (int*)nullptr, (int*)nullptr, (int*)nullptr, (int*)nullptr, cells, 0, 10);
-    need = std::max(need, b);
-    // one temporary area per resolution level: the two levels' sorts / scans run concurrently on two streams
-    ctx->cubPer = (need + 511) / 256 * 256;
-    CK(ctx->d_cub.ensure(2 * ctx->cubPer));
+    ctx->worldEpoch++;
     return 0;
 }
 
@@ -1459,9 +1453,10 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(d_stage); REL(d_local); REL(d_world); REL(d_normal_l); REL(d_normal_w); REL(d_tid); REL(d_ring); REL(d_flag);
     REL(d_p); REL(d_step); REL(d_batch); REL(d_globO); REL(d_globT); REL(d_quat); REL(d_extra); REL(d_dense); REL(d_Mtab); REL(d_Mpair);
     REL(d_linfo); REL(d_keys); REL(d_bb); REL(d_idx); REL(d_sidx); REL(d_flagA); REL(d_scanA); REL(d_raw_start); REL(d_raw_diff); REL(d_acc_flag);
-    REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_split_nbox); REL(d_split_search); REL(d_code); REL(d_scode); REL(d_cub); REL(d_ctl); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
+    REL(d_acc_scan); REL(d_out_cnt); REL(d_sub); REL(d_ntile); REL(d_tile_off); REL(d_best_ij); REL(d_scratch); REL(d_tiles); REL(d_best_v); REL(d_split_nbox); REL(d_split_search); REL(d_code); REL(d_scode); REL(d_ctl); REL(d_rec); REL(d_wrec); REL(d_cell_start); REL(d_cell_n); REL(d_cell_level);
     REL(d_cell_key); REL(d_cell_sub); REL(d_cell_kind); REL(d_okey); REL(d_oval); REL(d_nchunk); REL(d_chunk_off); REL(d_cell_info); REL(d_cell_w0); REL(d_cell_w); REL(d_chunks);
-    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_gkeys); REL(d_gskeys); REL(d_gidx); REL(d_gsidx); REL(d_gcount); REL(d_gpts); REL(d_gquery); REL(d_gsel); REL(d_mom); REL(d_solve); REL(d_iter); REL(d_chol);
+    REL(d_S); REL(d_Q); REL(d_E); REL(d_jpart); REL(d_hg); REL(d_ls); REL(d_lspart); REL(d_done); REL(d_mu); REL(d_biglist); REL(d_gbucket); REL(d_gstart); REL(d_gcursor); REL(d_gcount); REL(d_gpts); REL(d_gquery); REL(d_gsel); REL(d_gctl);
+    REL(p_linfo); REL(p_keys); REL(p_bb); REL(p_idx); REL(p_sidx); REL(p_scan); REL(p_raw_start); REL(p_raw_diff); REL(p_pick); REL(p_flag); REL(p_pos); REL(p_rand); REL(p_nn); REL(p_code); REL(p_scode); REL(p_ctl); REL(p_raw); REL(p_out); REL(p_pts); REL(p_cloud); REL(p_range); REL(d_mom); REL(d_solve); REL(d_iter); REL(d_chol);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
@@ -1624,6 +1619,7 @@ int dmsa_b200_traj_register_scans(dmsa_b200_ctx* ctx, int32_t n_scans, const dms
     }
     ctx->n_scan = total;
     ctx->worldValid = false;
+    ctx->worldEpoch++;
     ctx->G = 0;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1673,6 +1669,7 @@ int dmsa_b200_traj_add_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_s
            ctx->d_local.p, ctx->d_world.p, ctx->d_ring.p, ctx->d_tid.p, ctx->d_flag.p);
     ctx->n_static += n;
     ctx->worldValid = false;
+    ctx->worldEpoch++;
     ctx->G = 0;
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1789,6 +1786,7 @@ int dmsa_b200_kf_commit(dmsa_b200_ctx* ctx) {
     ctx->n_scan = total;
     ctx->n_static = 0;
     ctx->worldValid = false;
+    ctx->worldEpoch++;
     ctx->G = 0;
     int flag = 0;
     CK(cudaMemcpy(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost));
@@ -2178,35 +2176,69 @@ int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* sett
 
 // ---- static-point selection and overlap ratio (DmsaSlam.h:264-414) ---------------------------------
 namespace {
-// grid over `n` points (device, xyzw) with cell edge radius * 1.000001 -> sorted keys + points in key order
-int buildRadiusGrid(dmsa_b200_ctx* ctx, const float4* pts, int n, float radius, GridView* view) {
-    double h = (double)radius * 1.000001;
+// hashed grid over `n` points (device; every stride4-th float4 is a point) with cell edge h (kernels_knn.cuh)
+int buildHashGrid(dmsa_b200_ctx* ctx, const float4* pts, int n, int stride4, double h, HashGrid* view) {
     if (!(h > 0.0)) h = 1e-6;
+    int B = 4096;
+    while (B < 2 * n && B < (1 << 22)) B <<= 1;
     view->n = n;
+    view->B = B;
     view->h = h;
-    view->keys = nullptr;
+    view->start = nullptr;
     view->pts = nullptr;
     if (n == 0) return 0;
-    CK(ctx->d_gkeys.ensure(n));
-    CK(ctx->d_gskeys.ensure(n));
-    CK(ctx->d_gidx.ensure(n));
-    CK(ctx->d_gsidx.ensure(n));
+    CK(ctx->d_gbucket.ensure(n));
+    CK(ctx->d_gstart.ensure((size_t)B + 2));
+    CK(ctx->d_gcursor.ensure((size_t)2 * B + 2));  // [counts (B + 1) | cursors (B)]
     CK(ctx->d_gpts.ensure(n));
-    CKRC(ensureCub(ctx, n, 1));
-    LAUNCH(k_grid_keys, cdiv(n, 256), 256, 0, pts, n, h, ctx->d_gkeys.p, ctx->d_gidx.p);
-    size_t bytes = ctx->cubPer;
-    CK(cub::DeviceRadixSort::SortPairs(ctx->d_cub.p, bytes, ctx->d_gkeys.p, ctx->d_gskeys.p, ctx->d_gidx.p, ctx->d_gsidx.p, n, 0, 64, ctx->stream));
-    LAUNCH(k_grid_gather, cdiv(n, 256), 256, 0, pts, ctx->d_gsidx.p, n, ctx->d_gpts.p);
-    view->keys = ctx->d_gskeys.p;
+    const int tiles = (B + 1 + CS_TILE - 1) / CS_TILE;
+    const size_t ctlBytes = 16 + (size_t)tiles * sizeof(u64_t);
+    CK(ctx->d_gctl.ensure(ctlBytes));
+    CK(cudaMemsetAsync(ctx->d_gctl.p, 0, ctlBytes, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_gcursor.p, 0, ((size_t)2 * B + 2) * sizeof(int), ctx->stream));
+    int* counts = ctx->d_gcursor.p;
+    int* cursor = ctx->d_gcursor.p + B + 1;
+    LAUNCH(k_hg_count, cdiv(n, 256), 256, 0, pts, n, stride4, h, B, ctx->d_gbucket.p, counts);
+    ScanArgs sa;
+    sa.in = counts;
+    sa.out = ctx->d_gstart.p;
+    sa.n = B + 1;
+    sa.tiles = tiles;
+    sa.status = reinterpret_cast<u64_t*>(ctx->d_gctl.p + 16);
+    sa.ticket = reinterpret_cast<int*>(ctx->d_gctl.p);
+    LAUNCH(k_scan_excl, tiles, CS_T, 0, sa);
+    LAUNCH(k_hg_fill, cdiv(n, 256), 256, 0, pts, n, stride4, ctx->d_gbucket.p, ctx->d_gstart.p, cursor, ctx->d_gpts.p);
+    view->start = ctx->d_gstart.p;
     view->pts = ctx->d_gpts.p;
+    CK(cudaGetLastError());
+    return 0;
+}
+// the radius grid of the staged window cloud (cell edge radius * 1.000001), rebuilt only when the cloud or the radius changed
+int windowRadiusGrid(dmsa_b200_ctx* ctx, float radius, HashGrid* view) {
+    const int N = (int)numPoints(ctx);
+    if (ctx->gridEpoch == ctx->worldEpoch && ctx->gridRadius == radius && ctx->gridN == N && N > 0) {
+        view->n = N;
+        view->B = ctx->gridB;
+        view->h = ctx->gridH;
+        view->start = ctx->d_gstart.p;
+        view->pts = ctx->d_gpts.p;
+        return 0;
+    }
+    CKRC(buildHashGrid(ctx, ctx->d_world.p, N, 1, (double)radius * 1.000001, view));
+    ctx->gridEpoch = ctx->worldEpoch;
+    ctx->gridRadius = radius;
+    ctx->gridN = N;
+    ctx->gridB = view->B;
+    ctx->gridH = view->h;
     return 0;
 }
 }  // namespace
 
 // addStaticPoints, inner loop for ONE keyframe cloud (DmsaSlam.h:304-339): selected[j] = 1 iff the nearest point of the
 // staged window cloud (globalPoints as of the last update_global_points / add_static_points) is within max_dist and the
-// point is visible from pos; *num_selected = currOverlap.  The window grid is rebuilt on every call (the reference builds
-// its kd-tree once per addStaticPoints call; keyframe clouds are ~1e5 points, the grid build is a 64-bit sort of the window).
+// point is visible from pos; *num_selected = currOverlap.  The window grid is built by the first call and kept for the
+// following keyframe clouds as long as the window cloud and the radius stay the same (the reference builds its kd-tree once
+// per addStaticPoints call, DmsaSlam.h:283-286).
 int dmsa_b200_select_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_normal* cloud, int64_t n, const float* pos, float max_dist,
                                    uint8_t* selected, int64_t* num_selected) {
     if ((n > 0 && (!cloud || !selected)) || !pos || n < 0 || n > 0x3fffffff) ARGFAIL("select_static_points: bad arguments");
@@ -2215,8 +2247,8 @@ int dmsa_b200_select_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_nor
     if (n == 0) return 0;
     const int64_t N = numPoints(ctx);
     if (N > 0 && !ctx->worldValid) ARGFAIL("select_static_points: call update_global_points first (the search runs on globalPoints)");
-    GridView g;
-    CKRC(buildRadiusGrid(ctx, ctx->d_world.p, (int)N, max_dist, &g));
+    HashGrid g;
+    CKRC(windowRadiusGrid(ctx, max_dist, &g));
     const float max_sq = (float)std::pow((double)(1.0f * max_dist), 2);  // DmsaSlam.h:293
     CK(ctx->d_gquery.ensure((size_t)3 * n));
     CK(ctx->d_gsel.ensure((size_t)n));
@@ -2243,8 +2275,9 @@ int dmsa_b200_overlap(dmsa_b200_ctx* ctx, const float* pc1_xyzw, int64_t n1, flo
     if (!ctx->worldValid) ARGFAIL("overlap: call update_global_points first (the search runs on globalPoints)");
     CK(ctx->d_gquery.ensure((size_t)n1));
     CK(cudaMemcpyAsync(ctx->d_gquery.p, pc1_xyzw, (size_t)n1 * 16, cudaMemcpyHostToDevice, ctx->stream));
-    GridView g;
-    CKRC(buildRadiusGrid(ctx, ctx->d_gquery.p, (int)n1, max_dist, &g));
+    HashGrid g;
+    ctx->gridEpoch = ~0ull;  // the grid buffers now hold pc1, not the window
+    CKRC(buildHashGrid(ctx, ctx->d_gquery.p, (int)n1, 1, (double)max_dist * 1.000001, &g));
     const float max_sq = max_dist * max_dist;  // :386
     CK(ctx->d_gcount.ensure(1));
     CK(cudaMemsetAsync(ctx->d_gcount.p, 0, sizeof(int), ctx->stream));
@@ -2435,5 +2468,7 @@ int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, doub
     CKRC(uploadParams(ctx));
     return lineSearchInto(ctx, step, ls_dev);
 }
+
+#include "dmsa_b200_pre.inl"
 
 }  // extern "C"

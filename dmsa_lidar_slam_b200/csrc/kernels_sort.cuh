@@ -138,9 +138,18 @@ __global__ void __launch_bounds__(RS_T) k_sort_prepare(SortArgs a, PrepArgs pa) 
                 const u64_t x = (u64_t)((long long)kx - lo0), y = (u64_t)((long long)ky - lo1), z = (u64_t)((long long)kz - lo2);
                 m = (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
             }
-            code[i] = packed ? (m | ((u64_t)(u32_t)pa.ring[i] << RING_SHIFT)) : m;
+            code[i] = (packed && pa.ring) ? (m | ((u64_t)(u32_t)pa.ring[i] << RING_SHIFT)) : m;
         }
-        for (int p = 0; p < a.npass; ++p) hist_add_warp(sh + p * RS_BINS, (u32_t)(m >> (8 * p)) & 255u, valid);
+        // the low digits of a Morton code are well spread (plain shared-memory atomics); the top digits take few values
+        // (equal digits of a warp are counted once)
+        for (int p = 0; p < a.npass; ++p) {
+            const u32_t d = (u32_t)(m >> (8 * p)) & 255u;
+            if (p + 2 < a.npass) {
+                if (valid) atomicAdd(sh + p * RS_BINS + d, 1u);
+            } else {
+                hist_add_warp(sh + p * RS_BINS, d, valid);
+            }
+        }
     }
     __syncthreads();
     u32_t* __restrict__ gh = a.hist + (size_t)seg * RS_MAXPASS * RS_BINS;
@@ -489,7 +498,7 @@ __global__ void __launch_bounds__(SG_T, 3) k_segment(SegmentArgs a) {
         }
         next_invalid = (i0 + SG_ITEMS >= n) || (c[SG_ITEMS + 1] & cmask) >= inval;
     }
-    if (!packed) {  // ring ids by gather (independent loads, in flight while the scan and the look-back run)
+    if (!packed && a.ring) {  // ring ids by gather (independent loads, in flight while the scan and the look-back run)
 #pragma unroll
         for (int k = 0; k < SG_ITEMS; ++k) rg[k] = (i0 + k < n) ? (int)idx[i0 + k] : 0;
 #pragma unroll
@@ -524,7 +533,7 @@ __global__ void __launch_bounds__(SG_T, 3) k_segment(SegmentArgs a) {
     const int last = (int)(ex >> 31) - 1;
     // ring id of the run head that precedes this thread's items
     int hring = 0;
-    if ((valid & 1u) && !(heads & 1u) && last >= 0) hring = packed ? (int)(code[last] >> RING_SHIFT) : a.ring[idx[last]];
+    if ((valid & 1u) && !(heads & 1u) && last >= 0) hring = packed ? (int)(code[last] >> RING_SHIFT) : (a.ring ? a.ring[idx[last]] : 0);
     DMSA_TLK(2, 4);
     int* __restrict__ scan = a.scan[seg];
     int* __restrict__ raw_start = a.raw_start[seg];

@@ -273,6 +273,36 @@ int dmsa_b200_select_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_nor
  * (n1 x {x, y, z, w} floats on the host) is within max_dist; 0 when either cloud is empty. */
 int dmsa_b200_overlap(dmsa_b200_ctx* ctx, const float* pc1_xyzw, int64_t n1, float max_dist, float* overlap);
 
+/* ---- scan pre-processing and normal estimation (the producers of the optimizer's inputs) ----
+ * The reference seeds every randomGridDownsampling call with srand(time(0)); here the caller passes the seed, and the draw
+ * is glibc's rand() sequence for that seed (dmsa_b200_rand_sequence), one number per octree leaf in leaf order. */
+typedef struct dmsa_b200_preprocess_config {
+    int32_t max_num_points_per_scan; /* Config.h:24 */
+    float min_dist_ds;               /* Config.h:25 minDistDS */
+    float min_dist;                  /* Config.h:38 */
+    float lidar_to_imu[16];          /* Config.h:58 lidarToImuTform, column-major (Eigen::Matrix4f::data()) */
+} dmsa_b200_preprocess_config;
+/* out[k] = the k-th rand() after srand(seed) (glibc; host only, no context) */
+int dmsa_b200_rand_sequence(uint32_t seed, int64_t n, int32_t* out);
+/* randomGridDownsampling(rawPc, filteredPc, gridSize) (helpers.h:67-182): points = n records of stride_bytes (a multiple of
+ * 16) with x, y, z floats at offset 0 (PointStampId: 32, pcl::PointNormal: 48); indices_out[c] = index of the point copied to
+ * filteredPc->points[c] (PCL octree leaves in depth-first order, member int(r * (size - 1)) of each); *n_out = leaf count. */
+int dmsa_b200_grid_downsample(dmsa_b200_ctx* ctx, const void* points, int64_t n, int32_t stride_bytes, float grid_size, uint32_t seed,
+                              int32_t* indices_out /*n*/, int64_t* n_out);
+/* the same on the staged window's globalPoints (addNewKeyframeToMap, DmsaSlam.h:506) */
+int dmsa_b200_downsample_global_points(dmsa_b200_ctx* ctx, float grid_size, uint32_t seed, int32_t* indices_out /*num_points*/, int64_t* n_out);
+/* preProcess(rawPc, filteredPc) (DmsaSlam.h:570-634): adaptive grid (0.4 / 0.3 / 0.2 / 0.15 while fewer than max_num points),
+ * range cut at max(rangesSorted[min(max_num, size - 1)], minDistDS) and > min_dist, transform to the IMU frame (the arithmetic
+ * of pcl::transformPointCloud, PCL 1.10 SSE2 path), w = 1.  out: room for n records. */
+int dmsa_b200_preprocess_scan(dmsa_b200_ctx* ctx, const dmsa_b200_point_stamp_id* raw, int64_t n, const dmsa_b200_preprocess_config* cfg, uint32_t seed,
+                              dmsa_b200_point_stamp_id* out, int64_t* n_out, float* grid_size_out);
+/* updateNormals(cloud, origin) (DmsaSlam.h:557-568): pcl::NormalEstimationOMP with setKSearch(6) on the cloud itself, normals
+ * flipped towards the view point; normal_x/y/z and curvature are overwritten in place.  cell_size > 0: edge of the search
+ * grid (the cloud's grid size).  nn_indices (optional, n x 6): neighbour indices in search-result order (ascending distance,
+ * the point itself first), -1 where the cloud has fewer than 6 points. */
+int dmsa_b200_estimate_normals(dmsa_b200_ctx* ctx, dmsa_b200_point_normal* cloud, int64_t n, const float* viewpoint /*3*/, float cell_size,
+                               int32_t* nn_indices);
+
 #ifdef __cplusplus
 }
 #endif

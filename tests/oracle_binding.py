@@ -100,6 +100,12 @@ def lib(opt="O2"):
     L.orc_select_static_points.argtypes = [vp, i64, vp, i64, vp, C.c_float, C.c_float, vp]
     L.orc_overlap.restype = C.c_float
     L.orc_overlap.argtypes = [vp, i64, vp, i64, C.c_float]
+    L.orc_rand_sequence.argtypes = [C.c_uint, i64, vp]
+    L.orc_grid_downsample.restype = i64
+    L.orc_grid_downsample.argtypes = [vp, i64, C.c_float, C.c_uint, vp]
+    L.orc_preprocess.restype = i64
+    L.orc_preprocess.argtypes = [vp, i64, i32, C.c_float, C.c_float, vp, C.c_uint, vp, P(C.c_float)]
+    L.orc_update_normals.argtypes = [vp, i64, vp, vp]
     _LIBS[opt] = L
     return L
 
@@ -329,3 +335,39 @@ def overlap(pc1_xyzw, window_xyzw, max_dist):
     a = np.ascontiguousarray(pc1_xyzw, dtype=np.float32).reshape(-1, 4)
     w = np.ascontiguousarray(window_xyzw, dtype=np.float32).reshape(-1, 4)
     return float(L.orc_overlap(_p(a), len(a), _p(w), len(w), float(max_dist)))
+
+
+# ---- SURVEY 8(f) rank 3 (helpers.h:67-182, DmsaSlam.h:557-634) -------------------------------------------------------------
+def rand_sequence(seed, n):
+    out = np.zeros(int(n), dtype=np.int32)
+    lib().orc_rand_sequence(int(seed) & 0xFFFFFFFF, int(n), _p(out))
+    return out
+
+
+def grid_downsample(xyz, grid, seed):
+    """xyz: (N, 3) float32 -> picked indices in leaf order."""
+    xyzw = np.ones((len(xyz), 4), dtype=np.float32)
+    xyzw[:, :3] = xyz
+    idx = np.zeros(len(xyz), dtype=np.int32)
+    n = lib().orc_grid_downsample(_p(xyzw), len(xyz), float(grid), int(seed) & 0xFFFFFFFF, _p(idx))
+    return idx[:n]
+
+
+def preprocess(raw, max_num, minDistDS, min_dist, T, seed):
+    """raw: PointStampId structured array; T: 4 x 4 -> (filtered records, grid size)."""
+    raw = np.ascontiguousarray(raw)
+    out = np.zeros(len(raw), dtype=raw.dtype)
+    Tc = np.ascontiguousarray(np.asarray(T, dtype=np.float32).reshape(4, 4).T).ravel()  # column-major
+    gs = C.c_float(0.0)
+    n = lib().orc_preprocess(_p(raw), len(raw), int(max_num), float(minDistDS), float(min_dist), _p(Tc), int(seed) & 0xFFFFFFFF, _p(out), C.byref(gs))
+    return out[:n], float(gs.value)
+
+
+def update_normals(cloud, origin=(0.0, 0.0, 0.0)):
+    """cloud: pcl::PointNormal structured array -> (cloud with normals / curvature, (n, 6) neighbour indices)."""
+    c = np.ascontiguousarray(cloud).copy()
+    assert c.dtype.itemsize == 48
+    nn = np.zeros((len(c), 6), dtype=np.int32)
+    vp_ = np.asarray(origin, dtype=np.float32)
+    lib().orc_update_normals(_p(c), len(c), _p(vp_), _p(nn))
+    return c, nn
