@@ -225,6 +225,81 @@ def run_reference(args):
     emit(line)
 
 
+def measure_frontend(traj, win, local):
+    """SURVEY 8(f) ranks 2 and 3 through the C-ABI with host buffers (every call uploads its cloud and reads its result back),
+    next to the oracle port on the host cores; `identical` = the results of the two are equal."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from dmsa_lidar_slam_b200 import PreProcessor, PreprocessConfig
+    from dmsa_lidar_slam_b200.synth import POINT_NORMAL
+
+    def gpu_ms(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize()
+            ts.append(1e3 * (time.perf_counter() - t0))
+        return float(np.median(ts)), r
+
+    def cpu_ms(fn):
+        t0 = time.perf_counter()
+        r = fn()
+        return 1e3 * (time.perf_counter() - t0), r
+
+    out = {"what": "the producers and the neighbour of the optimizer's inputs (DmsaSlam.h:264-414, 557-634; helpers.h:67-182), host buffers in and out, "
+                   "wall time per call incl. copies; cpu = oracle port, OpenMP on all host cores where the step is parallel"}
+    pre = PreProcessor(ctx=traj.ctx)
+    raw = win["scans"][0]
+    cfg = PreprocessConfig(3000, 30.0, 0.0)
+    g_ms, (g_out, g_gs) = gpu_ms(lambda: pre.preProcess(raw, cfg, 7))
+    c_ms, (c_out, c_gs) = cpu_ms(lambda: ob.preprocess(raw, 3000, 30.0, 0.0, np.eye(4), 7))
+    out["preprocess_scan"] = {"points_in": int(len(raw)), "points_out": int(len(g_out)), "grid_size": g_gs, "gpu_ms": g_ms, "cpu_ms": c_ms,
+                              "identical": bool(g_out.tobytes() == c_out.tobytes())}
+    # keyframe cloud: the window's globalPoints downsampled at minGridSize (DmsaSlam.h:506), then k = 6 normals
+    traj.updateGlobalPoints()
+    world = traj.globalPoints()
+    import ctypes as C
+    idx = np.zeros(len(world), dtype=np.int32)
+    n_out = C.c_int64(0)
+
+    def ds():
+        traj.ctx._ck(traj.L.dmsa_b200_downsample_global_points(traj.h, C.c_float(0.3), 5, idx.ctypes.data_as(C.c_void_p), C.byref(n_out)))
+        return idx[: n_out.value].copy()
+
+    g_ms, g_idx = gpu_ms(ds)
+    c_ms, c_idx = cpu_ms(lambda: ob.grid_downsample(world[:, :3], 0.3, 5))
+    out["keyframe_downsample"] = {"points_in": int(len(world)), "points_out": int(len(g_idx)), "gpu_ms": g_ms, "cpu_ms": c_ms, "cpu_cores": 1,
+                                  "identical": bool(np.array_equal(g_idx, c_idx))}
+    kc = np.zeros(len(g_idx), dtype=POINT_NORMAL)
+    kc["x"], kc["y"], kc["z"], kc["w"] = world[g_idx, 0], world[g_idx, 1], world[g_idx, 2], 1.0
+    g_ms, (g_cl, g_nn) = gpu_ms(lambda: pre.updateNormals(kc, (0, 0, 0), 0.3, with_neighbours=True))
+    sub = kc[:20000]  # the oracle's neighbour search is exhaustive (O(n^2)): bounded sample
+    c_ms, (c_cl, c_nn) = cpu_ms(lambda: ob.update_normals(sub))
+    g_sub = pre.updateNormals(sub, (0, 0, 0), 0.3, with_neighbours=True)
+    out["update_normals_k6"] = {"points": int(len(kc)), "gpu_ms": g_ms, "points_per_s": len(kc) / (g_ms * 1e-3),
+                                "cpu_ms_20000_points_exhaustive": c_ms, "cpu_cores": os.cpu_count(),
+                                "neighbour_lists_identical_on_sample": bool(np.array_equal(g_sub[1], c_nn))}
+    # rank 2: static-point selection of one keyframe cloud against the window, and the overlap ratio
+    g_cl["x"] += 0.05
+    pos = np.zeros(3, dtype=np.float32)
+    g_ms, (sel, cnt) = gpu_ms(lambda: traj.selectStaticPoints(g_cl, pos, 0.3))
+    flat = np.ascontiguousarray(np.stack([g_cl["x"], g_cl["y"], g_cl["z"], g_cl["w"], g_cl["nx"], g_cl["ny"], g_cl["nz"], g_cl["nw"]], 1).astype(np.float32))
+    msq = np.float32(np.float64(np.float32(0.3)) ** 2)  # (float)std::pow(1.0f * minGridSize, 2), DmsaSlam.h:293
+    c_ms, (sel_o, cnt_o) = cpu_ms(lambda: ob.select_static_points(world, flat, pos, msq, 0.3))
+    out["select_static_points"] = {"window_points": int(len(world)), "keyframe_points": int(len(g_cl)), "selected": int(cnt), "gpu_ms_grid_cached": g_ms,
+                                   "cpu_ms": c_ms, "cpu_cores": os.cpu_count(), "identical": bool(cnt == cnt_o and np.array_equal(sel, sel_o))}
+    act = np.ascontiguousarray(np.stack([g_cl["x"], g_cl["y"], g_cl["z"], g_cl["w"]], 1)[sel.astype(bool)])
+    g_ms, ov = gpu_ms(lambda: traj.overlap(act, 0.3))
+    c_ms, ov_o = cpu_ms(lambda: ob.overlap(act, world, 0.3))
+    out["overlap"] = {"map_points": int(len(act)), "gpu_ms": g_ms, "cpu_ms": c_ms, "value": ov, "identical": bool(ov == ov_o)}
+    return out
+
+
 def pinned_copy(arr):
     import torch
 
@@ -355,6 +430,12 @@ def run_sliding(args):
     e2e_single, _ = time_e2e(e2e_step, e2e_steps)
     e2e_value, e2e_iters = time_e2e(e2e_optimize, max(3, min(args.steps // 2, 6)))
     clk = clocks.stop()
+    frontend = None
+    if world == 1 and args.frontend:
+        try:
+            frontend = measure_frontend(traj, win, local)
+        except Exception as e:  # never lose the headline over a side measurement
+            frontend = {"error": repr(e)}
     keyframe = None
     if args.keyframe:
         from dmsa_lidar_slam_b200 import distributed
@@ -414,7 +495,7 @@ def run_sliding(args):
                 "single_iteration_per_upload": {"value": e2e_single, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                                                 "what": "round-1 definition: one iteration per uploaded window (upload + centralize + 1 iteration + pose read-back)"}},
         "gpu_launches": int(launches),
-        "gpu_launches_note": "hand-written kernels only (CUB radix-sort/scan launches inside the set build are not counted)",
+        "gpu_launches_note": "every kernel of the step is hand-written (the radix sort and the scans of the set build included: no library primitive on the path)",
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                      "traffic_source": traffic_src,
                      "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "memberships_per_launch": units_M, "sets_per_launch": units_G,
@@ -427,6 +508,8 @@ def run_sliding(args):
     }
     if keyframe is not None:
         line["keyframe"] = keyframe
+    if frontend is not None:
+        line["frontend"] = frontend
     if world == 1:
         threads = best_thread_count(win)
         cb = oracle_cpu_baseline(win, threads)
@@ -449,6 +532,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sliding", choices=["sliding", "keyframe"])
     ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--frontend", type=int, default=1, help="1 (N = 1 only): also time SURVEY 8(f) ranks 2 / 3 (static points, pre-processing, normals) -> `frontend` object")
     ap.add_argument("--keyframe", type=int, default=1, help="1: also measure BASELINE config 4 (keyframe bundles, NCCL all-reduce) -> `keyframe` object")
     args = ap.parse_args()
     global RESULT_OUT

@@ -5,4 +5,5 @@ Only what the hot path needs lives here: `csrc/` (CUDA kernels + the C-ABI of in
 (deterministic synthetic windows of the BASELINE shapes) and `build.py` (in-tree nvcc build).
 """
 from .api import (ContinuousTrajectory, DmsaError, DmsaOptimizer, DmsaOptimSettings, MapManagement,  # noqa: F401
-                  OptimizablePointSet, PreProcessor, PreprocessConfig, load_library, rand_sequence)
+                  OptimizablePointSet, PreProcessor, PreprocessConfig, decode_pointcloud2, format_tum_pose, load_library,
+                  pc2_layout_for_sensor, rand_sequence, save_pcd_ascii)

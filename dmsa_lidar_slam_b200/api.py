@@ -58,6 +58,13 @@ class Report(C.Structure):
         return d
 
 
+class Pc2Layout(C.Structure):
+    """Where x / y / z / time / ring sit in one sensor_msgs/PointCloud2 point record (src/dmsa_slam_ros.cpp:399-483)."""
+
+    _fields_ = [("point_step", C.c_int32), ("x_offset", C.c_int32), ("y_offset", C.c_int32), ("z_offset", C.c_int32),
+                ("stamp_offset", C.c_int32), ("stamp_type", C.c_int32), ("ring_offset", C.c_int32), ("ring_type", C.c_int32)]
+
+
 class PreprocessConfig(C.Structure):
     """The fields of Config (Config.h:24-58) that preProcess reads (DmsaSlam.h:570-634); defaults are the reference's."""
 
@@ -148,6 +155,10 @@ def load_library():
         "dmsa_b200_downsample_global_points": (i32, [vp, C.c_float, C.c_uint32, vp, P(i64)]),
         "dmsa_b200_preprocess_scan": (i32, [vp, vp, i64, P(PreprocessConfig), C.c_uint32, vp, P(i64), P(C.c_float)]),
         "dmsa_b200_estimate_normals": (i32, [vp, vp, i64, vp, C.c_float, vp]),
+        "dmsa_b200_pc2_layout_for_sensor": (i32, [C.c_char_p, vp, i32, i32, P(Pc2Layout)]),
+        "dmsa_b200_decode_pointcloud2": (i32, [vp, vp, i64, P(Pc2Layout), f64, f64, vp]),
+        "dmsa_b200_format_tum_pose": (i32, [f64, vp, vp, C.c_char_p, i32]),
+        "dmsa_b200_save_pcd_ascii": (i32, [C.c_char_p, vp, i64]),
         "dmsa_b200_select_static_points": (i32, [vp, vp, i64, vp, C.c_float, vp, P(i64)]),
         "dmsa_b200_overlap": (i32, [vp, vp, i64, C.c_float, P(C.c_float)]),
         "dmsa_b200_lm_solve_device": (i32, [vp, P(DmsaOptimSettings), vp, i32, vp, P(i32)]),
@@ -172,6 +183,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode", "dmsa_b200_get_batch_tables",
+    "dmsa_b200_pc2_layout_for_sensor", "dmsa_b200_decode_pointcloud2", "dmsa_b200_format_tum_pose", "dmsa_b200_save_pcd_ascii",
     "dmsa_b200_rand_sequence", "dmsa_b200_grid_downsample", "dmsa_b200_downsample_global_points", "dmsa_b200_preprocess_scan", "dmsa_b200_estimate_normals",
     "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
     "dmsa_b200_spd_solve_dev", "dmsa_b200_spd_solve", "dmsa_b200_bundle_jacobian", "dmsa_b200_bundle_line_search", "dmsa_b200_bundle_verify",
@@ -648,3 +660,36 @@ class PreProcessor:
         nn = np.zeros((len(cloud), 6), dtype=np.int32) if with_neighbours else None
         self.ctx._ck(self.L.dmsa_b200_estimate_normals(self.h, _p(cloud), len(cloud), _p(vp), float(cell_size), _p(nn) if with_neighbours else None))
         return (cloud, nn) if with_neighbours else cloud
+
+
+# ---- data formats (src/dmsa_slam_ros.cpp:286-291, 372-486; OutputManagement.h:80-96) -------------------
+def pc2_layout_for_sensor(sensor, field_offsets, point_step):
+    L = load_library()
+    fo = np.ascontiguousarray(field_offsets, dtype=np.int32)
+    out = Pc2Layout()
+    if L.dmsa_b200_pc2_layout_for_sensor(sensor.encode(), _p(fo), len(fo), int(point_step), C.byref(out)):
+        raise DmsaError(f"unknown sensor type / missing field: {sensor}")
+    return out
+
+
+def decode_pointcloud2(ctx, data, n_points, layout, stamp_msg, delta_t=0.0):
+    """callbackPointCloud's per-point loop: msg->data (bytes / uint8 array) -> PointStampId array."""
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+    out = np.zeros(int(n_points), dtype=POINT_STAMP_ID)
+    ctx._ck(ctx.L.dmsa_b200_decode_pointcloud2(ctx.h, _p(buf), int(n_points), C.byref(layout), float(stamp_msg), float(delta_t), _p(out)))
+    return out
+
+
+def format_tum_pose(stamp, pos, orient):
+    L = load_library()
+    buf = C.create_string_buffer(256)
+    n = L.dmsa_b200_format_tum_pose(float(stamp), _p(_c64(pos)), _p(_c64(orient)), buf, 256)
+    if n < 0:
+        raise DmsaError("format_tum_pose failed")
+    return buf.value.decode()
+
+
+def save_pcd_ascii(filename, cloud):
+    c = np.ascontiguousarray(cloud, dtype=POINT_NORMAL)
+    if load_library().dmsa_b200_save_pcd_ascii(str(filename).encode(), _p(c), len(c)):
+        raise DmsaError(f"cannot write {filename}")

@@ -2470,5 +2470,6 @@ int dmsa_b200_line_search_costs_dev(dmsa_b200_ctx* ctx, const double* step, doub
 }
 
 #include "dmsa_b200_pre.inl"
+#include "dmsa_b200_io.inl"
 
 }  // extern "C"

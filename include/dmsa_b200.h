@@ -303,6 +303,33 @@ int dmsa_b200_preprocess_scan(dmsa_b200_ctx* ctx, const dmsa_b200_point_stamp_id
 int dmsa_b200_estimate_normals(dmsa_b200_ctx* ctx, dmsa_b200_point_normal* cloud, int64_t n, const float* viewpoint /*3*/, float cell_size,
                                int32_t* nn_indices);
 
+/* ---- the data formats either side of the path ------------------------------------------------
+ * sensor_msgs/PointCloud2 -> PointStampId (src/dmsa_slam_ros.cpp:372-486): where the x / y / z / time / ring fields sit
+ * inside one point record and how the reference interprets them per sensor type. */
+enum { DMSA_B200_STAMP_NONE = 0,       /* "unknown": stampMsg + deltaT * k / n                                  */
+       DMSA_B200_STAMP_F64_ABS = 1,    /* hesai, robosense, livoxXYZRTLT_s: double seconds                     */
+       DMSA_B200_STAMP_U32_NS_REL = 2, /* ouster: stampMsg + 1e-9 * uint32 nanoseconds                         */
+       DMSA_B200_STAMP_F32_REL = 3,    /* velodyne, sick: stampMsg + float seconds                             */
+       DMSA_B200_STAMP_F64_NS_ABS = 4  /* livoxXYZRTLT_ns: 1e-9 * double nanoseconds                           */ };
+enum { DMSA_B200_RING_NONE = 0 /* artificial ring k % 1000 */, DMSA_B200_RING_U16 = 1, DMSA_B200_RING_U8 = 2, DMSA_B200_RING_I8 = 3 };
+typedef struct dmsa_b200_pc2_layout {
+    int32_t point_step;
+    int32_t x_offset, y_offset, z_offset;
+    int32_t stamp_offset, stamp_type;
+    int32_t ring_offset, ring_type;
+} dmsa_b200_pc2_layout;
+/* layout of one of the reference's sensor types ("hesai", "ouster", "robosense", "velodyne", "livoxXYZRTLT_s",
+ * "livoxXYZRTLT_ns", "sick", "unknown") given msg->fields[i].offset for i < n_fields (host only, no context) */
+int dmsa_b200_pc2_layout_for_sensor(const char* sensor, const int32_t* field_offsets, int32_t n_fields, int32_t point_step, dmsa_b200_pc2_layout* out);
+/* the per-point loop of callbackPointCloud: data = msg->data (host), out = n_points records (host); stamp_msg =
+ * msg->header.stamp.toSec(), delta_t = stampMsg - lastPcMsgStamp (only read for DMSA_B200_STAMP_NONE) */
+int dmsa_b200_decode_pointcloud2(dmsa_b200_ctx* ctx, const uint8_t* data, int64_t n_points, const dmsa_b200_pc2_layout* layout, double stamp_msg,
+                                 double delta_t, dmsa_b200_point_stamp_id* out);
+/* addPoseToFile (OutputManagement.h:80-96): one line of the TUM trajectory file; returns the length, -1 if buf is too small */
+int dmsa_b200_format_tum_pose(double stamp, const double* pos /*3*/, const double* orient /*3, axis-angle*/, char* buf, int32_t buf_size);
+/* pcl::io::savePCDFileASCII of a pcl::PointNormal cloud (src/dmsa_slam_ros.cpp:286-291); 0 on success, -1 on I/O failure */
+int dmsa_b200_save_pcd_ascii(const char* filename, const dmsa_b200_point_normal* cloud, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif
