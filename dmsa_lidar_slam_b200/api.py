@@ -20,7 +20,7 @@ import numpy as np
 from .synth import POINT_NORMAL, POINT_STAMP_ID
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdmsa_b200.so")
+LIB_PATH = os.environ.get("DMSA_B200_LIB") or os.path.join(_HERE, "lib", "libdmsa_b200.so")  # (override: experiment builds only)
 
 STOP_REASONS = {0: "max_iter", 1: "few_gaussians", 2: "nan", 3: "no_improvement", 4: "epsilon"}
 
@@ -150,6 +150,7 @@ def load_library():
         "dmsa_b200_set_lm_solver": (i32, [vp, i32]),
         "dmsa_b200_set_pair_mode": (i32, [vp, i32]),
         "dmsa_b200_get_batch_tables": (i32, [vp, vp, vp]),
+        "dmsa_b200_set_run_ahead": (i32, [vp, i32]),
         "dmsa_b200_rand_sequence": (i32, [C.c_uint32, i64, vp]),
         "dmsa_b200_grid_downsample": (i32, [vp, vp, i64, i32, C.c_float, C.c_uint32, vp, P(i64)]),
         "dmsa_b200_downsample_global_points": (i32, [vp, C.c_float, C.c_uint32, vp, P(i64)]),
@@ -184,7 +185,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode", "dmsa_b200_get_batch_tables",
     "dmsa_b200_pc2_layout_for_sensor", "dmsa_b200_decode_pointcloud2", "dmsa_b200_format_tum_pose", "dmsa_b200_save_pcd_ascii",
-    "dmsa_b200_rand_sequence", "dmsa_b200_grid_downsample", "dmsa_b200_downsample_global_points", "dmsa_b200_preprocess_scan", "dmsa_b200_estimate_normals",
+    "dmsa_b200_set_run_ahead", "dmsa_b200_rand_sequence", "dmsa_b200_grid_downsample", "dmsa_b200_downsample_global_points", "dmsa_b200_preprocess_scan", "dmsa_b200_estimate_normals",
     "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
     "dmsa_b200_spd_solve_dev", "dmsa_b200_spd_solve", "dmsa_b200_bundle_jacobian", "dmsa_b200_bundle_line_search", "dmsa_b200_bundle_verify",
     "dmsa_b200_all_reduce", "dmsa_b200_comm_unique_id", "dmsa_b200_comm_init", "dmsa_b200_comm_destroy", "dmsa_b200_collective_count",
@@ -386,6 +387,10 @@ class OptimizablePointSet:
         out = np.zeros((int(dims[0]), int(dims[1]), 12), dtype=np.float32)
         self.ctx._ck(self.L.dmsa_b200_get_batch_tables(self.h, _p(out), _p(dims)))
         return out
+
+    def setRunAhead(self, on):
+        """optimizeSet: run-ahead loop (default) or one loop body at a time; bit-identical."""
+        self.ctx._ck(self.L.dmsa_b200_set_run_ahead(self.h, int(bool(on))))
 
     def setPairMode(self, mode):
         """1: pair-packed FP32x2 cost kernels for the forward-difference batch (default); 0: scalar kernels (bit-identical)."""

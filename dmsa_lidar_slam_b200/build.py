@@ -12,6 +12,7 @@ HOST_OBJ = os.path.join(_HERE, "lib", "host_solve.o")
 DEPS = [os.path.join(_HERE, "csrc", f) for f in ("host_solve.cpp", "dmsa_b200.cu", "kernels_cost.cuh", "kernels_pose.cuh", "kernels_sets.cuh", "kernels_solve.cuh", "kernels_sort.cuh", "kernels_chol.cuh", "kernels_knn.cuh", "kernels_pre.cuh", "dmsa_b200_pre.inl", "dmsa_b200_io.inl", "se3_math.cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", "dmsa_b200.h")]
 OUT = os.path.join(_HERE, "lib", "libdmsa_b200.so")
+OUT_FMA = os.path.join(_HERE, "lib", "libdmsa_b200_fma.so")  # experiment: the same kernels with FMA contraction allowed (scripts/fma_deviation.py)
 
 # -fmad=false: the reference's float arithmetic has no FMA contraction (CMakeLists.txt:13-17, baseline x86-64);
 # the kernels use explicit fma() where fusion is wanted (J^T J) and explicit *_rn intrinsics on the parity-critical path.
@@ -32,6 +33,16 @@ def is_stale():
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build_fma_variant():
+    """The experiment library of scripts/fma_deviation.py: -fmad=true and plain float operators on the cost path."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O3", "-mavx2", "-ffp-contract=off", "-fPIC", "-pthread", "-c", "-o", HOST_OBJ, HOST_SRC])
+    flags = [f for f in NVCC_FLAGS if f != "-fmad=false"] + ["-fmad=true", "-DDMSA_ALLOW_FMA"]
+    cmd = [nvcc_path()] + (["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []) + flags + ["-o", OUT_FMA, SRC, HOST_OBJ]
+    subprocess.check_call(cmd)
+    return OUT_FMA
 
 
 def build_library(force=False, verbose=False):

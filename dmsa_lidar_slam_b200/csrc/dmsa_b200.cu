@@ -183,6 +183,10 @@ struct dmsa_b200_ctx {
     int pairMode = 1;  // 1: pair-packed cost kernels (FMUL2/FADD2) with the shared-rotation fast path for the translation vectors of the
                        // forward-difference batch, 2: pair-packed without the fast path, 0: scalar kernels; all bit-identical
     int curV = 0, curVld = 0;
+    int runAhead = 1;  // dmsa_b200_optimize enqueues loop body i + 1 before reading body i's results (device LM solver only)
+    double* raPin = nullptr;  // pinned ring of two read-back blocks
+    size_t raCap = 0;
+    cudaEvent_t raEv[2] = {nullptr, nullptr};
     bool fdBatch = false;  // the tables hold the forward-difference batch [p, p + h e_0, ..]: vectors beyond 3 (n - 1) perturb translations only
 
     // set construction
@@ -423,6 +427,51 @@ __global__ void k_bundle_scatter(const double* __restrict__ hg, int Pl, const in
 __global__ void k_bundle_gather_step(const double* __restrict__ gstep, const int* __restrict__ idx, int Pl, double* __restrict__ step) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < Pl) step[i] = gstep[idx[i]];
+}
+// The tail of one loop body on the device (DmsaOptimizer.h:113-143, 152-182): line-search winner, parameter update, stop tests.
+// rec = the iteration's read-back block: [0, 9) trial costs | 9 best k | 10 stop code | 11 ||step|| | [16, 16 + P) step |
+// 16 + P err0 | 16 + P + 1 NaN flag | then P new parameters | P parameters of the last trial point.  d_p is advanced in
+// place, so the next loop body can be enqueued before the host has seen this one.  The expressions are the host's
+// (iterationImpl), operation for operation.
+__global__ void k_iter_decide(double* __restrict__ rec, double* __restrict__ p, int P, double epsilon) {
+    __shared__ int s_best;
+    const double* step = rec + 16;
+    const double err0 = rec[16 + P];
+    const bool nan = rec[16 + P + 1] != 0.0;
+    if (threadIdx.x == 0) {
+        double minError = err0;
+        int best = 0;
+        for (int k = 1; k < 10; ++k)
+            if (rec[k - 1] < minError) {
+                minError = rec[k - 1];
+                best = k;
+            }
+        double nrm = 0;
+        for (int i = 0; i < P; ++i) nrm += step[i] * step[i];
+        nrm = sqrt(nrm);
+        int stop = DMSA_B200_STOP_MAX_ITER;
+        if (nan)
+            stop = DMSA_B200_STOP_NAN;
+        else if (best == 0)
+            stop = DMSA_B200_STOP_NO_IMPROVEMENT;
+        else if (nrm < epsilon)
+            stop = DMSA_B200_STOP_EPSILON;
+        s_best = best;
+        rec[9] = (double)best;
+        rec[10] = (double)stop;
+        rec[11] = nrm;
+    }
+    __syncthreads();
+    const int best = s_best;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const double pv = p[i];
+        const double plast = pv + 0.1 * 9.0 * step[i];
+        double pnew = pv;
+        if (!nan) pnew = best == 0 ? plast : pv + 0.1 * (double)best * step[i];
+        rec[16 + P + 2 + i] = pnew;
+        rec[16 + 2 * P + 2 + i] = plast;
+        p[i] = pnew;
+    }
 }
 __global__ void k_add9(const double* __restrict__ src, double* __restrict__ dst) {
     if (threadIdx.x < 9) dst[threadIdx.x] += src[threadIdx.x];
@@ -1459,6 +1508,9 @@ void dmsa_b200_destroy(dmsa_b200_ctx* ctx) {
     REL(p_linfo); REL(p_keys); REL(p_bb); REL(p_idx); REL(p_sidx); REL(p_scan); REL(p_raw_start); REL(p_raw_diff); REL(p_pick); REL(p_flag); REL(p_pos); REL(p_rand); REL(p_nn); REL(p_code); REL(p_scode); REL(p_ctl); REL(p_raw); REL(p_out); REL(p_pts); REL(p_cloud); REL(p_range); REL(d_mom); REL(d_solve); REL(d_iter); REL(d_chol);
 #undef REL
     if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->raPin) cudaFreeHost(ctx->raPin);
+    for (cudaEvent_t e : ctx->raEv)
+        if (e) cudaEventDestroy(e);
     if (ctx->evUpload) cudaEventDestroy(ctx->evUpload);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -2072,6 +2124,34 @@ int dmsa_b200_iteration(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, 
     return rc;
 }
 
+}  // extern "C"
+namespace {
+// One loop body enqueued without any host synchronisation (device LM solver, deferred set build, winner / update / stop
+// tests by k_iter_decide), its read-back block copied to `slot` of the pinned ring.  upload: d_p <- the host's parameters
+// (first run-ahead body); otherwise d_p is what the previous body's k_iter_decide left.
+int enqueueBody(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, bool upload, double* slot, cudaEvent_t done) {
+    const size_t recN = 16 + 3 * (size_t)P + 2;
+    if (upload) CKRC(uploadParams(ctx));
+    CKRC(prepareFdBatch(ctx));
+    CKRC(transformBase(ctx));
+    CKRC(buildSets(ctx, st, true));
+    if (ctx->G >= 0) ARGFAIL("optimize: the run-ahead loop needs a deferred set build");
+    CKRC(runCost(ctx));
+    CKRC(jtjInto(ctx, ctx->d_hg.p));
+    CKRC(allReduceSum(ctx, ctx->d_hg.p, (size_t)P * P + P + 1));
+    CKRC(lmSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
+    CKRC(lineSearchDev(ctx, ctx->d_iter.p));
+    CKRC(allReduceSum(ctx, ctx->d_iter.p, 9));
+    LAUNCH(k_iter_decide, 1, 128, 0, ctx->d_iter.p, ctx->d_p.p, P, st->epsilon);
+    CK(cudaMemcpyAsync(slot, ctx->d_iter.p, recN * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(slot + recN, ctx->d_linfo.p, 2 * sizeof(LevelInfo), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(done, ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+extern "C" {
+
 int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, dmsa_b200_report* report) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->model == MODEL_NONE) ARGFAIL("optimize: no model staged");
@@ -2080,12 +2160,112 @@ int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, d
     if (settings->use_centralization) CKRC(dmsa_b200_centralize(ctx));  // :66-67
     int it = 0;
     int32_t stop = DMSA_B200_STOP_MAX_ITER;
+    const int P = 6 * (ctx->poses.n - 1);
+    // Run-ahead loop (device LM solver only): body i + 1 is enqueued before the host has read body i's results, so the GPU
+    // never waits for the host between bodies.  The host consumes the read-back blocks one body late and keeps the
+    // reference's pose bookkeeping (staleGlobal); a body that ran past a stop condition is discarded.
+    const bool runAhead = ctx->runAhead && ctx->solverMode == 0 && P > 0 && P <= LM_DEV_MAXN && !ctx->profiling && settings->num_iter >= 3;
+    if (runAhead) {
+        // body 0 takes the synchronous path (its set build has no size guess yet)
+        CKRC(iterationImpl(ctx, settings, &stop, &rep, nullptr, nullptr));
+        it = 1;
+        const size_t recN = 16 + 3 * (size_t)P + 2;
+        const size_t slotBytes = recN * sizeof(double) + 2 * sizeof(LevelInfo);
+        if (stop == DMSA_B200_STOP_MAX_ITER && it < settings->num_iter) {
+            if (ctx->raCap < 2 * slotBytes) {
+                if (ctx->raPin) cudaFreeHost(ctx->raPin);
+                ctx->raPin = nullptr;
+                CK(cudaHostAlloc((void**)&ctx->raPin, 2 * slotBytes, cudaHostAllocDefault));
+                ctx->raCap = 2 * slotBytes;
+            }
+            for (int k = 0; k < 2; ++k)
+                if (!ctx->raEv[k]) CK(cudaEventCreateWithFlags(&ctx->raEv[k], cudaEventDisableTiming));
+            CK(ctx->d_hg.ensure((size_t)P * P + P + 1));
+            CK(ctx->d_iter.ensure(recN + 8));
+            auto slotPtr = [&](int b) { return reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(ctx->raPin) + (size_t)(b & 1) * slotBytes); };
+            int enq = it;  // next body to enqueue
+            ctx->poses.relative2global();
+            CKRC(enqueueBody(ctx, settings, P, true, slotPtr(enq), ctx->raEv[enq & 1]));
+            ++enq;
+            bool fallback = false;
+            while (it < settings->num_iter) {
+                if (enq < settings->num_iter && enq == it + 1) {  // keep one body in flight behind the one being consumed
+                    CKRC(enqueueBody(ctx, settings, P, false, slotPtr(enq), ctx->raEv[enq & 1]));
+                    ++enq;
+                }
+                CK(cudaEventSynchronize(ctx->raEv[it & 1]));
+                const double* r = slotPtr(it);
+                LevelInfo li[2];
+                memcpy(li, r + recN, 2 * sizeof(LevelInfo));
+                // late verification of the guesses the deferred build ran on (octree depth, set count)
+                int G = 0;
+                bool miss = false;
+                for (int l = 0; l < 2; ++l) {
+                    if (!ctx->levelOn[l]) continue;
+                    if (li[l].error) ARGFAIL("build_sets: octree deeper than 21 levels (extent / resolution too large)");
+                    if (li[l].depth > ctx->cachedDepth[l]) miss = true;
+                    G += li[l].G;
+                }
+                if (G > ctx->cellCap) ARGFAIL("build_sets: Gaussian store capacity exceeded");
+                if (G > std::max(li[0].bound, li[1].bound)) miss = true;
+                if (miss) {  // redo this body (and the rest) on the synchronous path; the host state has not been touched by it
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    for (int l = 0; l < 2; ++l)
+                        if (ctx->levelOn[l]) ctx->cachedDepth[l] = std::max(ctx->cachedDepth[l], li[l].depth);
+                    fallback = true;
+                    break;
+                }
+                for (int l = 0; l < 2; ++l)
+                    if (ctx->levelOn[l]) ctx->cachedDepth[l] = li[l].depth;
+                ctx->Gguess = std::max(G, 1);
+                memcpy(ctx->h_linfo, li, sizeof(li));
+                rep.num_gaussians = G;
+                rep.num_extra = numExtra(ctx);
+                ++it;
+                if (G < settings->min_num_gaussians) {  // :89-93
+                    stop = DMSA_B200_STOP_FEW_GAUSSIANS;
+                    break;
+                }
+                const double error0 = r[16 + P];
+                ctx->lastErr0 = error0;
+                const int code = (int)r[10];
+                rep.error0 = error0;
+                if (code == DMSA_B200_STOP_NAN) {  // :113-122
+                    std::vector<double> cur;
+                    ctx->poses.getParams(cur);
+                    std::vector<double> plast = cur;
+                    plast[P - 1] += 1.0 * (double)sqrtf(FLT_EPSILON);
+                    staleGlobal(ctx, plast.data(), cur.data());
+                    stop = DMSA_B200_STOP_NAN;
+                    break;
+                }
+                rep.best_step = (int)r[9];
+                rep.step_norm = r[11];
+                staleGlobal(ctx, r + 16 + 2 * P + 2, r + 16 + P + 2);  // (last trial point, accepted parameters)
+                if (code != DMSA_B200_STOP_MAX_ITER) {
+                    stop = code;
+                    break;
+                }
+            }
+            ctx->G = rep.num_gaussians;
+            if (fallback) {
+                for (; it < settings->num_iter; ++it) {
+                    CKRC(iterationImpl(ctx, settings, &stop, &rep, nullptr, nullptr));
+                    if (stop != DMSA_B200_STOP_MAX_ITER) {
+                        ++it;
+                        break;
+                    }
+                }
+            }
+        }
+    } else {
     for (; it < settings->num_iter; ++it) {  // :69
         CKRC(iterationImpl(ctx, settings, &stop, &rep, nullptr, nullptr));
         if (stop != DMSA_B200_STOP_MAX_ITER) {
             ++it;
             break;
         }
+    }
     }
     if (settings->use_centralization) CKRC(dmsa_b200_decentralize(ctx));  // :146-147
     CKRC(updateGlobalPointsImpl(ctx));                                     // :149
@@ -2145,6 +2325,12 @@ int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode) {
     return 0;
 }
 
+// dmsa_b200_optimize: 1 (default) run-ahead loop — body i + 1 is enqueued before the host reads body i's results; 0: one
+// body at a time.  Same results bit for bit.
+int dmsa_b200_set_run_ahead(dmsa_b200_ctx* ctx, int32_t on) {
+    ctx->runAhead = on != 0;
+    return 0;
+}
 // Cost kernels of the forward-difference batch: 1 (default) pair-packed FP32x2 kernels, 0 scalar kernels (bit-identical).
 int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode) {
     if (mode < 0 || mode > 2) ARGFAIL("set_pair_mode: 1 (pair-packed with the shared-rotation fast path, default), 2 (pair-packed, every vector in full) or 0 (scalar)");

@@ -20,9 +20,17 @@ namespace dmsa {
 
 #define DMSA_KEYS_BLOCK 256
 
+#ifdef DMSA_ALLOW_FMA
+// EXPERIMENT ONLY (scripts/fma_deviation.py builds a second library with -fmad=true): plain operators, so that the compiler
+// contracts a * b + c into FFMA — the measurement of what fusing would do to H and g (profiles/r02_fma_deviation.json).
+__device__ __forceinline__ float fmul_(float a, float b) { return a * b; }
+__device__ __forceinline__ float fadd_(float a, float b) { return a + b; }
+__device__ __forceinline__ float fsub_(float a, float b) { return a - b; }
+#else
 __device__ __forceinline__ float fmul_(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fadd_(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub_(float a, float b) { return __fsub_rn(a, b); }
+#endif
 __device__ __forceinline__ float fdiv_(float a, float b) { return __fdiv_rn(a, b); }
 
 struct LevelInfo {

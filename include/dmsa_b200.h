@@ -258,6 +258,11 @@ int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode);
  * their table rows carry the same rotation bits), 2 = pair-packed, every vector evaluated in full, 0 = one vector per
  * thread.  Same rounding sequence per value: bit-identical results in all three modes. */
 int dmsa_b200_set_pair_mode(dmsa_b200_ctx* ctx, int32_t mode);
+/* dmsa_b200_optimize with the device LM solver: 1 (default) = run-ahead loop (loop body i + 1 is enqueued before the host has
+ * read body i's results: winner, parameter update and stop tests of DmsaOptimizer.h:113-143 run on the device, the host
+ * consumes the read-back blocks one body late; a body that ran past a stop condition is discarded), 0 = one body at a time.
+ * Bit-identical results. */
+int dmsa_b200_set_run_ahead(dmsa_b200_ctx* ctx, int32_t on);
 /* The device LM step on a HOST copy of [H | g | err0] (n_params <= 1024); validation twin of dmsa_b200_lm_solve(.., 1, ..). */
 int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, const double* hg, int32_t n_params, double* step,
                               int32_t* has_nan);

@@ -889,3 +889,27 @@ def test_keyframe_bundles_partial_systems_add_up_and_iterate():
     again = KeyframeBundleOptimizer(sm, s, bundle_size=5, overlap=3)
     d2 = again.iteration()
     assert d2["error0"] == d1["error0"] and np.array_equal(d1["step"], d2["step"]) and np.array_equal(again.p, whole.p)
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_run_ahead_optimize_equals_the_body_by_body_loop_bitwise(name):
+    """dmsa_b200_optimize enqueues loop body i + 1 before the host has read body i (winner, parameter update and stop tests on
+    the device, k_iter_decide).  Poses, report and stop behaviour must equal the loop that synchronises after every body."""
+    win = synth.make_config(name)
+    base = dict(CASES["cfg1"])
+    cases = [dict(base, num_iter=6), dict(base, num_iter=5, epsilon=1e9),  # epsilon stop after the first body
+             dict(base, num_iter=4, step_length_optim=500.0, max_step=50.0),  # no improvement: stays at p + 0.9 step
+             dict(base, num_iter=3, min_num_gaussians=10**7)]  # too few Gaussians
+    for st in cases:
+        out = []
+        for ahead in (1, 0):
+            traj = ContinuousTrajectory.from_window(win)
+            traj.setRunAhead(ahead)
+            rep = DmsaOptimizer().optimizeSet(traj, DmsaOptimSettings(**st))
+            out.append((rep, traj.getPoses(), traj.globalPoints()))
+        (ra, pa, wa), (rb, pb, wb) = out
+        assert ra["iterations"] == rb["iterations"] and ra["stop_reason"] == rb["stop_reason"], (st, ra, rb)
+        assert ra["num_gaussians"] == rb["num_gaussians"] and ra["error0"] == rb["error0"] and ra["best_step"] == rb["best_step"]
+        for k in ("rel_orient", "rel_transl", "glob_orient", "glob_transl"):
+            assert np.array_equal(pa[k], pb[k]), (st, k)
+        assert np.array_equal(wa, wb)
