@@ -158,6 +158,7 @@ def load_library():
         "dmsa_b200_estimate_normals": (i32, [vp, vp, i64, vp, C.c_float, vp]),
         "dmsa_b200_pc2_layout_for_sensor": (i32, [C.c_char_p, vp, i32, i32, P(Pc2Layout)]),
         "dmsa_b200_decode_pointcloud2": (i32, [vp, vp, i64, P(Pc2Layout), f64, f64, vp]),
+        "dmsa_b200_relative2global": (i32, [i32, vp, vp, vp, vp]),
         "dmsa_b200_format_tum_pose": (i32, [f64, vp, vp, C.c_char_p, i32]),
         "dmsa_b200_save_pcd_ascii": (i32, [C.c_char_p, vp, i64]),
         "dmsa_b200_select_static_points": (i32, [vp, vp, i64, vp, C.c_float, vp, P(i64)]),
@@ -184,7 +185,7 @@ EXPORTED_SYMBOLS = [
     "dmsa_b200_set_mean_mode", "dmsa_b200_profile_enable", "dmsa_b200_profile_num", "dmsa_b200_profile_name", "dmsa_b200_profile_read",
     "dmsa_b200_set_shard", "dmsa_b200_cost_jacobian_dev", "dmsa_b200_line_search_costs_dev", "dmsa_b200_lm_solve",
     "dmsa_b200_set_lm_solver", "dmsa_b200_lm_solve_device", "dmsa_b200_set_pair_mode", "dmsa_b200_get_batch_tables",
-    "dmsa_b200_pc2_layout_for_sensor", "dmsa_b200_decode_pointcloud2", "dmsa_b200_format_tum_pose", "dmsa_b200_save_pcd_ascii",
+    "dmsa_b200_relative2global", "dmsa_b200_pc2_layout_for_sensor", "dmsa_b200_decode_pointcloud2", "dmsa_b200_format_tum_pose", "dmsa_b200_save_pcd_ascii",
     "dmsa_b200_set_run_ahead", "dmsa_b200_rand_sequence", "dmsa_b200_grid_downsample", "dmsa_b200_downsample_global_points", "dmsa_b200_preprocess_scan", "dmsa_b200_estimate_normals",
     "dmsa_b200_select_static_points", "dmsa_b200_overlap", "dmsa_b200_traj_init_window", "dmsa_b200_traj_get_dense_poses",
     "dmsa_b200_spd_solve_dev", "dmsa_b200_spd_solve", "dmsa_b200_bundle_jacobian", "dmsa_b200_bundle_line_search", "dmsa_b200_bundle_verify",
@@ -683,6 +684,16 @@ def decode_pointcloud2(ctx, data, n_points, layout, stamp_msg, delta_t=0.0):
     out = np.zeros(int(n_points), dtype=POINT_STAMP_ID)
     ctx._ck(ctx.L.dmsa_b200_decode_pointcloud2(ctx.h, _p(buf), int(n_points), C.byref(layout), float(stamp_msg), float(delta_t), _p(out)))
     return out
+
+
+def relative2global(rel_orient, rel_transl):
+    """ConsecutivePoses.h:26-43 on 3 x n arrays (columns = poses) -> (global orientations, global translations)."""
+    L = load_library()
+    ro, rt = _c64(np.asarray(rel_orient).T), _c64(np.asarray(rel_transl).T)  # n x 3 row-major == 3 x n column-major
+    go, gt = np.zeros_like(ro), np.zeros_like(rt)
+    if L.dmsa_b200_relative2global(len(ro), _p(ro), _p(rt), _p(go), _p(gt)):
+        raise DmsaError("relative2global failed")
+    return np.ascontiguousarray(go.T), np.ascontiguousarray(gt.T)
 
 
 def format_tum_pose(stamp, pos, orient):

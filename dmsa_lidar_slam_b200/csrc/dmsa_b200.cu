@@ -2489,7 +2489,7 @@ int dmsa_b200_spd_solve_dev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, co
     if (!st || !hg_dev || !step_dev || !tail_dev || n <= 0 || n > CHOL_MAXN) ARGFAIL("spd_solve_dev: bad arguments (1 <= n <= 1024)");
     CK(cudaSetDevice(ctx->device));
     const int ld = pad32(n);
-    CK(ctx->d_chol.ensure((size_t)(n + 1) * ld + 8));
+    CK(ctx->d_chol.ensure((size_t)(n + 1) * ld + 8 + ld));
     CholArgs q;
     q.hg = hg_dev;
     q.n = n;
@@ -2502,10 +2502,11 @@ int dmsa_b200_spd_solve_dev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, co
     q.step2 = nullptr;
     q.tail = tail_dev;
     q.flag = reinterpret_cast<int*>(ctx->d_chol.p + (size_t)(n + 1) * ld);
+    q.dinv = ctx->d_chol.p + (size_t)(n + 1) * ld + 8;
     int nsm = 0;
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
     const int tiles = ((n + 31) / 32) * ((n + 31) / 32 + 1) / 2;
-    const unsigned grid = (unsigned)std::max(1, std::min(std::min(nsm, 64), tiles));
+    const unsigned grid = (unsigned)std::max(1, std::min(nsm, tiles));  // one trailing-update round per block column where possible
     void* args[] = {&q};
     ProfScope prof_(ctx, PROF_LM_SOLVE);
     CK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_T), args, 0, ctx->stream));

@@ -174,3 +174,17 @@ int dmsa_b200_save_pcd_ascii(const char* filename, const dmsa_b200_point_normal*
     }
     return fclose(f) == 0 ? 0 : -1;
 }
+
+// ConsecutivePoses.h:26-43 relative2global on plain arrays (3 x n column-major doubles; host only, no context): the pose chain
+// the bundle driver needs once per iteration to place every bundle's first keyframe.
+int dmsa_b200_relative2global(int32_t n, const double* rel_orient, const double* rel_transl, double* glob_orient, double* glob_transl) {
+    if (n <= 0 || !rel_orient || !rel_transl || !glob_orient || !glob_transl) return DMSA_B200_ERR_ARG;
+    HostPoses hp;
+    hp.resize(n);
+    std::copy(rel_orient, rel_orient + 3 * (size_t)n, hp.relO.begin());
+    std::copy(rel_transl, rel_transl + 3 * (size_t)n, hp.relT.begin());
+    hp.relative2global();
+    std::copy(hp.globO.begin(), hp.globO.end(), glob_orient);
+    std::copy(hp.globT.begin(), hp.globT.end(), glob_transl);
+    return 0;
+}

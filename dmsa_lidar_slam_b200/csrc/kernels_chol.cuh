@@ -12,6 +12,8 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include "kernels_sort.cuh"  // DMSA_TLK (development time stamps)
+
 namespace dmsa {
 
 #define CHOL_B 32
@@ -27,32 +29,56 @@ struct CholArgs {
     double* step2;     // out [n] second copy (may be null)
     double* tail;      // out [0] = err0, [1] = 0 ok / 1 NaN step / 2 not positive definite (caller falls back)
     int* flag;         // device scratch (1 int, zeroed by the kernel)
+    double* dinv;      // device scratch [ld]: reciprocals of the factor's diagonal
 };
 
 // 32 x 32 diagonal block at W[j0.., j0..] -> its Cholesky factor in place (one warp; lane = row).  nb = valid rows (<= 32).
-__device__ __forceinline__ void chol_diag_block(double* __restrict__ Wjj, int ld, int nb, int lane, int* flag) {
+// dinv[c] = 1 / L[c][c] for the substitutions that follow.  The square root and the division of the textbook step are ONE
+// reciprocal square root (l = d * rsqrt(d)): the two IEEE sequences were 90 % of this function's 30 us (measured with the
+// phase stamps of scripts/dbg_chol_timeline.py); the bundle scheme has no reference arithmetic to mirror, only determinism.
+__device__ __noinline__ void chol_diag_block(double* __restrict__ Wjj, int ld, int nb, int lane, int* flag, double* __restrict__ dinv,
+                                             double* __restrict__ sL /* shared, CHOL_B doubles */) {
     double a[CHOL_B];
 #pragma unroll
     for (int c = 0; c < CHOL_B; ++c) a[c] = (lane < nb && c <= lane) ? Wjj[(size_t)lane * ld + c] : (c == lane ? 1.0 : 0.0);
     bool bad = false;
+    double myinv = 1.0;
 #pragma unroll
     for (int c = 0; c < CHOL_B; ++c) {
         const double d = __shfl_sync(0xffffffffu, a[c], c);
         if (!(d > 0.0)) bad = true;
-        const double l = sqrt(d);
-        const double inv = 1.0 / l;
-        if (lane == c) a[c] = l;
-        if (lane > c) a[c] = a[c] * inv;
-#pragma unroll
-        for (int c2 = c + 1; c2 < CHOL_B; ++c2) {
-            const double v = __shfl_sync(0xffffffffu, a[c], c2);
-            if (lane >= c2) a[c2] = fma(-a[c], v, a[c2]);
+        const double inv = rsqrt(d);
+        if (lane == c) {
+            a[c] = d * inv;
+            myinv = inv;
         }
+        if (lane > c) a[c] = a[c] * inv;
+        sL[lane] = a[c];  // column c of the factor (rows above the diagonal hold zeros / the unit padding)
+        __syncwarp();
+#pragma unroll
+        for (int c2 = c + 1; c2 < CHOL_B; ++c2)
+            if (lane >= c2) a[c2] = fma(-a[c], sL[c2], a[c2]);
+        __syncwarp();
     }
     if (bad && lane == 0) *flag = 2;
+    if (lane < nb) dinv[lane] = myinv;
 #pragma unroll
     for (int c = 0; c < CHOL_B; ++c)
         if (lane < nb && c <= lane) Wjj[(size_t)lane * ld + c] = a[c];
+}
+
+// one row of the block column below a diagonal block, by ONE WARP: x L_jj^T = w with lane k owning x[k]; per step the
+// finished x[c] is broadcast and every later lane takes its term (32 short steps; one thread per row walked 496 dependent
+// multiply-adds and took 14 us per block column)
+__device__ __forceinline__ void chol_panel_row_warp(double* __restrict__ wr, int nbj, const double (*sA)[CHOL_B + 1], const double* sInv, int lane) {
+    double x = lane < nbj ? wr[lane] : 0.0;
+#pragma unroll
+    for (int c = 0; c < CHOL_B; ++c) {
+        const double xc = __shfl_sync(0xffffffffu, x, c) * sInv[c];
+        if (lane == c) x = xc;
+        if (lane > c) x = fma(-xc, sA[lane][c], x);
+    }
+    if (lane < nbj) wr[lane] = x;
 }
 
 __global__ void __launch_bounds__(CHOL_T, 1) k_chol_solve(CholArgs q) {
@@ -76,40 +102,34 @@ __global__ void __launch_bounds__(CHOL_T, 1) k_chol_solve(CholArgs q) {
         }
         W[(size_t)i * ld + j] = v;
     }
+    DMSA_TLK(3, 0);
     if (gtid == 0) *q.flag = 0;
     grid.sync();
+    DMSA_TLK(3, 1);
     const int nblk = (n + CHOL_B - 1) / CHOL_B;
     const int nrows = n + 1;  // the right-hand side is row n
     for (int jb = 0; jb < nblk; ++jb) {
         const int j0 = jb * CHOL_B, nbj = min(CHOL_B, n - j0);
         // (1) diagonal block
-        if (blockIdx.x == 0 && warp == 0) chol_diag_block(W + (size_t)j0 * ld + j0, ld, nbj, lane, q.flag);
+        if (blockIdx.x == 0 && warp == 0) chol_diag_block(W + (size_t)j0 * ld + j0, ld, nbj, lane, q.flag, q.dinv + j0, &sB[0][0]);
+        if (jb == 0) DMSA_TLK(3, 2);
         grid.sync();
-        // (2) rows below (and the right-hand-side row): x L_jj^T = w  ->  forward substitution along the row, one thread per row
+        if (jb == 0) DMSA_TLK(3, 3);
+        // (2) rows below (and the right-hand-side row): x L_jj^T = w, one thread per row, right-looking (as soon as x[c] is known
+        // every later entry takes its term: 32 short dependent steps instead of a chain of 496 multiply-adds and 32 divisions)
         {
+            __shared__ double sInv[CHOL_B];
             for (int e = tid; e < CHOL_B * CHOL_B; e += CHOL_T) {
                 const int r = e / CHOL_B, c = e - r * CHOL_B;
-                sA[r][c] = (r < nbj && c <= r) ? W[(size_t)(j0 + r) * ld + j0 + c] : (r == c ? 1.0 : 0.0);
+                sA[r][c] = (r < nbj && c <= r) ? W[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
             }
+            if (tid < CHOL_B) sInv[tid] = tid < nbj ? q.dinv[j0 + tid] : 1.0;
             __syncthreads();
             const int r0 = j0 + nbj;  // first row below the diagonal block
-            for (int r = r0 + gtid; r < nrows; r += gthreads) {
-                double* __restrict__ wr = W + (size_t)r * ld + j0;
-                double x[CHOL_B];
-#pragma unroll
-                for (int c = 0; c < CHOL_B; ++c) x[c] = (c < nbj) ? wr[c] : 0.0;
-#pragma unroll
-                for (int c = 0; c < CHOL_B; ++c) {
-                    double s = x[c];
-#pragma unroll
-                    for (int k = 0; k < c; ++k) s = fma(-x[k], sA[c][k], s);
-                    x[c] = s / sA[c][c];
-                }
-#pragma unroll
-                for (int c = 0; c < CHOL_B; ++c)
-                    if (c < nbj) wr[c] = x[c];
-            }
+            const int gwarp = blockIdx.x * (CHOL_T / 32) + warp, gwarps = gridDim.x * (CHOL_T / 32);
+            for (int r = r0 + gwarp; r < nrows; r += gwarps) chol_panel_row_warp(W + (size_t)r * ld + j0, nbj, sA, sInv, lane);
         }
+        if (jb == 0) DMSA_TLK(3, 4);
         grid.sync();
         // (3) trailing update: W[bi][bk] -= W[bi][jb] W[bk][jb]^T for jb < bk <= bi (row blocks run to row n)
         {
@@ -152,8 +172,10 @@ __global__ void __launch_bounds__(CHOL_T, 1) k_chol_solve(CholArgs q) {
                 }
             }
         }
+        if (jb == 0) DMSA_TLK(3, 5);
         grid.sync();
     }
+    DMSA_TLK(3, 6);
     if (blockIdx.x != 0) return;
     // back substitution L^T x = y (y = row n), block-wise from the bottom: one block
     for (int i = tid; i < n; i += CHOL_T) sx[i] = W[(size_t)n * ld + i];
@@ -161,21 +183,30 @@ __global__ void __launch_bounds__(CHOL_T, 1) k_chol_solve(CholArgs q) {
     __syncthreads();
     for (int jb = nblk - 1; jb >= 0; --jb) {
         const int j0 = jb * CHOL_B, nbj = min(CHOL_B, n - j0);
+        for (int e = tid; e < CHOL_B * CHOL_B; e += CHOL_T) {  // the diagonal block, coalesced
+            const int r = e / CHOL_B, c = e - r * CHOL_B;
+            sA[r][c] = (r < nbj && c <= r) ? W[(size_t)(j0 + r) * ld + j0 + c] : 0.0;
+        }
+        __syncthreads();
         if (warp == 0) {  // 32 x 32 triangular solve L_jj^T x_j = rhs_j: column-oriented, descending
             double xv = lane < nbj ? sx[j0 + lane] : 0.0;
+            const double myinv = lane < nbj ? q.dinv[j0 + lane] : 1.0;
             for (int c = nbj - 1; c >= 0; --c) {
-                const double lcc = W[(size_t)(j0 + c) * ld + j0 + c];
-                double xc = __shfl_sync(0xffffffffu, xv, c) / lcc;
+                const double xc = __shfl_sync(0xffffffffu, xv, c) * __shfl_sync(0xffffffffu, myinv, c);
                 if (lane == c) xv = xc;
-                if (lane < c) xv = fma(-W[(size_t)(j0 + c) * ld + j0 + lane], xc, xv);
+                if (lane < c) xv = fma(-sA[c][lane], xc, xv);
             }
             if (lane < nbj) sx[j0 + lane] = xv;
         }
         __syncthreads();
-        // rhs_k -= sum_c L[j0 + c][k] x[j0 + c] for k < j0
+        // rhs_k -= sum_c L[j0 + c][k] x[j0 + c] for k < j0 (32 independent coalesced loads per thread)
         for (int k = tid; k < j0; k += CHOL_T) {
+            double lv[CHOL_B];
+#pragma unroll
+            for (int c = 0; c < CHOL_B; ++c) lv[c] = c < nbj ? W[(size_t)(j0 + c) * ld + k] : 0.0;
             double s = sx[k];
-            for (int c = 0; c < nbj; ++c) s = fma(-W[(size_t)(j0 + c) * ld + k], sx[j0 + c], s);
+#pragma unroll
+            for (int c = 0; c < CHOL_B; ++c) s = fma(-lv[c], sx[j0 + c < n ? j0 + c : j0], s);
             sx[k] = s;
         }
         __syncthreads();
@@ -212,6 +243,7 @@ __global__ void __launch_bounds__(CHOL_T, 1) k_chol_solve(CholArgs q) {
         q.step[i] = s;
         if (q.step2) q.step2[i] = s;
     }
+    DMSA_TLK(3, 7);
     if (tid == 0) {
         q.tail[0] = q.hg[(size_t)n * n + n];
         q.tail[1] = (*q.flag == 2) ? 2.0 : (nan ? 1.0 : 0.0);

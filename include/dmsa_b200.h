@@ -330,6 +330,8 @@ int dmsa_b200_pc2_layout_for_sensor(const char* sensor, const int32_t* field_off
  * msg->header.stamp.toSec(), delta_t = stampMsg - lastPcMsgStamp (only read for DMSA_B200_STAMP_NONE) */
 int dmsa_b200_decode_pointcloud2(dmsa_b200_ctx* ctx, const uint8_t* data, int64_t n_points, const dmsa_b200_pc2_layout* layout, double stamp_msg,
                                  double delta_t, dmsa_b200_point_stamp_id* out);
+/* ConsecutivePoses::relative2global (ConsecutivePoses.h:26-43) on 3 x n column-major arrays (host only, no context) */
+int dmsa_b200_relative2global(int32_t n, const double* rel_orient, const double* rel_transl, double* glob_orient, double* glob_transl);
 /* addPoseToFile (OutputManagement.h:80-96): one line of the TUM trajectory file; returns the length, -1 if buf is too small */
 int dmsa_b200_format_tum_pose(double stamp, const double* pos /*3*/, const double* orient /*3, axis-angle*/, char* buf, int32_t buf_size);
 /* pcl::io::savePCDFileASCII of a pcl::PointNormal cloud (src/dmsa_slam_ros.cpp:286-291); 0 on success, -1 on I/O failure */

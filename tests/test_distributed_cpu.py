@@ -122,3 +122,16 @@ def test_row_sharded_iteration_over_gloo(tmp_path):
     np.testing.assert_allclose(r["step"], tr["step"], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(r["ls"], tr["ls_cost"], rtol=1e-8)
     assert int(r["best"]) == tr["best_k"]
+
+
+def test_library_pose_chain_matches_the_scipy_chain():
+    """The bundle driver places every bundle's first keyframe with the library's host pose chain (ConsecutivePoses.h:26-43);
+    scipy's rotation algebra is the independent check."""
+    import numpy as np
+
+    from dmsa_lidar_slam_b200 import distributed as d
+
+    rng = np.random.default_rng(4)
+    ro, rt = rng.normal(0, 0.4, (3, 64)), rng.normal(0, 2.0, (3, 64))
+    a, b = d.relative2global(ro, rt), d.relative2global_scipy(ro, rt)
+    assert np.abs(a[0] - b[0]).max() < 1e-12 and np.abs(a[1] - b[1]).max() < 1e-11
