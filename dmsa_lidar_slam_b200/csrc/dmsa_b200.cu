@@ -891,13 +891,13 @@ phase2:
                 int* nbox = ctx->d_split_nbox.p + 6 * N2 * l;
                 int* search = ctx->d_split_search.p + N2 * l;
                 LAUNCH_ON(strm, k_accept, cdiv(N, 256), 256, 0, raw_start, ga.raw_diff[s_], li, minPts, acc_flag, out_cnt, sub_start, sub_n, sub_code);
-                LAUNCH_ON(strm, k_split_nbox_init, cdiv(N2, 256), 256, 0, nbox, search, (int)N2);
+                LAUNCH_ON(strm, k_split_nbox_init, cdiv(N2, 256), 256, 0, nbox, search, (int)N2, li);
                 LAUNCH_ON(strm, k_split_nbox, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox);
                 LAUNCH_ON(strm, k_split_prefilter, cdiv(N, 256), 256, 0, sidx, scanA, acc_flag, li, ctx->d_normal_w.p, nbox, search);
                 LAUNCH_ON(strm, k_split_tile_counts, cdiv((size_t)N + 1, 256), 256, 0, raw_start, acc_flag, search, li, ntile);
                 CKRC(scanExclusive(ctx, strm, cl, 1 + s_, ntile, tile_off, N + 1));
                 LAUNCH_ON(strm, k_split_tile_fill, cdiv(N, 256), 256, 0, ntile, tile_off, li, tiles);
-                LAUNCH_ON(strm, k_split_pairs, (unsigned)tileBound, 256, 0, tiles, tile_off, li, raw_start, sidx, ctx->d_normal_w.p, best_v, best_i, best_j);
+                LAUNCH_ON(strm, k_split_pairs, (unsigned)std::min<size_t>(tileBound, 148 * 8), 256, 0, tiles, tile_off, li, raw_start, sidx, ctx->d_normal_w.p, best_v, best_i, best_j);
                 LAUNCH_ON(strm, k_split_decide, 148 * 8, 256, 0, acc_flag, ntile, tile_off, li, raw_start, sidx, scratch, ctx->d_normal_w.p, ctx->d_ring.p, best_v,
                           best_i, best_j, minPts, out_cnt, sub_start, sub_n, sub_code);
             }

@@ -461,9 +461,9 @@ __global__ void k_split_prefilter(const int* __restrict__ idx, const int* __rest
     if (!ok) search[c] = 1;
 }
 // nbox initial values: min slots = INT_MAX, max slots = INT_MIN
-__global__ void k_split_nbox_init(int* __restrict__ nbox, int* __restrict__ search, int n_cells) {
+__global__ void k_split_nbox_init(int* __restrict__ nbox, int* __restrict__ search, int n_cells, const LevelInfo* __restrict__ info) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_cells) return;
+    if (c >= n_cells || c > info->R) return;  // (only the leaves of this build)
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         nbox[6 * (size_t)c + a] = 2147483647;
@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(256) k_split_pairs(const SplitTile* __restrict
     __shared__ float rv[256];
     __shared__ int ri[256], rj[256];
     const int total = tile_off[info->R];
-    const int t = blockIdx.x;
-    if (t >= total) return;
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {  // persistent grid: the tile count lives on the device (block-uniform loop)
+    __syncthreads();
     const SplitTile tl = tiles[t];
     const int s = raw_start[tl.cell], n = raw_start[tl.cell + 1] - s;
     const int i1 = tl.i1_start + threadIdx.x;
@@ -513,9 +513,15 @@ __global__ void __launch_bounds__(256) k_split_pairs(const SplitTile* __restrict
         ay = a.y;
         az = a.z;
     }
+    // Two exact reductions of the reference's double loop over ordered pairs (Gaussians.h:33-52):
+    //  * ||n_a + n_b|| is bitwise symmetric in (a, b) (float addition commutes) and the first strict minimum in loop order is
+    //    the lexicographically smallest pair, so only the pairs a < b are visited;
+    //  * sqrt is monotone: a candidate whose squared length is not below the best one's cannot have a smaller norm, so the
+    //    square root is taken (and compared, strictly, like the reference's `<`) only for the few candidates that are.
     float bv = 3.402823466e+38f;  // std::numeric_limits<float>::max(), Gaussians.h:31
+    float bs = __int_as_float(0x7f800000);
     int bj = 0x7fffffff;
-    for (int j0 = 0; j0 < n; j0 += 256) {
+    for (int j0 = tl.i1_start; j0 < n; j0 += 256) {
         const int jj = j0 + threadIdx.x;
         if (jj < n) {
             const float4 b = normal_w[sidx[s + jj]];
@@ -526,14 +532,16 @@ __global__ void __launch_bounds__(256) k_split_pairs(const SplitTile* __restrict
         __syncthreads();
         const int lim = min(256, n - j0);
         if (i1 < n) {
-            for (int q = 0; q < lim; ++q) {
-                const int j = j0 + q;
-                if (j == i1) continue;  // id1 == id2
+            for (int q = (j0 == tl.i1_start ? (int)threadIdx.x + 1 : 0); q < lim; ++q) {
                 const float ux = fadd_(ax, sx[q]), uy = fadd_(ay, sy[q]), uz = fadd_(az, sz[q]);
-                const float v = __fsqrt_rn(fadd_(fmul_(ux, ux), fadd_(fmul_(uy, uy), fmul_(uz, uz))));  // (n1 + n2).norm()
-                if (v < bv) {
-                    bv = v;
-                    bj = j;
+                const float ss = fadd_(fmul_(ux, ux), fadd_(fmul_(uy, uy), fmul_(uz, uz)));  // (n1 + n2).squaredNorm()
+                if (ss < bs) {
+                    const float v = __fsqrt_rn(ss);  // .norm()
+                    if (v < bv) {
+                        bv = v;
+                        bs = ss;
+                        bj = j0 + q;
+                    }
                 }
             }
         }
@@ -558,6 +566,7 @@ __global__ void __launch_bounds__(256) k_split_pairs(const SplitTile* __restrict
         best_i[t] = ri[0];
         best_j[t] = rj[0];
     }
+  }
 }
 // One block per accepted leaf: reduce the tiles' winners; if min <= 0.5 split the members by the nearer reference normal
 // (stable partition of the leaf's range of sidx through `scratch`), ring test of the first half, the reference's two
