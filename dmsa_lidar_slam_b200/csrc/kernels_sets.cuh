@@ -6,11 +6,10 @@
 //            genOctreeKeyforPoint and the depth-first leaf iterator (third-party, restated from the published algorithm)
 //   Gaussians.h:130-168      addPointSet (covariance), :181-201 limitCovariance, :170-179 updateRebalancingWeights
 //
-// Pipeline per resolution level: anchor -> voxel keys (+ per-block key boxes) -> octree root growth replay ->
-// Morton codes (x most significant == PCL child index (x<<2)|(y<<1)|z) -> stable radix sort (members stay in
-// ascending point index) -> run heads -> ring test -> accept/compact -> gather member records -> per-set
-// covariance / eigen clamp / information matrix.  All of it streams the point set a constant number of times:
-// HBM-bandwidth bound.
+// Pipeline (both resolution levels per launch): anchor -> voxel keys (+ per-block key boxes) -> octree root growth replay ->
+// [kernels_sort.cuh: Morton codes (x most significant == PCL child index (x<<2)|(y<<1)|z) -> stable radix sort (members stay
+// in ascending point index) -> run heads / ring test -> accept / number / emit -> gather member records] -> per-set
+// covariance / eigen clamp / information matrix.  All of it streams the point set a constant number of times.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -320,57 +319,6 @@ __device__ __forceinline__ unsigned long long spread3(unsigned long long x) {  /
     return x;
 }
 
-// Morton code of (key - root origin): depth-first leaf order of the octree (x is the most significant axis)
-__global__ void k_morton(const int* __restrict__ keys, int N, const LevelInfo* __restrict__ info, unsigned long long* __restrict__ code,
-                         int* __restrict__ idx) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    int kx = keys[3 * (size_t)i], ky = keys[3 * (size_t)i + 1], kz = keys[3 * (size_t)i + 2];
-    unsigned long long m;
-    if (kx == (-2147483647 - 1)) {
-        m = 1ull << (3 * info->depth);  // non-finite points sort behind every leaf (PCL skips them)
-    } else {
-        unsigned long long x = (unsigned long long)((long long)kx - info->lo[0]);
-        unsigned long long y = (unsigned long long)((long long)ky - info->lo[1]);
-        unsigned long long z = (unsigned long long)((long long)kz - info->lo[2]);
-        m = (spread3(x) << 2) | (spread3(y) << 1) | spread3(z);
-    }
-    code[i] = m;
-    idx[i] = i;
-}
-
-__global__ void k_heads(const unsigned long long* __restrict__ code, int N, const LevelInfo* __restrict__ info, int* __restrict__ flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const unsigned long long inval = 1ull << (3 * info->depth);
-    unsigned long long m = code[i];
-    flag[i] = (m < inval) && (i == 0 || code[i - 1] != m) ? 1 : 0;
-}
-
-// scan = inclusive scan of flag.  Writes raw leaf starts, leaf count, finite count.
-__global__ void k_raw_starts(const unsigned long long* __restrict__ code, const int* __restrict__ flag, const int* __restrict__ scan, int N,
-                             LevelInfo* __restrict__ info, int* __restrict__ raw_start) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const unsigned long long inval = 1ull << (3 * info->depth);
-    const bool valid = code[i] < inval;
-    if (flag[i]) raw_start[scan[i] - 1] = i;
-    if (valid && (i == N - 1 || code[i + 1] >= inval)) {
-        info->n_valid = i + 1;
-        info->R = scan[i];
-        raw_start[scan[i]] = i + 1;
-    }
-}
-
-// DmsaOptimizer.h:303-307: max(ring) != min(ring)  <=>  some member's ring differs from the first member's
-__global__ void k_ring_diff(const int* __restrict__ idx, const int* __restrict__ scan, const int* __restrict__ raw_start, const int* __restrict__ ring,
-                            const LevelInfo* __restrict__ info, int* __restrict__ raw_diff) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= info->n_valid) return;
-    const int c = scan[i] - 1;
-    if (ring[idx[i]] != ring[idx[raw_start[c]]]) raw_diff[c] = 1;
-}
-
 // Acceptance of a leaf (DmsaOptimizer.h:307) and its default emission plan: one unsplit set.
 // out_cnt[c] in {0,1,2} sets are emitted for leaf c; sub_* describe them (2 slots per leaf).
 __global__ void k_accept(const int* __restrict__ raw_start, const int* __restrict__ raw_diff, const LevelInfo* __restrict__ info, int minPts,
@@ -675,50 +623,6 @@ struct CellStore {
     float* w0;    // (1/n) * observation weight
     float* w;     // rebalancing weight
 };
-
-// out_scan = exclusive scan of out_cnt.  prev: LevelInfo of the previous level (or null).
-__global__ void k_emit_cells(const int* __restrict__ raw_start, const int* __restrict__ out_cnt, const int* __restrict__ out_scan,
-                             const int* __restrict__ sub_start, const int* __restrict__ sub_n, const int* __restrict__ sub_code,
-                             const int* __restrict__ idx, const int* __restrict__ keys, LevelInfo* __restrict__ info,
-                             const LevelInfo* __restrict__ prev, int level, int mbase, CellStore cs, int cap) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int R = info->R;
-    const int gbase = prev ? prev->gbase + prev->G : 0;
-    if (c == 0) {
-        info->gbase = gbase;
-        info->G = R > 0 ? out_scan[R - 1] + out_cnt[R - 1] : 0;
-    }
-    if (c >= R) return;
-    const int cnt = out_cnt[c];
-    if (cnt == 0) return;
-    const int p = idx[raw_start[c]];
-    for (int e = 0; e < cnt; ++e) {
-        const int g = gbase + out_scan[c] + e;
-        if (g >= cap) return;
-        cs.start[g] = mbase + sub_start[2 * c + e];
-        cs.n[g] = sub_n[2 * c + e];
-        cs.level[g] = level;
-        cs.sub[g] = sub_code[2 * c + e];
-        cs.key[3 * g] = keys[3 * (size_t)p];
-        cs.key[3 * g + 1] = keys[3 * (size_t)p + 1];
-        cs.key[3 * g + 2] = keys[3 * (size_t)p + 2];
-    }
-}
-
-// Member records in sorted order: rec = (local xyz, transform-table row as int bits; static points -> identity row),
-// wrec = world xyz at the base pose (input of the covariance).
-__global__ void k_gather(const int* __restrict__ idx, const LevelInfo* __restrict__ info, const float4* __restrict__ local,
-                         const int* __restrict__ tid, int identity_row, const float4* __restrict__ world, float4* __restrict__ rec,
-                         float4* __restrict__ wrec) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= info->n_valid) return;
-    const int p = idx[i];
-    float4 l = local[p];
-    const int t = tid[p];
-    l.w = __int_as_float(t < 0 ? identity_row : t);  // static points: the table's identity row reproduces them exactly
-    rec[i] = l;
-    wrec[i] = world[p];
-}
 
 // cyclic Jacobi, symmetric 3x3, double
 __device__ inline void jacobi3(const double Ain[9], double l[3], double V[9]) {

@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(RS_T, 3) k_sort_pass(SortArgs a) {
 }
 
 // ---- chained scans ------------------------------------------------------------------------------------------------------
-// Status word of a tile: bits 62..63 flag (1 partial, 2 inclusive), payload below.  One warp looks back over 32 earlier
-// tiles per step.  `combine` semantics are supplied by the callers (sum, or sum | max packed in the payload).
+// Status word of a tile: bits 62..63 flag (1 partial, 2 inclusive), payload below.  `combine` semantics are supplied by the
+// callers (sum, or sum | max packed in the payload).
 #define CS_T 512
 #define CS_ITEMS 8
 #define CS_TILE (CS_T * CS_ITEMS)
@@ -344,47 +344,7 @@ __device__ __forceinline__ u64_t seg_combine(u64_t earlier, u64_t later) {
 }
 __device__ __forceinline__ u64_t sum_combine(u64_t a, u64_t b) { return a + b; }
 
-// exclusive prefix (over earlier tiles) of this tile's aggregate; called by warp 0 only.  status[] is zero-initialised.
-template <u64_t (*COMBINE)(u64_t, u64_t)>
-__device__ __forceinline__ u64_t chain_lookback(u64_t* status, int tile, u64_t aggregate) {
-    const int lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) st_volatile_u64(status, aggregate | CS_INCL);
-        return 0;
-    }
-    if (lane == 0) st_volatile_u64(status + tile, aggregate | CS_PART);
-    u64_t excl = 0;
-    bool have = false;
-    int j = tile - 1;
-    while (true) {
-        const int jj = j - lane;
-        u64_t v = CS_INCL;  // tiles before the first count as an inclusive 0
-        if (jj >= 0) {
-            do {
-                v = ld_volatile_u64(status + jj);
-            } while ((v >> 62) == 0);
-        }
-        const u32_t incl = __ballot_sync(0xffffffffu, (v >> 62) == 2);
-        const int stop = __ffs(incl) - 1;  // nearest inclusive predecessor in this window (always exists once jj < 0 appears)
-        // aggregate of the window's tiles (lanes stop..0, or all 32), earlier tiles first; the window lies before everything
-        // folded so far
-        u64_t win = 0;
-        bool whave = false;
-        for (int l = (stop >= 0 ? stop : 31); l >= 0; --l) {
-            const u64_t pv = __shfl_sync(0xffffffffu, v, l) & CS_PMASK;
-            win = whave ? COMBINE(win, pv) : pv;
-            whave = true;
-        }
-        excl = have ? COMBINE(win, excl) : win;
-        have = true;
-        if (stop >= 0) break;
-        j -= 32;
-    }
-    if (lane == 0) st_volatile_u64(status + tile, COMBINE(excl, aggregate) | CS_INCL);
-    return excl;
-}
-
-// The same look-back with the WHOLE block reading status words: thread q takes the q-th nearest earlier tile, so up to NT
+// Decoupled look-back with the WHOLE block reading status words: thread q takes the q-th nearest earlier tile, so up to NT
 // predecessors cost one L2 round trip plus a block reduction (all tiles of a scan are usually resident together and publish
 // their partial aggregates at about the same time; a warp-wide window would walk them 32 at a time).  COMBINE must be
 // commutative with 0 as identity.  Returns the exclusive prefix to every thread.  s_red: NT / 32 + 2 words of shared scratch.
