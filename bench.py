@@ -328,6 +328,8 @@ def run_sliding(args):
     assert stream != 0
     s = DmsaOptimSettings(**SETTINGS)
     traj = ContinuousTrajectory.from_window(win, device=local, stream=stream)
+    if args.lm_solver:
+        traj.setLmSolver(args.lm_solver)
     traj.centralize()
     P = traj.numParams
     rel_o, rel_t = win["rel_orient"].copy(), win["rel_transl"].copy()
@@ -509,7 +511,7 @@ def run_sliding(args):
         "dtype": "f32 point arithmetic / f64 pose chain, sums, J^T J (the reference's types)", "data": "synthetic",
         "config": {"workload": workload_string(args.config, win, P, world),
                    "N": N_points, "M": int(M), "G": int(G), "l2": "flushed between timed steps (256 MiB write, untimed)",
-                   "settings": SETTINGS},
+                   "settings": SETTINGS, "lm_solver": args.lm_solver},
         "point_jacobians_per_s": value * M,
         "membership_evals_per_s": value * M * (P + 10),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d / e2e_iters), "d2h_bytes_per_step": int(d2h / e2e_iters),
@@ -560,6 +562,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="sliding", choices=["sliding", "keyframe"])
     ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--lm-solver", type=int, default=0, help="dmsa_b200_set_lm_solver: 0 default (device LU for P <= 128, host beyond), 1 host, 2 device Cholesky")
     ap.add_argument("--frontend", type=int, default=1, help="1 (N = 1 only): also time SURVEY 8(f) ranks 2 / 3 (static points, pre-processing, normals) -> `frontend` object")
     ap.add_argument("--keyframe", type=int, default=1, help="1: also measure BASELINE config 4 (keyframe bundles, NCCL all-reduce) -> `keyframe` object")
     args = ap.parse_args()

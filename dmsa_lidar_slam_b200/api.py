@@ -398,7 +398,8 @@ class OptimizablePointSet:
         self.ctx._ck(self.L.dmsa_b200_set_pair_mode(self.h, int(mode)))
 
     def setLmSolver(self, mode):
-        """0: LM step on the device (default; no host round trip inside an iteration); 1: host solver (bit-identical)."""
+        """0: LM step on the device for P <= 128 (default; no host round trip inside a loop body); 1: host solver (bit-identical);
+        2: device Cholesky for every P <= 1024 (agrees to the conditioning of the system, not bit for bit)."""
         self.ctx._ck(self.L.dmsa_b200_set_lm_solver(self.h, int(mode)))
 
     def lmSolveDevice(self, settings, hg, n_params):

@@ -437,7 +437,7 @@ __global__ void k_iter_decide(double* __restrict__ rec, double* __restrict__ p, 
     __shared__ int s_best;
     const double* step = rec + 16;
     const double err0 = rec[16 + P];
-    const bool nan = rec[16 + P + 1] != 0.0;
+    const bool nan = rec[16 + P + 1] != 0.0;  // (2.0 = the Cholesky solver refused the system: parameters stay, the host redoes the body)
     if (threadIdx.x == 0) {
         double minError = err0;
         int best = 0;
@@ -1200,6 +1200,46 @@ int lmSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, const do
     return 0;
 }
 
+// LM step by the device Cholesky (kernels_chol.cuh, any P <= 1024): solver mode 2 of the reference-shaped loop and the solver
+// of the bundle extension.  step / step2: two copies of the step; tail = [err0, 0 ok / 1 NaN / 2 not positive definite].
+int cholSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int n, const double* hg_dev, double* step, double* step2, double* tail) {
+    const int ld = pad32(n);
+    CK(ctx->d_chol.ensure((size_t)(n + 1) * ld + 8 + ld));
+    CholArgs q;
+    q.hg = hg_dev;
+    q.n = n;
+    q.ld = ld;
+    q.lambda = (double)st->lambda_diag;
+    q.alpha = st->step_length_optim;
+    q.max_step = st->max_step;
+    q.W = ctx->d_chol.p;
+    q.step = step;
+    q.step2 = step2;
+    q.tail = tail;
+    q.flag = reinterpret_cast<int*>(ctx->d_chol.p + (size_t)(n + 1) * ld);
+    q.dinv = ctx->d_chol.p + (size_t)(n + 1) * ld + 8;
+    int nsm = 0;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int tiles = ((n + 31) / 32) * ((n + 31) / 32 + 1) / 2;
+    const unsigned grid = (unsigned)std::max(1, std::min(nsm, tiles));  // one trailing-update round per block column where possible
+    void* args[] = {&q};
+    ProfScope prof_(ctx, PROF_LM_SOLVE);
+    CK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_T), args, 0, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+// which solver a loop body of this context uses: 0 device LU + explicit inverse (P <= 128), 2 device Cholesky, 1 host
+inline int bodySolver(const dmsa_b200_ctx* ctx, int P, bool forceHost = false) {
+    if (forceHost) return 1;
+    if (ctx->solverMode == 2 && P <= CHOL_MAXN) return 2;
+    if (ctx->solverMode == 0 && P <= LM_DEV_MAXN) return 0;
+    return 1;
+}
+int solveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, int which) {
+    if (which == 2) return cholSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_step.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P);
+    return lmSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P);
+}
+
 // H.diag += lambda; step = -alpha * H^-1 * (J^T e0); NaN guard; infinity-norm clamp      DmsaOptimizer.h:107-128
 // returns 1 if the step contains NaN
 int solveStep(const dmsa_b200_settings* st, const double* hg, int P, std::vector<double>& step, bool explicit_inverse = true) {
@@ -1294,7 +1334,9 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
             }
         }
     } wall_{ctx, PROF_HOST_ITER};
-    const bool devSolve = ctx->solverMode == 0 && P <= LM_DEV_MAXN;  // larger systems: host solver
+    bool forceHost = false;
+    int which = bodySolver(ctx, P);
+    bool devSolve = which != 1;  // 0: device LU (P <= 128), 2: device Cholesky (opt-in, any P <= 1024), 1: host solver
     CKRC(ensurePinned(ctx, P));
     CK(ctx->d_hg.ensure((size_t)P * P + P + 1));
     CK(ctx->d_ls.ensure(16));
@@ -1304,7 +1346,9 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
     double error0 = 0;
     double ls[9];
     bool tryDefer = devSolve;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        which = bodySolver(ctx, P, forceHost);
+        devSolve = which != 1;
         // getPoseParameters + updateGlobalPoints at the base pose (the forward-difference batch's vector 0)   :72-75
         ctx->poses.relative2global();
         CKRC(uploadParams(ctx));
@@ -1328,7 +1372,7 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
         CKRC(allReduceSum(ctx, ctx->d_hg.p, (size_t)P * P + P + 1));
         if (devSolve) {
             // device-resident LM step: solve, line search and ONE read-back
-            CKRC(lmSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
+            CKRC(solveDev(ctx, st, P, which));
             CKRC(lineSearchDev(ctx, ctx->d_iter.p));
             CKRC(allReduceSum(ctx, ctx->d_iter.p, 9));
             CK(cudaMemcpyAsync(pinHg(ctx), ctx->d_iter.p, (16 + (size_t)P + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1366,6 +1410,12 @@ int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* sto
                 }
             }
             const double* r = pinHg(ctx);
+            if (r[16 + P + 1] == 2.0) {  // Cholesky: the system is not numerically positive definite -> the reference's LU on the host
+                if (ctx->profiling) profCollect(ctx);
+                forceHost = true;
+                tryDefer = false;
+                continue;
+            }
             std::copy(r, r + 9, ls);
             step.assign(r + 16, r + 16 + P);
             error0 = r[16 + P];
@@ -2139,7 +2189,7 @@ int enqueueBody(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, bool up
     CKRC(runCost(ctx));
     CKRC(jtjInto(ctx, ctx->d_hg.p));
     CKRC(allReduceSum(ctx, ctx->d_hg.p, (size_t)P * P + P + 1));
-    CKRC(lmSolveDev(ctx, st, P, ctx->d_hg.p, ctx->d_iter.p + 16, ctx->d_iter.p + 16 + P));
+    CKRC(solveDev(ctx, st, P, bodySolver(ctx, P)));
     CKRC(lineSearchDev(ctx, ctx->d_iter.p));
     CKRC(allReduceSum(ctx, ctx->d_iter.p, 9));
     LAUNCH(k_iter_decide, 1, 128, 0, ctx->d_iter.p, ctx->d_p.p, P, st->epsilon);
@@ -2164,7 +2214,7 @@ int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, d
     // Run-ahead loop (device LM solver only): body i + 1 is enqueued before the host has read body i's results, so the GPU
     // never waits for the host between bodies.  The host consumes the read-back blocks one body late and keeps the
     // reference's pose bookkeeping (staleGlobal); a body that ran past a stop condition is discarded.
-    const bool runAhead = ctx->runAhead && ctx->solverMode == 0 && P > 0 && P <= LM_DEV_MAXN && !ctx->profiling && settings->num_iter >= 3;
+    const bool runAhead = ctx->runAhead && P > 0 && bodySolver(ctx, P) != 1 && !ctx->profiling && settings->num_iter >= 3;
     if (runAhead) {
         // body 0 takes the synchronous path (its set build has no size guess yet)
         CKRC(iterationImpl(ctx, settings, &stop, &rep, nullptr, nullptr));
@@ -2208,6 +2258,7 @@ int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, d
                 }
                 if (G > ctx->cellCap) ARGFAIL("build_sets: Gaussian store capacity exceeded");
                 if (G > std::max(li[0].bound, li[1].bound)) miss = true;
+                if (r[16 + P + 1] == 2.0) miss = true;  // Cholesky refused the system: this body goes to the host LU
                 if (miss) {  // redo this body (and the rest) on the synchronous path; the host state has not been touched by it
                     CK(cudaStreamSynchronize(ctx->stream));
                     for (int l = 0; l < 2; ++l)
@@ -2320,7 +2371,7 @@ int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int
 // loop body then runs behind one read-back; larger systems use the host solver in either mode), 1 the host solver.
 // Same operation sequence, bit-identical steps.
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode) {
-    if (mode != 0 && mode != 1) ARGFAIL("set_lm_solver: 0 (device, default) or 1 (host)");
+    if (mode < 0 || mode > 2) ARGFAIL("set_lm_solver: 0 (device LU + explicit inverse for P <= 128, default), 1 (host) or 2 (device Cholesky, P <= 1024)");
     ctx->solverMode = mode;
     return 0;
 }
@@ -2488,30 +2539,7 @@ int dmsa_b200_set_shard(dmsa_b200_ctx* ctx, int32_t rank, int32_t world) {
 int dmsa_b200_spd_solve_dev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, const double* hg_dev, int32_t n, double* step_dev, double* tail_dev) {
     if (!st || !hg_dev || !step_dev || !tail_dev || n <= 0 || n > CHOL_MAXN) ARGFAIL("spd_solve_dev: bad arguments (1 <= n <= 1024)");
     CK(cudaSetDevice(ctx->device));
-    const int ld = pad32(n);
-    CK(ctx->d_chol.ensure((size_t)(n + 1) * ld + 8 + ld));
-    CholArgs q;
-    q.hg = hg_dev;
-    q.n = n;
-    q.ld = ld;
-    q.lambda = (double)st->lambda_diag;
-    q.alpha = st->step_length_optim;
-    q.max_step = st->max_step;
-    q.W = ctx->d_chol.p;
-    q.step = step_dev;
-    q.step2 = nullptr;
-    q.tail = tail_dev;
-    q.flag = reinterpret_cast<int*>(ctx->d_chol.p + (size_t)(n + 1) * ld);
-    q.dinv = ctx->d_chol.p + (size_t)(n + 1) * ld + 8;
-    int nsm = 0;
-    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-    const int tiles = ((n + 31) / 32) * ((n + 31) / 32 + 1) / 2;
-    const unsigned grid = (unsigned)std::max(1, std::min(nsm, tiles));  // one trailing-update round per block column where possible
-    void* args[] = {&q};
-    ProfScope prof_(ctx, PROF_LM_SOLVE);
-    CK(cudaLaunchCooperativeKernel((const void*)k_chol_solve, dim3(grid), dim3(CHOL_T), args, 0, ctx->stream));
-    ctx->launches++;
-    return 0;
+    return cholSolveDev(ctx, st, n, hg_dev, step_dev, nullptr, tail_dev);
 }
 // the same on host buffers (validation): step[n], *flag = 0 ok / 1 NaN / 2 not positive definite
 int dmsa_b200_spd_solve(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, const double* hg, int32_t n, double* step, int32_t* flag) {

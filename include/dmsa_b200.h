@@ -247,10 +247,14 @@ int64_t dmsa_b200_collective_count(const dmsa_b200_ctx* ctx); /* NCCL all-reduce
 int dmsa_b200_lm_solve(const dmsa_b200_settings* settings, const double* hg, int32_t n_params, int32_t explicit_inverse, double* step,
                        int32_t* has_nan);
 
-/* Solver of the LM step inside dmsa_b200_iteration / dmsa_b200_optimize (DmsaOptimizer.h:107-128): 0 (default) = device
- * kernels for P <= 128 (the whole loop body then runs behind ONE read-back; larger systems use the host solver in either
- * mode), 1 = host solver.
- * Both run the same operation sequence (LU with partial pivoting, explicit inverse, ascending accumulation): bit-identical. */
+/* LM step of dmsa_b200_iteration / dmsa_b200_optimize (DmsaOptimizer.h:107-128):
+ *   0 (default) device kernels for P <= 128 (kernels_solve.cuh: LU with partial pivoting + explicit inverse, the operation
+ *     sequence of the host solver, bit-identical); larger systems use the host solver;
+ *   1 host solver (host_solve.cpp), the reference's expression (-alpha * H.inverse()) * J^T e;
+ *   2 device Cholesky (kernels_chol.cuh) for every P <= 1024: H + lambda I is symmetric positive definite, the step agrees
+ *     with the LU-inverse step to the conditioning of the system (not bit for bit); a system the factorisation refuses
+ *     falls back to the host solver.  Keeps loop bodies with P > 128 (keyframe submaps of more than 22 keyframes, BASELINE
+ *     config 5) free of host round trips. */
 int dmsa_b200_set_lm_solver(dmsa_b200_ctx* ctx, int32_t mode);
 /* Cost kernels of the forward-difference batch (V = P + 1 vectors): 1 (default) = two vectors per thread with Blackwell's
  * packed FP32x2 instructions (FMUL2 / FADD2; every multiply->add edge keeps a scalar side, so nothing is fused) and the
