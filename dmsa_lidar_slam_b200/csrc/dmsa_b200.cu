@@ -611,7 +611,7 @@ int transformBase(dmsa_b200_ctx* ctx) {
 
 // control block of the hand-written sort / chained scans of one set build (kernels_sort.cuh); one memset zeroes all of it
 struct CtlLayout {
-    size_t tickets = 0, gbready = 0, hist = 0, look = 0, segStatus = 0, emitStatus = 0, scanStatus[3] = {0, 0, 0}, bytes = 0;
+    size_t tickets = 0, gbready = 0, bigCount = 0, orderHist = 0, hist = 0, look = 0, segStatus = 0, emitStatus = 0, scanStatus[3] = {0, 0, 0}, bytes = 0;
     int tilesSort = 0, tilesScan = 0;
     static size_t al(size_t x) { return (x + 15) / 16 * 16; }
     CtlLayout(int N, int npass, int cells) {
@@ -623,6 +623,10 @@ struct CtlLayout {
         o = al(o + 16 * sizeof(int));
         gbready = o;
         o = al(o + RS_MAXSEG * sizeof(int));
+        bigCount = o;  // number of sets with more than GAUSS_WARP_MAX members (k_gauss_list)
+        o = al(o + sizeof(int));
+        orderHist = o;  // size-class histogram + cursors of the fused kernel's issue order (k_cell_plan / k_cell_order)
+        o = al(o + 2 * ORDER_CLASSES * sizeof(int));
         hist = o;
         o = al(o + (size_t)RS_MAXSEG * RS_MAXPASS * RS_BINS * sizeof(u32_t));
         look = o;
@@ -710,7 +714,10 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
     CK(ctx->d_cell_w.ensure(cap));
     CK(ctx->d_nchunk.ensure((size_t)cap + 1));
     CK(ctx->d_chunk_off.ensure((size_t)cap + 1));
-    CK(ctx->d_done.ensure(4 * ((size_t)cap + 1)));
+    if (4 * ((size_t)cap + 1) > ctx->d_done.cap) {
+        CK(ctx->d_done.ensure(4 * ((size_t)cap + 1)));
+        CK(cudaMemsetAsync(ctx->d_done.p, 0, ctx->d_done.cap * sizeof(int), ctx->stream));
+    }
     CellStore cs;
     cs.start = ctx->d_cell_start.p;
     cs.n = ctx->d_cell_n.p;
@@ -958,20 +965,19 @@ phase2:
     CK(ctx->d_chunks.ensure(ctx->chunkBound));
     {
         cudaStream_t s2 = ctx->stream2;
-        int* cnt = ctx->d_biglist.p + cap;
-        int* hist = ctx->d_oval.p;  // [ORDER_CLASSES histogram | ORDER_CLASSES cursors], then the order at + cellCap
+        // (both live in the build's control block: zeroed by its one memset)
+        int* cnt = reinterpret_cast<int*>(ctx->d_ctl.p + cl.bigCount);
+        int* hist = reinterpret_cast<int*>(ctx->d_ctl.p + cl.orderHist);  // [ORDER_CLASSES histogram | ORDER_CLASSES cursors]
         CK(cudaEventRecord(ctx->evFork, ctx->stream));
         CK(cudaStreamWaitEvent(s2, ctx->evFork, 0));
-        CK(cudaMemsetAsync(cnt, 0, sizeof(int), s2));
         LAUNCH_ON(s2, k_gauss_list, cdiv(Gb, 256), 256, 0, cs, li, ctx->d_biglist.p, cnt);
         LAUNCH_ON(s2, k_gaussian_big, 148 * 2, GAUSS_BIG_T, 0, ctx->d_wrec.p, cs, ctx->d_biglist.p, cnt, ctx->d_mom.p);
         LAUNCH_ON(s2, k_weights, 1, 1024, 0, cs, li);  // depends on the set sizes only
         CK(cudaEventRecord(ctx->evJoin, s2));
         LAUNCH(k_gaussian, cdiv((size_t)Gb * 32, 256), 256, 0, ctx->d_wrec.p, cs, li, ctx->d_mom.p);
-        CK(cudaMemsetAsync(hist, 0, 2 * ORDER_CLASSES * sizeof(int), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_done.p, 0, 4 * ((size_t)cap + 1) * sizeof(int), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_nchunk.p, 0, ((size_t)Gb + 1) * sizeof(int), ctx->stream));  // entries behind the last set stay 0
-        LAUNCH(k_cell_plan, cdiv(Gb, 256), 256, 0, cs, li, CHUNK, FUSE_MAX, ctx->rank, ctx->world, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
+        // (the completion counters in d_done reset themselves at the end of every cost launch: zeroed when allocated only;
+        //  k_cell_plan writes the zeros behind the last set of nchunk itself)
+        LAUNCH(k_cell_plan, cdiv((size_t)Gb + 1, 256), 256, 0, cs, li, CHUNK, FUSE_MAX, ctx->rank, ctx->world, Gb, ctx->d_cell_kind.p, ctx->d_nchunk.p, ctx->d_okey.p, hist);
         LAUNCH(k_cell_order, cdiv(Gb, 256), 256, 0, li, ctx->d_okey.p, hist, ctx->d_oval.p + ctx->cellCap + 2 * ORDER_CLASSES);
         CKRC(scanExclusive(ctx, ctx->stream, cl, 0, ctx->d_nchunk.p, ctx->d_chunk_off.p, Gb + 1));  // [Gb] = total
         LAUNCH(k_chunk_fill, cdiv(Gb, 256), 256, 0, cs, li, CHUNK, ctx->d_nchunk.p, ctx->d_chunk_off.p, ctx->d_chunks.p);

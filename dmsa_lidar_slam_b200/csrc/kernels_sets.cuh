@@ -865,10 +865,13 @@ __global__ void k_weights(CellStore cs, const LevelInfo* __restrict__ li) {
 struct Chunk {
     int cell, start, count, first;  // first: index of the set's first chunk
 };
-__global__ void k_cell_plan(CellStore cs, const LevelInfo* __restrict__ li, int CH, int fuse_max, int rank, int world, int* __restrict__ kind,
+__global__ void k_cell_plan(CellStore cs, const LevelInfo* __restrict__ li, int CH, int fuse_max, int rank, int world, int bound, int* __restrict__ kind,
                             int* __restrict__ nchunk, int* __restrict__ okey, int* __restrict__ oval) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_sets(li)) return;
+    if (g >= total_sets(li)) {
+        if (g <= bound) nchunk[g] = 0;  // the scan behind this kernel runs over bound + 1 entries
+        return;
+    }
     const int n = cs.n[g];
     const int k = (g % world == rank) ? (n <= fuse_max ? 1 : 2) : 0;
     kind[g] = k;
