@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "dmsa_b200.cu")
 HOST_SRC = os.path.join(_HERE, "csrc", "host_solve.cpp")
 HOST_OBJ = os.path.join(_HERE, "lib", "host_solve.o")
-DEPS = [os.path.join(_HERE, "csrc", f) for f in ("host_solve.cpp", "dmsa_b200.cu", "kernels_cost.cuh", "kernels_pose.cuh", "kernels_sets.cuh", "kernels_solve.cuh", "kernels_sort.cuh", "kernels_chol.cuh", "kernels_knn.cuh", "kernels_pre.cuh", "dmsa_b200_pre.inl", "dmsa_b200_io.inl", "se3_math.cuh")] + [
+DEPS = [os.path.join(_HERE, "csrc", f) for f in ("host_solve.cpp", "dmsa_b200.cu", "kernels_cost.cuh", "kernels_pose.cuh", "kernels_sets.cuh", "kernels_solve.cuh", "kernels_sort.cuh", "kernels_chol.cuh", "kernels_knn.cuh", "kernels_pre.cuh", "dmsa_b200_pre.inl", "dmsa_b200_io.inl", "se3_math.cuh", "pdl.cuh")] + [
     os.path.join(os.path.dirname(_HERE), "include", "dmsa_b200.h")]
 OUT = os.path.join(_HERE, "lib", "libdmsa_b200.so")
 OUT_FMA = os.path.join(_HERE, "lib", "libdmsa_b200_fma.so")  # experiment: the same kernels with FMA contraction allowed (scripts/fma_deviation.py)

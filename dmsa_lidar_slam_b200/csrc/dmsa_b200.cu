@@ -27,6 +27,26 @@
 #include "nccl_dyn.h"
 #include "se3_math.cuh"
 
+#include <atomic>
+
+// ---- programmatic dependent launch bookkeeping (pdl.cuh) ---------------------------------------------------------------
+// A kernel may only carry the programmatic-stream-serialization attribute when the operation right before it ON ITS
+// STREAM is a kernel of this library: griddepcontrol.wait orders a kernel behind the previous GRID only, and a kernel
+// launched with the attribute behind a copy / memset / event wait was measured to start before that operation had
+// finished (pageable uploads of the front-end calls, parameter uploads of the keyframe pass).  Every such stream
+// operation of the library therefore bumps a process-wide epoch, a launch chains to its predecessor only when no such
+// operation was issued since that predecessor, and only inside a PdlScope (a span of a C-ABI call in which nothing but
+// this library enqueues work on the context's streams; the first launch of an outermost scope never chains).
+static std::atomic<unsigned long long> g_opEpoch{1};
+static inline void pdlBreak() { g_opEpoch.fetch_add(1, std::memory_order_relaxed); }
+#define cudaMemcpyAsync(...) (pdlBreak(), cudaMemcpyAsync(__VA_ARGS__))
+#define cudaMemsetAsync(...) (pdlBreak(), cudaMemsetAsync(__VA_ARGS__))
+#define cudaMemcpy(...) (pdlBreak(), cudaMemcpy(__VA_ARGS__))
+#define cudaMemcpyFromSymbol(...) (pdlBreak(), cudaMemcpyFromSymbol(__VA_ARGS__))
+#define cudaStreamWaitEvent(...) (pdlBreak(), cudaStreamWaitEvent(__VA_ARGS__))
+#define cudaEventRecord(...) (pdlBreak(), cudaEventRecord(__VA_ARGS__))
+#define cudaLaunchCooperativeKernel(...) (pdlBreak(), cudaLaunchCooperativeKernel(__VA_ARGS__))
+
 using namespace dmsa;
 
 namespace {
@@ -136,6 +156,9 @@ struct dmsa_b200_ctx {
     std::vector<cudaEvent_t> evScan;  // one per uploaded scan (register_scans)
     std::string err;
     int64_t launches = 0;
+    // programmatic dependent launch: nesting depth of the PdlScopes, and per stream (0: stream, 1: stream2) the epoch of its last launch
+    int pdlDepth = 0;
+    unsigned long long pdlEpoch[2] = {0, 0};
     int model = MODEL_NONE;
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;  // set by dmsa_b200_comm_init: the row-sharded iteration all-reduces [H | g | e0^T e0] and the 9 trial costs
@@ -319,15 +342,49 @@ static void profCollect(dmsa_b200_ctx* ctx) {  // call after a stream synchroniz
         int rc__ = (call);         \
         if (rc__ != 0) return rc__; \
     } while (0)
-#define LAUNCH(kern, grid, block, smem, ...)                       \
-    do {                                                           \
-        kern<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__); \
-        ctx->launches++;                                           \
+// Kernels go out through cudaLaunchKernelEx; inside a PdlScope a launch whose predecessor on the stream is a kernel of this
+// library carries the programmatic-stream-serialization attribute (pdl.cuh): it is set up while the predecessor still
+// runs and its threads wait in DMSA_PDL_ENTER() until that one has completed.  DMSA_B200_PDL=0 in the environment
+// launches everything plainly (the kernels' griddepcontrol instructions are then no-ops).
+static const bool g_pdl = !(getenv("DMSA_B200_PDL") && atoi(getenv("DMSA_B200_PDL")) == 0);
+struct PdlScope {
+    dmsa_b200_ctx* c;
+    explicit PdlScope(dmsa_b200_ctx* ctx) : c(ctx) {
+        if (c->pdlDepth++ == 0) pdlBreak();
+    }
+    ~PdlScope() { --c->pdlDepth; }
+    PdlScope(const PdlScope&) = delete;
+    PdlScope& operator=(const PdlScope&) = delete;
+};
+template <typename... KArgs, typename... Args>
+static inline void launchKernel(dmsa_b200_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t strm, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = strm;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    const unsigned long long ep = g_opEpoch.load(std::memory_order_relaxed);
+    int slot = -1;
+    if (strm == ctx->stream) slot = 0;
+    else if (strm == ctx->stream2) slot = 1;
+    const bool chain = g_pdl && ctx->pdlDepth > 0 && slot >= 0 && ctx->pdlEpoch[slot] == ep;
+    cfg.numAttrs = chain ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // (errors surface at the next cudaGetLastError, like <<< >>>)
+    if (slot >= 0) ctx->pdlEpoch[slot] = ep;
+}
+#define LAUNCH(kern, grid, block, smem, ...)                                             \
+    do {                                                                                 \
+        launchKernel(ctx, kern, (grid), (block), (smem), ctx->stream, __VA_ARGS__);      \
+        ctx->launches++;                                                                 \
     } while (0)
-#define LAUNCH_ON(strm, kern, grid, block, smem, ...)          \
-    do {                                                       \
-        kern<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__); \
-        ctx->launches++;                                       \
+#define LAUNCH_ON(strm, kern, grid, block, smem, ...)                            \
+    do {                                                                         \
+        launchKernel(ctx, kern, (grid), (block), (smem), (strm), __VA_ARGS__);   \
+        ctx->launches++;                                                         \
     } while (0)
 #define ARGFAIL(msg)               \
     do {                           \
@@ -342,6 +399,7 @@ inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 __global__ void k_unpack_psi(const unsigned char* __restrict__ raw, int n, int out_off, const double* __restrict__ trajTime, int n_total, double t0,
                              int is_static, float4* __restrict__ local, float4* __restrict__ world, int* __restrict__ ring, int* __restrict__ tid,
                              int* __restrict__ flag) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = reinterpret_cast<const float4*>(raw)[2 * (size_t)i];
@@ -372,6 +430,7 @@ __global__ void k_unpack_psi(const unsigned char* __restrict__ raw, int n, int o
 
 __global__ void k_unpack_pn(const unsigned char* __restrict__ raw, const int* __restrict__ rings, int n, int out_off, int kf, float4* __restrict__ local,
                             float4* __restrict__ normal, int* __restrict__ ring, int* __restrict__ tid, int* __restrict__ flag) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4* r = reinterpret_cast<const float4*>(raw) + 3 * (size_t)i;
@@ -387,6 +446,7 @@ __global__ void k_unpack_pn(const unsigned char* __restrict__ raw, const int* __
 
 // centralize / decentralize static points: point -= float(origin) / += float(origin)    ContinuousTrajectory.h:83-87, 95-99
 __global__ void k_shift_static(float4* __restrict__ local, float4* __restrict__ world, int off, int n, float ox, float oy, float oz, int sign) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = world[off + i];
@@ -408,6 +468,7 @@ __global__ void k_shift_static(float4* __restrict__ local, float4* __restrict__ 
 // other, so plain read-modify-write is race-free and the summation order is fixed
 __global__ void k_bundle_scatter(const double* __restrict__ hg, int Pl, const int* __restrict__ idx, int Pg, const LevelInfo* __restrict__ li,
                                  int depth0, int depth1, double* __restrict__ ghg) {
+    DMSA_PDL_ENTER();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     const int nH = Pl * Pl;
     if (e < nH) {
@@ -425,6 +486,7 @@ __global__ void k_bundle_scatter(const double* __restrict__ hg, int Pl, const in
     }
 }
 __global__ void k_bundle_gather_step(const double* __restrict__ gstep, const int* __restrict__ idx, int Pl, double* __restrict__ step) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < Pl) step[i] = gstep[idx[i]];
 }
@@ -434,6 +496,7 @@ __global__ void k_bundle_gather_step(const double* __restrict__ gstep, const int
 // place, so the next loop body can be enqueued before the host has seen this one.  The expressions are the host's
 // (iterationImpl), operation for operation.
 __global__ void k_iter_decide(double* __restrict__ rec, double* __restrict__ p, int P, double epsilon) {
+    DMSA_PDL_ENTER();
     __shared__ int s_best;
     const double* step = rec + 16;
     const double err0 = rec[16 + P];
@@ -474,6 +537,7 @@ __global__ void k_iter_decide(double* __restrict__ rec, double* __restrict__ p, 
     }
 }
 __global__ void k_add9(const double* __restrict__ src, double* __restrict__ dst) {
+    DMSA_PDL_ENTER();
     if (threadIdx.x < 9) dst[threadIdx.x] += src[threadIdx.x];
 }
 
@@ -488,6 +552,7 @@ int numTableRows(const dmsa_b200_ctx* ctx) { return ctx->model == MODEL_TRAJ ? c
 
 // pose chain (+ dense table) for the V vectors currently in d_batch
 int runPoseTables(dmsa_b200_ctx* ctx, int V) {
+    PdlScope pdl_(ctx);
     const int P = 6 * (ctx->poses.n - 1), n = ctx->poses.n, Vld = pad32(V), rows = numTableRows(ctx);
     const int E = numExtra(ctx);
     CK(ctx->d_globO.ensure((size_t)3 * n * Vld));
@@ -594,6 +659,7 @@ int uploadParams(dmsa_b200_ctx* ctx) {
 }
 
 int transformBase(dmsa_b200_ctx* ctx) {
+    PdlScope pdl_(ctx);
     const int64_t N = numPoints(ctx);
     if (N == 0) return 0;
     CK(ctx->d_world.ensure(N));
@@ -661,6 +727,7 @@ int scanExclusive(dmsa_b200_ctx* ctx, cudaStream_t strm, const CtlLayout& cl, in
 // set count stays on the device (LevelInfo::G), the kernels behind the build read it there, and the caller verifies the
 // guess (and the octree depth guess) with the iteration's single read-back.
 int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = false) {
+    PdlScope pdl_(ctx);
     const int64_t N64 = numPoints(ctx);
     if (N64 <= 0 || N64 > 0x3fffffff) ARGFAIL("build_sets: no points staged (or more than 2^30)");
     if (!ctx->worldValid) ARGFAIL("build_sets: call update_global_points first (the sets are built on globalPoints)");
@@ -990,6 +1057,7 @@ phase2:
 
 // V cost evaluations on the tables in Mtab -> E rows [0, G) (+ extra rows)
 int runCost(dmsa_b200_ctx* ctx) {
+    PdlScope pdl_(ctx);
     const int V = ctx->curV, Vld = ctx->curVld, G = ctx->Gb, E = numExtra(ctx);  // G: the bound the build sized its grids for
     if (Vld > 1024) ARGFAIL("more than 1023 pose parameters are not supported by the cost kernels");
     if (ctx->model == MODEL_TRAJ && ctx->useImu && !ctx->imuSet)
@@ -1103,6 +1171,7 @@ int runCost(dmsa_b200_ctx* ctx) {
 
 // forward-difference batch -> tables (parameters must be uploaded)
 int prepareFdBatch(dmsa_b200_ctx* ctx) {
+    PdlScope pdl_(ctx);
     const int P = 6 * (ctx->poses.n - 1);
     // `1.0 * sqrt(std::numeric_limits<float>::epsilon())` resolves to sqrt(float)       DmsaOptimizer.h:209
     const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
@@ -1113,6 +1182,7 @@ int prepareFdBatch(dmsa_b200_ctx* ctx) {
 }
 
 int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
+    PdlScope pdl_(ctx);
     const int P = 6 * (ctx->poses.n - 1), E = numExtra(ctx), Vld = ctx->curVld;
     const double h = 1.0 * (double)sqrtf(FLT_EPSILON);
     const double inv_h = 1.0 / h;  // one_div_incr, DmsaOptimizer.h:210
@@ -1141,6 +1211,7 @@ int jtjInto(dmsa_b200_ctx* ctx, double* hg_dev) {
 
 // the 9 trial costs of adaptiveStepSize for the step in d_step -> ls_dev[9]
 int lineSearchDev(dmsa_b200_ctx* ctx, double* ls_dev) {
+    PdlScope pdl_(ctx);
     const int P = 6 * (ctx->poses.n - 1);
     LAUNCH(k_make_ls_batch, cdiv((size_t)9 * P, 256), 256, 0, ctx->d_p.p, ctx->d_step.p, P, ctx->d_batch.p);
     ctx->phase = 1;
@@ -1167,6 +1238,7 @@ int lineSearchInto(dmsa_b200_ctx* ctx, const double* step_host, double* ls_dev) 
 
 // LM step on the device (kernels_solve.cuh, P <= 128): hg_dev = [H | g | err0] -> d_step (+ copy in step2), tail = [err0, nan flag]
 int lmSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, const double* hg_dev, double* step2, double* tail) {
+    PdlScope pdl_(ctx);
     if (P > LM_DEV_MAXN) ARGFAIL("lm_solve: the device solver takes at most 128 parameters (larger systems: host solver)");
     const int ld = pad32(P);
     const size_t need = 2 * (size_t)P * ld + P + 2 * (size_t)P + 8;
@@ -1181,6 +1253,7 @@ int lmSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, const do
     const size_t smem = ((size_t)P * ld + P) * sizeof(double);
     if (!ctx->solveAttr) {
         CK(cudaFuncSetAttribute(k_inv128, cudaFuncAttributeMaxDynamicSharedMemorySize, (LM_DEV_MAXN * LM_DEV_MAXN + LM_DEV_MAXN) * (int)sizeof(double)));
+        CK(cudaFuncSetAttribute(k_step_fin, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_DEV_MAXN * LM_DEV_MAXN * (int)sizeof(double)));
         ctx->solveAttr = true;
     }
     ProfScope prof_(ctx, PROF_LM_SOLVE);
@@ -1201,7 +1274,7 @@ int lmSolveDev(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, const do
     Inv128Args ia{LUT, rdiag, piv, P, ld, XT};
     LAUNCH(k_inv128, (P + INV128_WARPS - 1) / INV128_WARPS, INV128_WARPS * 32, smem, ia);
     StepFinArgs fa{hg_dev, XT, P, ld, st->step_length_optim, st->max_step, ctx->d_step.p, step2, tail};
-    LAUNCH(k_step_fin, 1, LM_DEV_MAXN, 0, fa);
+    LAUNCH(k_step_fin, 1, STEPFIN_T, (size_t)P * ld * sizeof(double), fa);
     CK(cudaGetLastError());
     return 0;
 }
@@ -1310,6 +1383,7 @@ int allReduceSum(dmsa_b200_ctx* ctx, double* buf, size_t count) {
                                     "without one, combine the partial results of cost_jacobian_dev / line_search_costs_dev yourself");
         return 0;
     }
+    pdlBreak();
     ncclResult_t r = nccl_api().AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
     if (r != ncclSuccess) {
         ctx->err = "ncclAllReduce: " + nccl_api().describe(r);
@@ -1326,6 +1400,7 @@ int allReduceSum(dmsa_b200_ctx* ctx, double* buf, size_t count) {
 // body with a synchronous build).  With the host solver (default, and always for P > 128) the body stops twice more: for
 // [H | g] before the solve and for the 9 trial costs.
 int iterationImpl(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int32_t* stop, dmsa_b200_report* rep, double* step_out, double* ls_out) {
+    PdlScope pdl_(ctx);
     const int P = 6 * (ctx->poses.n - 1);
     if (P <= 0) ARGFAIL("need at least two poses");
     *stop = DMSA_B200_STOP_MAX_ITER;
@@ -2060,6 +2135,7 @@ int dmsa_b200_traj_get_dense_poses(dmsa_b200_ctx* ctx, double* orient, double* t
 }
 
 int dmsa_b200_build_sets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, int32_t* num_gaussians, int64_t* num_memberships) {
+    PdlScope pdl_(ctx);
     CK(cudaSetDevice(ctx->device));
     CKRC(buildSets(ctx, settings));
     if (num_gaussians) *num_gaussians = ctx->G;
@@ -2137,6 +2213,7 @@ int dmsa_b200_eval_cost(dmsa_b200_ctx* ctx, const double* params, int32_t n_vect
 }
 
 int dmsa_b200_cost_jacobian(dmsa_b200_ctx* ctx, double* H, double* g, double* err0, double* e0, double* J) {
+    PdlScope pdl_(ctx);
     CK(cudaSetDevice(ctx->device));
     const int P = 6 * (ctx->poses.n - 1);
     if (ctx->G <= 0) ARGFAIL("cost_jacobian: build_sets first");
@@ -2186,6 +2263,7 @@ namespace {
 // tests by k_iter_decide), its read-back block copied to `slot` of the pinned ring.  upload: d_p <- the host's parameters
 // (first run-ahead body); otherwise d_p is what the previous body's k_iter_decide left.
 int enqueueBody(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, bool upload, double* slot, cudaEvent_t done) {
+    PdlScope pdl_(ctx);
     const size_t recN = 16 + 3 * (size_t)P + 2;
     if (upload) CKRC(uploadParams(ctx));
     CKRC(prepareFdBatch(ctx));
@@ -2209,6 +2287,7 @@ int enqueueBody(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, int P, bool up
 extern "C" {
 
 int dmsa_b200_optimize(dmsa_b200_ctx* ctx, const dmsa_b200_settings* settings, dmsa_b200_report* report) {
+    PdlScope pdl_(ctx);
     CK(cudaSetDevice(ctx->device));
     if (ctx->model == MODEL_NONE) ARGFAIL("optimize: no model staged");
     dmsa_b200_report rep;
@@ -2421,6 +2500,7 @@ int dmsa_b200_lm_solve_device(dmsa_b200_ctx* ctx, const dmsa_b200_settings* sett
 namespace {
 // hashed grid over `n` points (device; every stride4-th float4 is a point) with cell edge h (kernels_knn.cuh)
 int buildHashGrid(dmsa_b200_ctx* ctx, const float4* pts, int n, int stride4, double h, HashGrid* view) {
+    PdlScope pdl_(ctx);
     if (!(h > 0.0)) h = 1e-6;
     int B = 4096;
     while (B < 2 * n && B < (1 << 22)) B <<= 1;
@@ -2484,6 +2564,7 @@ int windowRadiusGrid(dmsa_b200_ctx* ctx, float radius, HashGrid* view) {
 // per addStaticPoints call, DmsaSlam.h:283-286).
 int dmsa_b200_select_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_normal* cloud, int64_t n, const float* pos, float max_dist,
                                    uint8_t* selected, int64_t* num_selected) {
+    PdlScope pdl_(ctx);
     if ((n > 0 && (!cloud || !selected)) || !pos || n < 0 || n > 0x3fffffff) ARGFAIL("select_static_points: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (num_selected) *num_selected = 0;
@@ -2510,6 +2591,7 @@ int dmsa_b200_select_static_points(dmsa_b200_ctx* ctx, const dmsa_b200_point_nor
 
 // getOverlap(pc1, pc2 = the staged window cloud, max_dist) (DmsaSlam.h:377-414): pc1 = n1 x (x, y, z, w) floats on the host
 int dmsa_b200_overlap(dmsa_b200_ctx* ctx, const float* pc1_xyzw, int64_t n1, float max_dist, float* overlap) {
+    PdlScope pdl_(ctx);
     if (!overlap || n1 < 0 || n1 > 0x3fffffff || (n1 > 0 && !pc1_xyzw)) ARGFAIL("overlap: bad arguments");
     CK(cudaSetDevice(ctx->device));
     *overlap = 0.0f;
@@ -2568,6 +2650,7 @@ int dmsa_b200_spd_solve(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, const 
 //      jacobian (every bundle) -> all_reduce -> spd_solve_dev -> line_search (every bundle) -> all_reduce -> ONE read-back
 //      -> verify (every bundle).  Nothing in between touches the host.
 int dmsa_b200_bundle_jacobian(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, const int32_t* idx_dev, int32_t P_global, double* ghg_dev, int32_t sync_build) {
+    PdlScope pdl_(ctx);
     if (!st || !idx_dev || !ghg_dev) ARGFAIL("bundle_jacobian: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (ctx->model == MODEL_NONE) ARGFAIL("bundle_jacobian: no model staged");
@@ -2590,6 +2673,7 @@ int dmsa_b200_bundle_jacobian(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, 
     return 0;
 }
 int dmsa_b200_bundle_line_search(dmsa_b200_ctx* ctx, const double* gstep_dev, const int32_t* idx_dev, double* gls_dev) {
+    PdlScope pdl_(ctx);
     if (!gstep_dev || !idx_dev || !gls_dev) ARGFAIL("bundle_line_search: bad arguments");
     CK(cudaSetDevice(ctx->device));
     const int P = 6 * (ctx->poses.n - 1);
@@ -2676,6 +2760,7 @@ int dmsa_b200_comm_destroy(dmsa_b200_ctx* ctx) {
 int64_t dmsa_b200_collective_count(const dmsa_b200_ctx* ctx) { return ctx ? ctx->collectives : 0; }
 
 int dmsa_b200_cost_jacobian_dev(dmsa_b200_ctx* ctx, double* hg_dev) {
+    PdlScope pdl_(ctx);
     CK(cudaSetDevice(ctx->device));
     if (ctx->G <= 0) ARGFAIL("cost_jacobian_dev: build_sets first");
     CKRC(uploadParams(ctx));

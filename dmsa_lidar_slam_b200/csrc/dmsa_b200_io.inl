@@ -9,6 +9,7 @@ namespace {
 // One thread per point: byte-wise gathers out of the message buffer (fields may be unaligned), one 32-byte record out.
 __global__ void k_decode_pc2(const unsigned char* __restrict__ data, int n, dmsa_b200_pc2_layout L, double stamp_msg, double delta_t,
                              dmsa_b200_point_stamp_id* __restrict__ out) {
+    DMSA_PDL_ENTER();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const unsigned char* p = data + (size_t)k * L.point_step;

@@ -27,6 +27,7 @@ void glibcRandSequence(uint32_t seed, size_t n, int32_t* out) {
 // PCL octree leaves of `n` points at resolution `res` on the device: p_sidx = point indices in leaf (depth-first) order,
 // p_raw_start[c] = first slot of leaf c; *R_out = number of leaves.  Two host synchronisations (octree depth, leaf count).
 int preLeaves(dmsa_b200_ctx* ctx, const float4* pts, int n, float res, int* R_out) {
+    PdlScope pdl_(ctx);
     *R_out = 0;
     if (n <= 0) return 0;
     const int nb = (n + DMSA_KEYS_BLOCK - 1) / DMSA_KEYS_BLOCK;
@@ -115,6 +116,7 @@ int preLeaves(dmsa_b200_ctx* ctx, const float4* pts, int n, float res, int* R_ou
 }
 // randomGridDownsampling: p_pick[c] = index of the member drawn from leaf c (helpers.h:86-106), c = 0 .. R - 1
 int preDownsample(dmsa_b200_ctx* ctx, const float4* pts, int n, float grid_size, uint32_t seed, int* R_out) {
+    PdlScope pdl_(ctx);
     CKRC(preLeaves(ctx, pts, n, grid_size, R_out));
     const int R = *R_out;
     if (R == 0) return 0;
@@ -179,6 +181,7 @@ int dmsa_b200_downsample_global_points(dmsa_b200_ctx* ctx, float grid_size, uint
 // out: room for n records; *n_out records are written; *grid_size_out = filteredPc->gridSize.
 int dmsa_b200_preprocess_scan(dmsa_b200_ctx* ctx, const dmsa_b200_point_stamp_id* raw, int64_t n, const dmsa_b200_preprocess_config* cfg, uint32_t seed,
                               dmsa_b200_point_stamp_id* out, int64_t* n_out, float* grid_size_out) {
+    PdlScope pdl_(ctx);
     if (!cfg || !n_out || n < 0 || n > 0x3fffffff || (n > 0 && (!raw || !out))) ARGFAIL("preprocess_scan: bad arguments");
     CK(cudaSetDevice(ctx->device));
     *n_out = 0;
@@ -265,6 +268,7 @@ int dmsa_b200_preprocess_scan(dmsa_b200_ctx* ctx, const dmsa_b200_point_stamp_id
 // cell_size: edge of the search grid (> 0; the cloud's grid size is a good value: about one point per cell).
 // nn_indices (optional): the 6 neighbour indices of every point in search-result order, -1 where fewer exist.
 int dmsa_b200_estimate_normals(dmsa_b200_ctx* ctx, dmsa_b200_point_normal* cloud, int64_t n, const float* viewpoint, float cell_size, int32_t* nn_indices) {
+    PdlScope pdl_(ctx);
     if (n < 0 || n > 0x3fffffff || (n > 0 && !cloud) || !viewpoint || !(cell_size > 0.0f)) ARGFAIL("estimate_normals: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (n == 0) return 0;

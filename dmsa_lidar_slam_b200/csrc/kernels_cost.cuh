@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pdl.cuh"
+
 #include "kernels_sets.cuh"
 
 namespace dmsa {
@@ -226,6 +228,7 @@ __device__ __forceinline__ double pass_quad(const CostArgs& a, const float4* __r
 // Also zero-fills the rows of sets owned by other ranks.
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ double ex[PACKED_WARPS][16];
@@ -259,6 +262,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused(CostArgs a) {
 // therefore not the default; it exists to show that the only arithmetic difference between the fast path and the
 // reference's operation order is that one reduction (DESIGN.md §3 "mean").
 __global__ void __launch_bounds__(1024) k_cost_seq(CostArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(16) float4 srec[COST_CHUNK];
     const int g = blockIdx.x;
     if (g >= total_sets(a.li)) return;
@@ -390,6 +394,7 @@ __device__ __forceinline__ bool last_block_of_set(int* counter, int nc, int* s_f
 // Big sets, pass 1: per-chunk coordinate sums (double)
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ double ex[PACKED_WARPS][16];
@@ -433,6 +438,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum(CostArgs a) {
 // in the block that finishes last for its set - e = sqrt(|sum of the chunk partials|) in fixed chunk order (:267).
 template <bool PACKED, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad(CostArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ double ex[PACKED_WARPS][16];
@@ -686,6 +692,7 @@ __device__ __forceinline__ PairMap pair_map(const CostArgs& a) {
 
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused2(CostArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     const PairMap pm = pair_map(a);
@@ -725,6 +732,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_fused2(CostArgs a) {
 
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_last;
@@ -773,6 +781,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_sum2(CostArgs a) {
 
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad2(CostArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(128) float4 srec[COST_CHUNK];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_last;
@@ -822,6 +831,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cost_quad2(CostArgs a) {
 // per-vector cost sum_r e[r][v]^2 (line search, DmsaOptimizer.h:171): COLSUM_PARTS row slices per vector, fixed reduction order
 #define COLSUM_PARTS 16
 __global__ void k_col_sumsq(const double* __restrict__ E, const LevelInfo* __restrict__ li, int n_extra, int Vld, double* __restrict__ part /*[9][COLSUM_PARTS]*/) {
+    DMSA_PDL_ENTER();
     __shared__ double red[256];
     const int R = total_sets(li) + n_extra;
     const int v = blockIdx.x, y = blockIdx.y;
@@ -841,6 +851,7 @@ __global__ void k_col_sumsq(const double* __restrict__ E, const LevelInfo* __res
     if (threadIdx.x == 0) part[v * COLSUM_PARTS + y] = red[0];
 }
 __global__ void k_col_sumsq_fin(const double* __restrict__ part, double* __restrict__ out) {
+    DMSA_PDL_ENTER();
     const int v = threadIdx.x;
     if (v >= 9) return;
     double s = 0.0;
@@ -850,6 +861,7 @@ __global__ void k_col_sumsq_fin(const double* __restrict__ part, double* __restr
 
 // additional residual rows (IMU / gravity / odometry) behind the set rows: E[G + r][v] = extra[r][v]   (DmsaOptimizer.h:271-272)
 __global__ void k_append_extra(double* __restrict__ E, const LevelInfo* __restrict__ li, const double* __restrict__ extra, int n_extra, int Vld) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_extra * Vld) return;
     E[(size_t)total_sets(li) * Vld + i] = extra[i];
@@ -877,6 +889,7 @@ __device__ __forceinline__ void jtj_partition(int R, int& nsplit, int& rps) {
 // column P is e0.  Upper-triangular 32x32 tiles, split over row ranges; partials are reduced in fixed order.
 __global__ void __launch_bounds__(256) k_jtj(const double* __restrict__ E, const LevelInfo* __restrict__ li, int n_extra, int Vld, int P, double inv_h,
                                              double* __restrict__ part /*[split][(P+1)*(P+1)]*/) {
+    DMSA_PDL_ENTER();
     __shared__ double A[JTJ_T][JTJ_T + 1], B[JTJ_T][JTJ_T + 1];
     const int R = total_sets(li) + n_extra;
     int nsplit, rows_per_split;
@@ -937,6 +950,7 @@ __global__ void __launch_bounds__(256) k_jtj(const double* __restrict__ E, const
 }
 // out = [H (P*P row-major) | g (P) | err0]
 __global__ void k_jtj_reduce(const double* __restrict__ part, const LevelInfo* __restrict__ li, int n_extra, int P, double* __restrict__ out) {
+    DMSA_PDL_ENTER();
     const int n1 = P + 1;
     int nsplit, rps_;
     jtj_partition(total_sets(li) + n_extra, nsplit, rps_);
@@ -969,6 +983,7 @@ __global__ void k_jtj_reduce(const double* __restrict__ part, const LevelInfo* _
 #define JD_MAXN 128
 __global__ void __launch_bounds__(JD_T, 1) k_jtj_dmma(const double* __restrict__ E, const LevelInfo* __restrict__ li, int n_extra, int Vld, int P, double inv_h,
                                                        double* __restrict__ part /*[block][n1*n1]*/) {
+    DMSA_PDL_ENTER();
     __shared__ __align__(16) double As[JD_ROWS * JD_LD];
     __shared__ unsigned char tij[JD_MAXN / 8 * (JD_MAXN / 8 + 1) / 2][2];
     const int R = total_sets(li) + n_extra;
@@ -1034,6 +1049,7 @@ __global__ void __launch_bounds__(JD_T, 1) k_jtj_dmma(const double* __restrict__
 // ascending k), the streams are combined in ascending order: fixed summation order, coalesced 256-byte reads.
 __global__ void __launch_bounds__(256) k_jtj_reduce8(const double* __restrict__ part, const LevelInfo* __restrict__ li, int n_extra, int P,
                                                      double* __restrict__ out) {
+    DMSA_PDL_ENTER();
     __shared__ double red[8][33];
     const int n1 = P + 1;
     int nsplit, rpb_;
@@ -1070,6 +1086,7 @@ __global__ void __launch_bounds__(256) k_jtj_reduce8(const double* __restrict__ 
 // ContinuousTrajectory.h:137-155 | MapManagement.h:140-147
 __global__ void k_transform_points(const float4* __restrict__ local, const int* __restrict__ tid, int n, const float4* __restrict__ Mtab, int Vld,
                                    int v, float4* __restrict__ world, const float4* __restrict__ normal_l, float4* __restrict__ normal_w) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = local[i];

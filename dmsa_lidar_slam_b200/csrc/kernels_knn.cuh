@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pdl.cuh"
+
 #include "kernels_sets.cuh"
 
 namespace dmsa {
@@ -35,6 +37,7 @@ __device__ __forceinline__ unsigned grid_bucket(int cx, int cy, int cz, int B) {
 }
 // bucket of every point (-1: not finite, in no bucket) + bucket histogram
 __global__ void k_hg_count(const float4* __restrict__ pts, int n, int stride4, double h, int B, int* __restrict__ bucket, int* __restrict__ counts) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 p = pts[(size_t)i * stride4];
@@ -47,6 +50,7 @@ __global__ void k_hg_count(const float4* __restrict__ pts, int n, int stride4, d
 }
 __global__ void k_hg_fill(const float4* __restrict__ pts, int n, int stride4, const int* __restrict__ bucket, const int* __restrict__ start,
                           int* __restrict__ cursor, float4* __restrict__ spts) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int b = bucket[i];
@@ -78,6 +82,7 @@ __device__ __forceinline__ bool grid_any_within(const HashGrid& g, float qx, flo
 // addStaticPoints inner loop (DmsaSlam.h:304-339) for one keyframe cloud of pcl::PointNormal (3 float4 per point)
 __global__ void k_select_static(HashGrid g, const float4* __restrict__ cloud, int n, float px, float py, float pz, float max_sq,
                                 unsigned char* __restrict__ selected, int* __restrict__ count) {
+    DMSA_PDL_ENTER();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     bool sel = false;
     if (j < n) {
@@ -95,6 +100,7 @@ __global__ void k_select_static(HashGrid g, const float4* __restrict__ cloud, in
 }
 // getOverlap (DmsaSlam.h:377-414): window points with a point of the searched cloud within max_dist
 __global__ void k_overlap_count(HashGrid g, const float4* __restrict__ window, int n, float max_sq, int* __restrict__ count) {
+    DMSA_PDL_ENTER();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false;
     if (j < n) {
@@ -332,6 +338,7 @@ __device__ inline bool pcl_point_normal(const float4* nb, int cnt, float n[3], f
 // surface = the cloud itself; normals flipped towards the view point (flipNormalTowardsViewpoint, float& overload).
 // nn_out (optional): the 6 neighbour indices of every point in result order.
 __global__ void __launch_bounds__(128) k_normals_knn6(HashGrid g, float4* __restrict__ cloud, int n, float vx, float vy, float vz, int* __restrict__ nn_out) {
+    DMSA_PDL_ENTER();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const float4 q = cloud[3 * (size_t)j];

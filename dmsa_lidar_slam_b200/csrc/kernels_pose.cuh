@@ -13,6 +13,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pdl.cuh"
+
 #include "se3_math.cuh"
 
 namespace dmsa {
@@ -61,6 +63,7 @@ struct KfFactors {        // MapManagement.h:36-70
 
 // Builds the forward-difference batch: row 0 = p, row k+1 = p + h e_k   (DmsaOptimizer.h:209-218)
 __global__ void k_make_fd_batch(const double* __restrict__ p, int P, double h, double* __restrict__ out) {
+    DMSA_PDL_ENTER();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int total = (P + 1) * P;
     if (i >= total) return;
@@ -71,6 +74,7 @@ __global__ void k_make_fd_batch(const double* __restrict__ p, int P, double h, d
 }
 // Builds the line-search batch: row k-1 = p + 0.1*k*step, k = 1..9   (DmsaOptimizer.h:160-162)
 __global__ void k_make_ls_batch(const double* __restrict__ p, const double* __restrict__ step, int P, double* __restrict__ out) {
+    DMSA_PDL_ENTER();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 9 * P) return;
     int v = i / P, k = i % P;
@@ -90,6 +94,7 @@ __device__ __forceinline__ void store_pair_entry(float* __restrict__ Mpair, int 
 // One block per parameter vector.  Shared memory: n * (9 + 9 + 3 + 3) doubles.
 template <int MODEL>  // 0 = trajectory (also writes quaternions), 1 = keyframes (also writes the per-keyframe table)
 __global__ void k_pose_chain(PoseBatch pb, float* __restrict__ Mtab, ImuFactors imu, KfFactors kf, TrajTiming tt) {
+    DMSA_PDL_ENTER();
     extern __shared__ double sm[];
     const int n = pb.n, v = blockIdx.x, Vld = pb.Vld;
     double* sE = sm;            // exp(relO_k)            [n][9]
@@ -303,6 +308,7 @@ __device__ __forceinline__ void dense_pose(const PoseBatch& pb, const TrajTiming
 
 // Dense trajectory table: thread (v, j).  ContinuousTrajectory.h:194-225.
 __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ Mtab) {
+    DMSA_PDL_ENTER();
     const int v = blockIdx.x * 32 + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     if (v >= pb.V || j > tt.n_total) return;
@@ -332,6 +338,7 @@ __global__ void k_dense_table(PoseBatch pb, TrajTiming tt, float* __restrict__ M
 
 // denseGlobalPoses of vector v (the double poses behind the table): orient / transl are 3 x n_total column-major
 __global__ void k_dense_poses(PoseBatch pb, TrajTiming tt, int v, double* __restrict__ orient, double* __restrict__ transl) {
+    DMSA_PDL_ENTER();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= tt.n_total) return;
     Vec3 aa;

@@ -9,12 +9,15 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pdl.cuh"
+
 #include "kernels_sets.cuh"
 
 namespace dmsa {
 
 // xyz of a point record (stride bytes apart, three floats at offset 0) -> float4 (w = 1)
 __global__ void k_pre_unpack(const unsigned char* __restrict__ raw, int n, int stride, float4* __restrict__ pts) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
@@ -22,6 +25,7 @@ __global__ void k_pre_unpack(const unsigned char* __restrict__ raw, int n, int s
 }
 // helpers.h:96-103: the member of leaf c (members in ascending point index == PCL's container order)
 __global__ void k_pre_pick(const int* __restrict__ raw_start, const int* __restrict__ sidx, const int* __restrict__ rnd, int R, int* __restrict__ pick) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= R) return;
     const int s = raw_start[c], n = raw_start[c + 1] - s;
@@ -32,6 +36,7 @@ __global__ void k_pre_pick(const int* __restrict__ raw_start, const int* __restr
 // ranges of the picked points: Eigen::Vector3f(x, y, z).norm() = sqrt(x^2 + (y^2 + z^2))   (DmsaSlam.h:599-603); key = float bits
 __global__ void k_pre_ranges(const float4* __restrict__ pts, const int* __restrict__ pick, int R, float* __restrict__ range,
                              unsigned long long* __restrict__ key) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= R) return;
     const float4 p = pts[pick[c]];
@@ -42,6 +47,7 @@ __global__ void k_pre_ranges(const float4* __restrict__ pts, const int* __restri
 // thresRange = max(rangesSorted[min(max_num, size - 1)], minDistDS) (:609); keep[c] = ranges[c] < thresRange && ranges[c] > min_dist (:616)
 __global__ void k_pre_keep(const float* __restrict__ range, const unsigned long long* __restrict__ sorted_key, int R, int max_num, float min_dist_ds,
                            float min_dist, int* __restrict__ keep) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= R) return;
     const float kth = __uint_as_float((unsigned)sorted_key[min(max_num, R - 1)]);
@@ -57,6 +63,7 @@ struct PreTform {
 };
 __global__ void k_pre_emit(const unsigned char* __restrict__ raw, int stride, const int* __restrict__ pick, const int* __restrict__ keep,
                            const int* __restrict__ pos, int R, PreTform T, unsigned char* __restrict__ out, int* __restrict__ n_out) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= R) return;
     if (c == R - 1) *n_out = pos[c] + keep[c];

@@ -13,6 +13,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pdl.cuh"
+
 #include <cstdint>
 
 namespace dmsa {
@@ -61,6 +63,7 @@ struct LevelPlan {  // the resolution levels built in this pass (DmsaOptimizer.h
     float res[2];
 };
 __global__ void k_anchor(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* infos, int bound) {
+    DMSA_PDL_ENTER();
     if (blockIdx.x != 0 || (int)threadIdx.x >= plan.n) return;
     LevelInfo* info = infos + plan.level[threadIdx.x];
     info->bound = bound;
@@ -112,6 +115,7 @@ __global__ void k_anchor(const float4* __restrict__ world, int N, LevelPlan plan
 // grid = (blocks of 256 points, levels): both resolution levels in one launch.
 __global__ void k_keys(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* __restrict__ infos, int* __restrict__ keys_all,
                        int* __restrict__ bb_all, int nb) {
+    DMSA_PDL_ENTER();
     const int lvl = plan.level[blockIdx.y];
     LevelInfo* __restrict__ info = infos + lvl;
     int* __restrict__ keys = keys_all + (size_t)3 * N * lvl;
@@ -201,6 +205,7 @@ __global__ void k_keys(const float4* __restrict__ world, int N, LevelPlan plan, 
 // blocks that cannot contain a violator (conservative integer test), candidates are re-tested exactly in double.
 __global__ void k_root(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* __restrict__ infos, const int* __restrict__ bb_all,
                        int nb_) {
+    DMSA_PDL_ENTER();
     const int lvl = plan.level[blockIdx.x];  // one block per level
     LevelInfo* __restrict__ info = infos + lvl;
     const int* __restrict__ bbmin = bb_all + (size_t)12 * nb_ * lvl;
@@ -324,6 +329,7 @@ __device__ __forceinline__ unsigned long long spread3(unsigned long long x) {  /
 __global__ void k_accept(const int* __restrict__ raw_start, const int* __restrict__ raw_diff, const LevelInfo* __restrict__ info, int minPts,
                          int* __restrict__ acc_flag, int* __restrict__ out_cnt, int* __restrict__ sub_start, int* __restrict__ sub_n,
                          int* __restrict__ sub_code) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= info->R) return;
     const int s = raw_start[c];
@@ -355,6 +361,7 @@ __device__ __forceinline__ int f2ord(float f) {  // order-preserving float -> in
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 __global__ void k_split_nbox(const int* __restrict__ idx, const int* __restrict__ scan, const int* __restrict__ acc_flag, const LevelInfo* __restrict__ info,
                              const float4* __restrict__ normal_w, int* __restrict__ nbox /*[R][6]: ordered-int min xyz, max xyz*/) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool in = i < info->n_valid;
@@ -392,6 +399,7 @@ __global__ void k_split_nbox(const int* __restrict__ idx, const int* __restrict_
 }
 __global__ void k_split_prefilter(const int* __restrict__ idx, const int* __restrict__ scan, const int* __restrict__ acc_flag, const LevelInfo* __restrict__ info,
                                   const float4* __restrict__ normal_w, const int* __restrict__ nbox, int* __restrict__ search /*[R]: 1 = run the pair search*/) {
+    DMSA_PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= info->n_valid) return;
     const int c = scan[i] - 1;
@@ -410,6 +418,7 @@ __global__ void k_split_prefilter(const int* __restrict__ idx, const int* __rest
 }
 // nbox initial values: min slots = INT_MAX, max slots = INT_MIN
 __global__ void k_split_nbox_init(int* __restrict__ nbox, int* __restrict__ search, int n_cells, const LevelInfo* __restrict__ info) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells || c > info->R) return;  // (only the leaves of this build)
 #pragma unroll
@@ -421,6 +430,7 @@ __global__ void k_split_nbox_init(int* __restrict__ nbox, int* __restrict__ sear
 }
 __global__ void k_split_tile_counts(const int* __restrict__ raw_start, const int* __restrict__ acc_flag, const int* __restrict__ search,
                                     const LevelInfo* __restrict__ info, int* __restrict__ ntile) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int R = info->R;
     if (c > R) return;
@@ -428,6 +438,7 @@ __global__ void k_split_tile_counts(const int* __restrict__ raw_start, const int
 }
 __global__ void k_split_tile_fill(const int* __restrict__ ntile, const int* __restrict__ tile_off, const LevelInfo* __restrict__ info,
                                   SplitTile* __restrict__ tiles) {
+    DMSA_PDL_ENTER();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= info->R) return;
     const int nt = ntile[c], o = tile_off[c];
@@ -445,6 +456,7 @@ __global__ void __launch_bounds__(256) k_split_pairs(const SplitTile* __restrict
                                                      const int* __restrict__ raw_start, const int* __restrict__ sidx,
                                                      const float4* __restrict__ normal_w, float* __restrict__ best_v, int* __restrict__ best_i,
                                                      int* __restrict__ best_j) {
+    DMSA_PDL_ENTER();
     __shared__ float sx[256], sy[256], sz[256];
     __shared__ float rv[256];
     __shared__ int ri[256], rj[256];
@@ -525,6 +537,7 @@ __global__ void __launch_bounds__(256) k_split_decide(const int* __restrict__ ac
                                                       const float* __restrict__ best_v, const int* __restrict__ best_i, const int* __restrict__ best_j,
                                                       int minPts, int* __restrict__ out_cnt, int* __restrict__ sub_start, int* __restrict__ sub_n,
                                                       int* __restrict__ sub_code) {
+    DMSA_PDL_ENTER();
     __shared__ int scan[256];
     __shared__ int s_rmin, s_rmax;
     __shared__ float s_bv;
@@ -718,6 +731,7 @@ __device__ inline void gaussian_finish(CellStore cs, int g, int n, const double 
 // k_gauss_list): centred second moments -> mom[g][6]; k_gaussian_fin turns them into information matrices.  The member loops are unrolled so that the loads of four strides are in flight together; every
 // thread still adds its terms in ascending member order.
 __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, const LevelInfo* __restrict__ li, double* __restrict__ mom) {
+    DMSA_PDL_ENTER();
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (g >= total_sets(li)) return;
@@ -757,6 +771,7 @@ __global__ void k_gaussian(const float4* __restrict__ wrec, CellStore cs, const 
 }
 // compact list of the sets with n > GAUSS_WARP_MAX (order irrelevant: every set's result depends on the set alone)
 __global__ void k_gauss_list(CellStore cs, const LevelInfo* __restrict__ li, int* __restrict__ list, int* __restrict__ count) {
+    DMSA_PDL_ENTER();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_sets(li)) return;
     if (cs.n[g] > GAUSS_WARP_MAX) list[atomicAdd(count, 1)] = g;
@@ -766,6 +781,7 @@ __global__ void k_gauss_list(CellStore cs, const LevelInfo* __restrict__ li, int
 // compact list.
 __global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __restrict__ wrec, CellStore cs, const int* __restrict__ list,
                                                                const int* __restrict__ count, double* __restrict__ mom) {
+    DMSA_PDL_ENTER();
     __shared__ double red[GAUSS_BIG_T / 32][6];
     __shared__ float smean[3];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -829,6 +845,7 @@ __global__ void __launch_bounds__(GAUSS_BIG_T) k_gaussian_big(const float4* __re
 // Eigen clamp + information matrix + observation weight of every set from its centred second moments: one THREAD per
 // set (the 3x3 Jacobi sweeps are long dependent FP64 chains; with one lane per warp they cost 32x the issue slots).
 __global__ void k_gaussian_fin(CellStore cs, const LevelInfo* __restrict__ li, const double* __restrict__ mom) {
+    DMSA_PDL_ENTER();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_sets(li)) return;
     double a[6];
@@ -840,6 +857,7 @@ __global__ void k_gaussian_fin(CellStore cs, const LevelInfo* __restrict__ li, c
 // Gaussians.h:172-177: w0 = (1 / n) * observation weight (1, OptimizablePointSet.h:52), w = w0 / mean(w0)   (one block;
 // deterministic double reduction, one rounding).  Depends on the set sizes only, so it runs beside the set statistics.
 __global__ void k_weights(CellStore cs, const LevelInfo* __restrict__ li) {
+    DMSA_PDL_ENTER();
     __shared__ double part[1024];
     const int G = total_sets(li);
     double s = 0;
@@ -867,6 +885,7 @@ struct Chunk {
 };
 __global__ void k_cell_plan(CellStore cs, const LevelInfo* __restrict__ li, int CH, int fuse_max, int rank, int world, int bound, int* __restrict__ kind,
                             int* __restrict__ nchunk, int* __restrict__ okey, int* __restrict__ oval) {
+    DMSA_PDL_ENTER();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_sets(li)) {
         if (g <= bound) nchunk[g] = 0;  // the scan behind this kernel runs over bound + 1 entries
@@ -884,6 +903,7 @@ __global__ void k_cell_plan(CellStore cs, const LevelInfo* __restrict__ li, int 
 // order[] = set indices grouped by size class, longest class first.  The position inside a class comes from an atomic
 // cursor: the order is a scheduling hint only and does not influence any result.
 __global__ void k_cell_order(const LevelInfo* __restrict__ li, const int* __restrict__ okey, int* __restrict__ hist_cursor, int* __restrict__ order) {
+    DMSA_PDL_ENTER();
     __shared__ int base[ORDER_CLASSES];
     if (threadIdx.x == 0) {
         int acc = 0;
@@ -902,6 +922,7 @@ __global__ void k_cell_order(const LevelInfo* __restrict__ li, const int* __rest
 // chunk_off = exclusive scan of nchunk (G+1 entries, last = total)
 __global__ void k_chunk_fill(CellStore cs, const LevelInfo* __restrict__ li, int CH, const int* __restrict__ nchunk, const int* __restrict__ chunk_off,
                              Chunk* __restrict__ chunks) {
+    DMSA_PDL_ENTER();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_sets(li)) return;
     const int nc = nchunk[g], o = chunk_off[g], s = cs.start[g], n = cs.n[g];

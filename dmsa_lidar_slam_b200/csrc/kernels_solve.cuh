@@ -18,9 +18,11 @@
 //               in place (a position table replaces the physical row swaps), panels of 8 columns, ONE barrier per panel;
 //   k_inv128    the n right-hand sides are independent: one warp per column of the inverse, L\U staged column-major in
 //               shared memory, per step one shuffle broadcast + a multiply-subtract per row (chain of 2 n steps);
-//   k_step_fin  step = (-alpha X) g, NaN flag, infinity-norm clamp.
+//   k_step_fin  step = (-alpha X) g, NaN flag, infinity-norm clamp (products in parallel, the additions of a row in order).
 #pragma once
 #include <cuda_runtime.h>
+
+#include "pdl.cuh"
 
 namespace dmsa {
 
@@ -66,6 +68,7 @@ __device__ __forceinline__ bool lu_div_operand_safe(double x) {  // zero, or a n
 // unblocked elimination).
 template <bool DBG>
 __global__ void __launch_bounds__(LU128_T, 1) k_lu128(Lu128Args q) {
+    DMSA_PDL_ENTER();
     __shared__ double f_s[2][LU128_PANEL][LM_DEV_MAXN];  // multipliers of the panel's steps, by physical row
     __shared__ int pinfo[2][LU128_PANEL];                // pivot of each step: (position it came from) * 128 + physical row
     __shared__ int s_piv[LM_DEV_MAXN];
@@ -288,6 +291,7 @@ struct Inv128Args {
     double* XT;           // out: the inverse TRANSPOSED: XT[c * ld + i] = X[i][c]
 };
 __global__ void __launch_bounds__(INV128_WARPS * 32, 1) k_inv128(Inv128Args q) {
+    DMSA_PDL_ENTER();
     extern __shared__ __align__(16) double inv_s[];  // LUT (n x ld) | rdiag (n)
     const int n = q.n, ld = q.ld, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* __restrict__ S = inv_s;
@@ -357,40 +361,48 @@ struct StepFinArgs {
     double* step2;     // second copy inside the iteration's read-back block (may be null)
     double* tail;      // out [0] = err0 (copied from hg), [1] = 1.0 if the step contains NaN (then left unclamped), else 0.0
 };
-__global__ void __launch_bounds__(LM_DEV_MAXN, 1) k_step_fin(StepFinArgs q) {
+// The n^2 products (-alpha X[i][b]) g[b] are independent: 512 threads form them with coalesced loads (one L2 round trip)
+// and leave them in shared memory; only the n additions of a row are a dependent chain (ascending b, like the host).
+#define STEPFIN_T 512
+__global__ void __launch_bounds__(STEPFIN_T, 1) k_step_fin(StepFinArgs q) {
+    DMSA_PDL_ENTER();
+    extern __shared__ __align__(16) double sf_t[];  // [b][ld] products
     __shared__ double s_red[2][LM_DEV_MAXN / 32];
     __shared__ double s_g[LM_DEV_MAXN];
     __shared__ int s_nan;
-    const int n = q.n, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = q.n, ld = q.ld, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double INF = __longlong_as_double(0x7ff0000000000000ll);
     if (tid == 0) s_nan = 0;
     if (tid < n) s_g[tid] = q.hg[(size_t)n * n + tid];
     __syncthreads();
+    {
+        const double na = -q.alpha;
+        const int i = tid & (LM_DEV_MAXN - 1), b0 = tid / LM_DEV_MAXN;  // X[i][b] = XT[b * ld + i]: coalesced over the threads
+        if (i < n) {
+#pragma unroll 8
+            for (int b = b0; b < n; b += STEPFIN_T / LM_DEV_MAXN) sf_t[(size_t)b * ld + i] = __dmul_rn(__dmul_rn(na, q.XT[(size_t)b * ld + i]), s_g[b]);
+        }
+    }
+    __syncthreads();
     double s = 0.0, mx = -INF, mn = INF;
     if (tid < n) {
-        const double na = -q.alpha;
-        const double* __restrict__ xr = q.XT + tid;  // X[tid][b] = XT[b * ld + tid]: coalesced over the threads
-        int b = 0;
-        for (; b + 8 <= n; b += 8) {
-            double xv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) xv[u] = xr[(size_t)(b + u) * q.ld];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s = __dadd_rn(s, __dmul_rn(__dmul_rn(na, xv[u]), s_g[b + u]));
-        }
-        for (; b < n; ++b) s = __dadd_rn(s, __dmul_rn(__dmul_rn(na, xr[(size_t)b * q.ld]), s_g[b]));
+        const double* __restrict__ tr = sf_t + tid;
+#pragma unroll 8
+        for (int b = 0; b < n; ++b) s = __dadd_rn(s, tr[(size_t)b * ld]);
         if (s != s) s_nan = 1;
         mx = s;
         mn = s;
     }
+    if (tid < LM_DEV_MAXN) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    if (lane == 0) {
-        s_red[0][wid] = mx;
-        s_red[1][wid] = mn;
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        }
+        if (lane == 0) {
+            s_red[0][wid] = mx;
+            s_red[1][wid] = mn;
+        }
     }
     __syncthreads();
     if (tid == 0) q.tail[0] = q.hg[(size_t)n * n + n];

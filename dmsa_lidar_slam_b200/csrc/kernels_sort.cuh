@@ -14,6 +14,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "pdl.cuh"
+
 #include "kernels_sets.cuh"
 
 namespace dmsa {
@@ -114,6 +116,7 @@ struct PrepArgs {
 #define RING_SHIFT 48
 __device__ __forceinline__ bool ring_packed(const LevelInfo* info, const int* flags) { return info->depth <= 15 && flags[1] == 0; }
 __global__ void __launch_bounds__(RS_T) k_sort_prepare(SortArgs a, PrepArgs pa) {
+    DMSA_PDL_ENTER();
     __shared__ u32_t sh[RS_MAXPASS * RS_BINS];
     const int seg = blockIdx.y, lvl = pa.level[seg];
     const LevelInfo* __restrict__ info = pa.infos + lvl;
@@ -158,6 +161,7 @@ __global__ void __launch_bounds__(RS_T) k_sort_prepare(SortArgs a, PrepArgs pa) 
 }
 // the same histograms for keys that already exist (keyA of every segment)
 __global__ void __launch_bounds__(RS_T) k_sort_hist(SortArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ u32_t sh[RS_MAXPASS * RS_BINS];
     const int seg = blockIdx.y;
     const u64_t* __restrict__ code = a.seg[seg].keyA;
@@ -193,6 +197,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 // 3 blocks per SM (<= 85 registers, 58 KB of shared memory each): the 346 tiles of the two 705 k-point levels of BASELINE
 // config 2 are resident together, one wave.
 __global__ void __launch_bounds__(RS_T, 3) k_sort_pass(SortArgs a) {
+    DMSA_PDL_ENTER();
     extern __shared__ __align__(16) unsigned char rs_smem[];
     u64_t* s_keys = reinterpret_cast<u64_t*>(rs_smem);           // [RS_TILE]
     u32_t* s_vals = reinterpret_cast<u32_t*>(s_keys + RS_TILE);  // [RS_TILE]
@@ -408,6 +413,7 @@ struct SegmentArgs {
     int* ticket;    // zeroed
 };
 __global__ void __launch_bounds__(SG_T, 3) k_segment(SegmentArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ u64_t s_agg[SG_T / 32 + 2];
     __shared__ u64_t s_code[SG_TILE + SG_TILE / SG_ITEMS + 2 + 18];  // tile + halo, one pad word per SG_ITEMS (conflict-free thread-blocked reads)
     __shared__ int s_t;
@@ -554,6 +560,7 @@ struct EmitArgs {
 };
 template <bool FROM_PLAN>
 __global__ void __launch_bounds__(EM_T) k_emit(EmitArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ u32_t s_w[EM_T / 32];
     __shared__ u64_t s_red[EM_T / 32 + 2];
     __shared__ int s_t;
@@ -668,6 +675,7 @@ struct GatherArgs {
     int level[RS_MAXSEG];
 };
 __global__ void k_gather2(GatherArgs a, const float4* __restrict__ local, const int* __restrict__ tid, int identity_row, const float4* __restrict__ world) {
+    DMSA_PDL_ENTER();
     const int seg = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.infos[a.level[seg]].n_valid) return;
@@ -688,6 +696,7 @@ struct ScanArgs {
     int* ticket;    // zeroed
 };
 __global__ void __launch_bounds__(CS_T) k_scan_excl(ScanArgs a) {
+    DMSA_PDL_ENTER();
     __shared__ u32_t s_w[CS_T / 32];
     __shared__ u64_t s_red[CS_T / 32 + 2];
     __shared__ int s_t;
