@@ -38,13 +38,18 @@
 // operation was issued since that predecessor, and only inside a PdlScope (a span of a C-ABI call in which nothing but
 // this library enqueues work on the context's streams; the first launch of an outermost scope never chains).
 static std::atomic<unsigned long long> g_opEpoch{1};
+// Once the process owns an NCCL communicator no launch chains any more: NCCL enqueues its own kernels on the contexts'
+// streams (with whatever launch attributes its version uses), and the multi-GPU runs that would have to prove the
+// combination are the expensive ones.  The sharded paths therefore launch exactly as they did before PDL.
+static std::atomic<bool> g_commSeen{false};
 static inline void pdlBreak() { g_opEpoch.fetch_add(1, std::memory_order_relaxed); }
 #define cudaMemcpyAsync(...) (pdlBreak(), cudaMemcpyAsync(__VA_ARGS__))
 #define cudaMemsetAsync(...) (pdlBreak(), cudaMemsetAsync(__VA_ARGS__))
 #define cudaMemcpy(...) (pdlBreak(), cudaMemcpy(__VA_ARGS__))
 #define cudaMemcpyFromSymbol(...) (pdlBreak(), cudaMemcpyFromSymbol(__VA_ARGS__))
 #define cudaStreamWaitEvent(...) (pdlBreak(), cudaStreamWaitEvent(__VA_ARGS__))
-#define cudaEventRecord(...) (pdlBreak(), cudaEventRecord(__VA_ARGS__))
+// (cudaEventRecord does not break a chain: the record completes with the kernel before it, and the kernel behind it waits for
+// that same kernel in DMSA_PDL_ENTER() whether or not the driver lets it start early)
 #define cudaLaunchCooperativeKernel(...) (pdlBreak(), cudaLaunchCooperativeKernel(__VA_ARGS__))
 
 using namespace dmsa;
@@ -371,7 +376,7 @@ static inline void launchKernel(dmsa_b200_ctx* ctx, void (*kern)(KArgs...), dim3
     int slot = -1;
     if (strm == ctx->stream) slot = 0;
     else if (strm == ctx->stream2) slot = 1;
-    const bool chain = g_pdl && ctx->pdlDepth > 0 && slot >= 0 && ctx->pdlEpoch[slot] == ep;
+    const bool chain = g_pdl && ctx->pdlDepth > 0 && slot >= 0 && ctx->pdlEpoch[slot] == ep && !g_commSeen.load(std::memory_order_relaxed);
     cfg.numAttrs = chain ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);  // (errors surface at the next cudaGetLastError, like <<< >>>)
     if (slot >= 0) ctx->pdlEpoch[slot] = ep;
@@ -802,7 +807,8 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
     const int deferBound = defer ? (int)std::min<int64_t>(cap, (int64_t)ctx->Gguess + ctx->Gguess / 4 + 1024) : cap;
     const float factors[2] = {st->grid_size_1_factor, st->grid_size_2_factor};
     for (int l = 0; l < 2; ++l) ctx->levelOn[l] = factors[l] > std::numeric_limits<float>::min();  // DmsaOptimizer.h:81,85
-    CK(cudaMemsetAsync(ctx->d_linfo.p, 0, 2 * sizeof(LevelInfo), ctx->stream));
+    if (!ctx->levelOn[0] && !ctx->levelOn[1]) CK(cudaMemsetAsync(ctx->d_linfo.p, 0, 2 * sizeof(LevelInfo), ctx->stream));  // (otherwise k_anchor clears the records)
+    int prezeroedPasses = -1;  // >= 0: k_keys cleared phase 2's control block for that number of digit passes
     // phase 1: anchors, keys, octree roots
     {
     ProfScope prof_(ctx, PROF_SETS_KEYS);
@@ -815,8 +821,27 @@ int buildSets(dmsa_b200_ctx* ctx, const dmsa_b200_settings* st, bool defer = fal
         plan.n++;
     }
     if (plan.n > 0) {
+        // with a depth guess the layout of phase 2's control block is known already: k_keys clears it (and the ring-test flags)
+        // on the side, and phase 2 starts without its two memsets
+        ZeroRanges zr{};
+        int npass0 = 1;
+        bool guess0 = true;
+        for (int l = 0; l < 2; ++l) {
+            if (!ctx->levelOn[l]) continue;
+            if (ctx->cachedDepth[l] <= 0) guess0 = false;
+            npass0 = std::max(npass0, (std::min(64, 3 * ctx->cachedDepth[l] + 1) + 7) / 8);
+        }
+        if (guess0) {
+            const CtlLayout cl0(N, npass0, cap);
+            CK(ctx->d_ctl.ensure(cl0.bytes));
+            zr.p[0] = reinterpret_cast<unsigned int*>(ctx->d_ctl.p);
+            zr.words[0] = cl0.bytes / sizeof(unsigned int);
+            zr.p[1] = reinterpret_cast<unsigned int*>(ctx->d_raw_diff.p);
+            zr.words[1] = 2 * (size_t)N2;
+            prezeroedPasses = npass0;
+        }
         LAUNCH(k_anchor, 1, 32, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, deferBound);
-        LAUNCH(k_keys, dim3(nb, plan.n), DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_keys.p, ctx->d_bb.p, nb);
+        LAUNCH(k_keys, dim3(nb, plan.n), DMSA_KEYS_BLOCK, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_keys.p, ctx->d_bb.p, nb, zr);
         LAUNCH(k_root, plan.n, 1024, 0, ctx->d_world.p, N, plan, ctx->d_linfo.p, ctx->d_bb.p, nb);
     }
     }
@@ -856,8 +881,11 @@ phase2:
         CK(cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
         ctx->sortAttr = true;
     }
-    CK(cudaMemsetAsync(ctx->d_ctl.p, 0, cl.bytes, strm));
-    CK(cudaMemsetAsync(ctx->d_raw_diff.p, 0, 2 * N2 * sizeof(int), strm));
+    if (prezeroedPasses != npass) {  // (no depth guess, or phase 2 is being redone with a deeper tree)
+        CK(cudaMemsetAsync(ctx->d_ctl.p, 0, cl.bytes, strm));
+        CK(cudaMemsetAsync(ctx->d_raw_diff.p, 0, 2 * N2 * sizeof(int), strm));
+    }
+    prezeroedPasses = -1;  // a second pass through phase 2 finds the control block used
     SortArgs sa;
     memset(&sa, 0, sizeof(sa));
     PrepArgs pa;
@@ -2741,6 +2769,7 @@ int dmsa_b200_comm_init(dmsa_b200_ctx* ctx, const void* id128, int32_t rank, int
     }
     ncclUniqueId id;
     memcpy(id.internal, id128, sizeof(id.internal));
+    g_commSeen.store(true, std::memory_order_relaxed);
     ncclResult_t r = nccl_api().CommInitRank(&ctx->comm, world, id, rank);
     if (r != ncclSuccess) {
         ctx->comm = nullptr;

@@ -43,7 +43,6 @@ int preLeaves(dmsa_b200_ctx* ctx, const float4* pts, int n, float res, int* R_ou
     CK(ctx->p_raw_start.ensure(n2));
     CK(ctx->p_raw_diff.ensure(n2));
     cudaStream_t strm = ctx->stream;
-    CK(cudaMemsetAsync(ctx->p_linfo.p, 0, 2 * sizeof(LevelInfo), strm));
     LevelPlan plan;
     plan.n = 1;
     plan.level[0] = 0;
@@ -51,7 +50,7 @@ int preLeaves(dmsa_b200_ctx* ctx, const float4* pts, int n, float res, int* R_ou
     plan.res[0] = res;
     plan.res[1] = res;
     LAUNCH(k_anchor, 1, 32, 0, pts, n, plan, ctx->p_linfo.p, n);
-    LAUNCH(k_keys, dim3(nb, 1), DMSA_KEYS_BLOCK, 0, pts, n, plan, ctx->p_linfo.p, ctx->p_keys.p, ctx->p_bb.p, nb);
+    LAUNCH(k_keys, dim3(nb, 1), DMSA_KEYS_BLOCK, 0, pts, n, plan, ctx->p_linfo.p, ctx->p_keys.p, ctx->p_bb.p, nb, ZeroRanges{});
     LAUNCH(k_root, 1, 1024, 0, pts, n, plan, ctx->p_linfo.p, ctx->p_bb.p, nb);
     LevelInfo li;
     CK(cudaMemcpyAsync(&li, ctx->p_linfo.p, sizeof(LevelInfo), cudaMemcpyDeviceToHost, strm));

@@ -64,7 +64,13 @@ struct LevelPlan {  // the resolution levels built in this pass (DmsaOptimizer.h
 };
 __global__ void k_anchor(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* infos, int bound) {
     DMSA_PDL_ENTER();
-    if (blockIdx.x != 0 || (int)threadIdx.x >= plan.n) return;
+    if (blockIdx.x != 0) return;
+    {  // both level records start from zero (a disabled level keeps G = R = 0); launched with one warp
+        unsigned int* w = reinterpret_cast<unsigned int*>(infos);
+        for (unsigned int i = threadIdx.x; i < 2 * sizeof(LevelInfo) / sizeof(unsigned int); i += blockDim.x) w[i] = 0u;
+        __syncwarp();
+    }
+    if ((int)threadIdx.x >= plan.n) return;
     LevelInfo* info = infos + plan.level[threadIdx.x];
     info->bound = bound;
     const double res = (double)plan.res[threadIdx.x];  // OctreePointCloud(const double resolution)
@@ -113,9 +119,23 @@ __global__ void k_anchor(const float4* __restrict__ world, int N, LevelPlan plan
 // points closer to a voxel face than PCL's bounding-box fudge (float eps on the upper side) or than the rounding
 // noise of the lattice arithmetic; only those can make the exact double test of k_root disagree with the integer test.
 // grid = (blocks of 256 points, levels): both resolution levels in one launch.
+// The launch also zeroes up to two word ranges the NEXT phase needs cleared (the control block of the sort / scans and the
+// ring-test flags: ~7 MB at BASELINE config 2) — spread over all blocks it costs nothing here and takes two memsets off the
+// dependent chain between k_root and k_sort_prepare.
+struct ZeroRanges {
+    unsigned int* p[2];
+    size_t words[2];
+};
 __global__ void k_keys(const float4* __restrict__ world, int N, LevelPlan plan, LevelInfo* __restrict__ infos, int* __restrict__ keys_all,
-                       int* __restrict__ bb_all, int nb) {
+                       int* __restrict__ bb_all, int nb, ZeroRanges zr) {
     DMSA_PDL_ENTER();
+    {
+        const size_t nthreads = (size_t)gridDim.x * gridDim.y * blockDim.x;
+        const size_t t0 = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            for (size_t w = t0; w < zr.words[r]; w += nthreads) zr.p[r][w] = 0u;
+    }
     const int lvl = plan.level[blockIdx.y];
     LevelInfo* __restrict__ info = infos + lvl;
     int* __restrict__ keys = keys_all + (size_t)3 * N * lvl;

@@ -175,3 +175,31 @@ def test_host_solver_pool_is_race_free_under_thread_sanitizer(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, DMSA_B200_SOLVER_THREADS="1"))
     assert "mismatches 0" in r.stdout, r.stdout + r.stderr[-2000:]
     assert "ThreadSanitizer" not in r.stderr and r.returncode == 0, r.stderr[-3000:]
+
+
+def test_no_kernel_reads_memory_ahead_of_its_dependency_wait():
+    """Programmatic dependent launch (csrc/pdl.cuh): a kernel is set up while its predecessor still runs and must not touch
+    memory before griddepcontrol.wait (SASS: ACQBULK).  ptxas hoists non-coherent loads (LDG...CONSTANT: __ldg, loads through
+    const __restrict__ kernel parameters) above that instruction, which once gave wrong set counts on the GPU — so the shipped
+    library must hold no such load outside libdevice's sin / cos reduction tables, and no memory instruction ahead of the wait."""
+    import shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    lib = build.build_library()
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    kernels = re.split(r"\n\s*Function : ", sass)[1:]
+    assert len(kernels) >= 60
+    trig_tables = ("k_pose_chain", "k_dense_table", "k_dense_poses", "k_normals_knn6")  # Payne-Hanek table of sin / cos / atan2
+    for k in kernels:
+        name = k.split("\n", 1)[0]
+        ins = [re.sub(r"/\*.*?\*/", "", l).strip() for l in k.split("\n") if re.match(r"\s*/\*[0-9a-f]{4,}\*/", l)]
+        if "k_chol_solve" in name:  # cooperative launch, never a programmatic dependent
+            continue
+        wait = [i for i, l in enumerate(ins) if "ACQBULK" in l]
+        assert wait and any("PREEXIT" in l for l in ins), f"{name}: no griddepcontrol prologue"
+        early = [l for l in ins[: wait[0]] if re.search(r"\b(LDG|LD\.|ST\.|STG|ATOM|ATOMG|RED|LDS|STS)\b", l)]
+        assert not early, f"{name}: memory instructions ahead of griddepcontrol.wait: {early[:3]}"
+        if not any(t in name for t in trig_tables):
+            assert ".CONSTANT" not in k, f"{name}: non-coherent load in a kernel that may be launched as a programmatic dependent"
