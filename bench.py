@@ -505,6 +505,15 @@ def run_sliding(args):
         if dom in tj:
             traffic, traffic_src = tj[dom], tj["_source"]
     breakdown = {k: round(v[0] / max(args.steps, 1), 4) for k, v in prof.items() if v[1]}
+    # the kernel family that IS memory-shaped by SURVEY §8d: set construction (keys, sort, segmentation, statistics), 24 B per
+    # point (read the world point, write the member record), 4 B per membership (the sorted index) and 48 B per set (its record)
+    sets_ms = sum(v for k, v in breakdown.items() if k.startswith("sets_"))
+    sets_bytes = 24.0 * N_points + 4.0 * float(M) + 48.0 * float(G)
+    sets_roofline = {"phases": [k for k in breakdown if k.startswith("sets_")], "ms_per_build": sets_ms, "algorithmic_bytes_per_build": sets_bytes,
+                     "achieved": sets_bytes / (sets_ms * 1e-3) / 1e9 if sets_ms > 0 else None, "unit": "GB/s",
+                     "frac": sets_bytes / (sets_ms * 1e-3) / 1e9 / peak if sets_ms > 0 else None,
+                     "note": "a chain of ~20 dependent launches over 1.4 M keys (four radix digit passes, two chained scans): bound by the latency of "
+                             "the chain, not by bandwidth (DESIGN.md §5)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -529,7 +538,8 @@ def run_sliding(args):
                      "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes, "memberships_per_launch": units_M, "sets_per_launch": units_G,
                      "vectors_per_launch": V, "peak_source": peak_src,
                      "fp32": {"algorithmic_flop_per_launch": flop_alg, "achieved_tflops": flop_alg / (avg_ms * 1e-3) / 1e12,
-                              "note": "the forward-difference formulation is FP32-issue bound, not HBM bound (SURVEY §8d, DESIGN.md)"}},
+                              "note": "the forward-difference formulation is FP32-issue bound, not HBM bound (SURVEY §8d, DESIGN.md)"},
+                     "set_build": sets_roofline},
         "device_ms_per_step_breakdown": breakdown,
         "clocks": clk,
         "last_step": {"G": last["num_gaussians"], "error0": last["error0"], "best_step": last["best_step"], "stop": last["stop"]},
