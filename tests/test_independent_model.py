@@ -313,3 +313,44 @@ def test_keyframe_model_with_and_without_split_sets(split):
         t2[:, 1:] = p[3 * (n - 1):].reshape(n - 1, 3).T
         col = (residuals(keyframe_world(sm, r2, t2)[0], sets_np, infos, wt)[idx] - e_np) / h
         assert rel(col, J_or[:G, k]) < 2e-3, (k, rel(col, J_or[:G, k]))
+
+
+# ---- one loop body of optimizeSet (DmsaOptimizer.h:69-144) with the numpy model ---------------------------------------------
+def test_one_loop_body_step_line_search_and_update():
+    """H = J^T J + lambda I, step = -alpha H^-1 J^T e0, infinity-norm clamp, the nine line-search trials with a strict `<`, the
+    parameter update — all in numpy on the numpy model's own cost function — against the oracle's iteration trace."""
+    win = synth.make_config("tiny")
+    st = dict(SETTINGS)
+    om = ob.OracleModel.from_window(win)
+    om.set_mode(0)
+    assert om.iteration(ob.settings(**st)) == 0  # ran to the end of the body, no stop condition
+    tr = om.last_trace()
+    mdl = NumpyTrajectoryModel(win)
+    p0 = mdl.params()
+    world0 = mdl.world(p0)[0]
+    sets_np = []
+    for f in (2.0, 5.0):
+        sets_np += voxel_sets(world0, mdl.ring, np.float32(f) * np.float32(mdl.min_grid), st["min_num_points_per_set"])
+    infos, wt = gaussians(world0, sets_np)
+    cost = lambda p: residuals(mdl.world(p)[0], sets_np, infos, wt)
+    e0 = cost(p0)
+    assert len(e0) == len(tr["e0"]) and abs(e0 @ e0 - tr["e0"] @ tr["e0"]) <= 1e-5 * (e0 @ e0)  # (set order differs; the sums do not care)
+    h = float(np.sqrt(np.float64(np.finfo(np.float32).eps)))
+    J = np.stack([(cost(p0 + h * np.eye(len(p0))[k]) - e0) / h for k in range(len(p0))], axis=1)
+    H = J.T @ J + float(np.float32(1e-5)) * np.eye(len(p0))  # lambda_diag is a float member
+    step = -st["step_length_optim"] * np.linalg.inv(H) @ (J.T @ e0)
+    m = max(step.max(), -step.min())
+    if m > st["max_step"]:
+        step = st["max_step"] / m * step
+    # observed: H 1.8e-5, g 1.1e-5, step 1.1e-3 (cond(H) = 5.8e3 amplifies the float noise of J), line-search costs 2.3e-7
+    assert rel(H, tr["H"]) < 1e-4 and rel(J.T @ e0, tr["g"]) < 1e-4
+    assert rel(step, tr["step"]) < 1e-2, rel(step, tr["step"])
+    # the line search itself, on the ORACLE's step so that both sides evaluate the same nine points
+    ls = np.array([float(np.dot(e, e)) for e in (cost(p0 + 0.1 * k * tr["step"]) for k in range(1, 10))])
+    assert rel(ls, tr["ls_cost"]) < 1e-5, rel(ls, tr["ls_cost"])
+    best, best_k = float(e0 @ e0), 0
+    for k in range(1, 10):
+        if ls[k - 1] < best:
+            best, best_k = ls[k - 1], k
+    assert best_k == tr["best_k"] and best_k > 0
+    assert rel(p0 + 0.1 * best_k * tr["step"], om.get_params()) < 1e-12
