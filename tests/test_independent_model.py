@@ -354,3 +354,114 @@ def test_one_loop_body_step_line_search_and_update():
             best, best_k = ls[k - 1], k
     assert best_k == tr["best_k"] and best_k > 0
     assert rel(p0 + 0.1 * best_k * tr["step"], om.get_params()) < 1e-12
+
+
+# ---- the additional residual rows -------------------------------------------------------------------------------------------
+def test_imu_factor_rows_independent():
+    """ContinuousTrajectory::updateImuError (ContinuousTrajectory.h:603-661) in numpy / scipy against the oracle's extra rows."""
+    win = synth.make_config("tiny")
+    n = win["n_poses"]
+    rng = np.random.default_rng(11)
+    om = ob.OracleModel.from_window(win)
+    om.set_mode(0)
+    preR = np.stack([Rotation.from_rotvec(win["rel_orient"][:, k] + rng.normal(0, 0.002, 3)).as_matrix().ravel() for k in range(n)])
+    preP, preV = rng.normal(0, 0.1, (n, 3)), rng.normal(0, 0.1, (n, 3))
+    cov = np.stack([(lambda A: A @ A.T + 9 * np.eye(9))(rng.normal(size=(9, 9))).ravel() for _ in range(n)])
+    bal = float(np.float32(0.001))  # `double balancingImu = 0.001f`, ContinuousTrajectory.h:52
+    grav = np.array([0.0, 0.0, -9.805])
+    pi = np.ascontiguousarray(om.timing["param_indices"], dtype=np.int32)
+    a = [ob.c64(x) for x in (preR, preP, preV, cov)]
+    om.L.orc_traj_set_imu(om.h, ob._p(pi), ob._p(a[0]), ob._p(a[1]), ob._p(a[2]), ob._p(a[3]), bal, ob._p(ob.c64(grav)))
+    om.update_global_points()
+    G = om.build_sets(ob.settings(**SETTINGS))
+    assert om.E == n - 1
+    e_or = om.cost()[G:]
+
+    mdl = NumpyTrajectoryModel(win)
+    ro, rt = mdl.rel_orient0, mdl.rel_transl0
+    go, gt = relative2global(ro, rt)
+    stamps, tt, dt = mdl.tim["stamps"], mdl.tim["traj_time"], win["dt_res"]
+    dense_t = np.stack([FloaterHormannInterpolator(stamps, gt[a_], d=2)(tt) for a_ in range(3)], axis=0)  # 3 x n_total
+    e_np = np.zeros(n - 1)
+    for k in range(1, n):
+        R0 = axang2rotm(go[:, k - 1])
+        delta_t = stamps[k] - stamps[k - 1]
+        v0 = (dense_t[:, pi[k - 1] + 1] - dense_t[:, pi[k - 1]]) / dt
+        v1 = (dense_t[:, pi[k]] - dense_t[:, pi[k] - 1]) / dt
+        pos_err = R0.T @ (gt[:, k] - gt[:, k - 1] - v0 * delta_t - 0.5 * delta_t ** 2 * grav) - preP[k]
+        # global2relative() first (:606): the relative rotation of pose k is R_{k-1}^T R_k of the global poses
+        Rrel = axang2rotm(go[:, k - 1]).T @ axang2rotm(go[:, k])
+        rot_err = Rotation.from_matrix(preR[k].reshape(3, 3).T @ Rrel).as_rotvec()
+        vel_err = R0.T @ (v1 - v0 - grav * delta_t) - preV[k]
+        c = np.concatenate([rot_err, vel_err, pos_err])
+        e_np[k - 1] = np.sqrt(c @ cov[k].reshape(9, 9) @ c * bal)
+    assert rel(e_np, e_or) < 1e-7, rel(e_np, e_or)
+
+
+def test_gravity_and_odometry_rows_independent():
+    """MapManagement::updateGravityErrors / updateOdometryErrors (MapManagement.h:210-252; constants :58-70) in numpy / scipy."""
+    sm = synth.make_keyframe_submap(n_keyframes=4, n_points=3000, seed=5)
+    n = sm["n_keyframes"]
+    rng = np.random.default_rng(3)
+    om = ob.OracleModel.from_submap(sm)
+    om.set_mode(0)
+    grav_m = np.tile([0.0, 0.0, -9.805], (n, 1)) + rng.normal(0, 0.05, (n, 3))
+    plaus = np.array([1, 1, 0, 1], dtype=np.int32)
+    odomT = sm["rel_transl"].T + rng.normal(0, 0.01, (n, 3))
+    odomR = np.stack([Rotation.from_rotvec(sm["rel_orient"][:, k] + rng.normal(0, 0.002, 3)).as_matrix().ravel() for k in range(n)])
+    bal_g, bal_o = 1.0, 1000.0
+    om.L.orc_kf_set_gravity(om.h, ob._p(ob.c64(grav_m)), ob._p(np.ascontiguousarray(plaus)), bal_g)
+    om.L.orc_kf_set_odometry(om.h, ob._p(ob.c64(odomT)), ob._p(ob.c64(odomR)), bal_o)
+    om.update_global_points()
+    st = dict(num_iter=1, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=6, min_num_gaussians=10)
+    G = om.build_sets(ob.settings(**st))
+    assert om.E == 2 * n - 1
+    e_or = om.cost()[G:]
+
+    ro, rt = sm["rel_orient"].astype(np.float64), sm["rel_transl"].astype(np.float64)
+    go, _ = relative2global(ro, rt)
+    gravity = np.array([0.0, 0.0, -9.805])
+    cov_grav_inv = np.linalg.inv(0.3 ** 2 * np.eye(3))  # std_dev_acc = 0.3, MapManagement.h:48,66-67
+    e_g = np.zeros(n)
+    for k in range(1, n):
+        if plaus[k]:
+            d = axang2rotm(go[:, k]) @ grav_m[k] - gravity
+            e_g[k] = np.sqrt(d @ cov_grav_inv @ d * bal_g)
+    cinv = np.linalg.inv(0.01 ** 2 * np.eye(3))
+    e_o = np.zeros(n - 1)
+    for k in range(1, n):
+        td = odomT[k] - rt[:, k]
+        od = Rotation.from_matrix(axang2rotm(ro[:, k]).T @ odomR[k].reshape(3, 3)).as_rotvec()
+        e_o[k - 1] = np.sqrt((td @ cinv @ td + od @ cinv @ od) * bal_o)
+    assert rel(np.concatenate([e_g, e_o]), e_or) < 1e-7, rel(np.concatenate([e_g, e_o]), e_or)  # gravity rows, then odometry rows (:185-187)
+
+
+def test_centralize_and_decentralize_independent():
+    """ContinuousTrajectory::centralize / decentralize (ContinuousTrajectory.h:75-100): pose 0 moves to the origin, the static
+    points move with it (a float subtraction), the relative poses of the other control poses do not change, and the round trip
+    restores poses and points."""
+    win = synth.make_config("tiny")
+    om = ob.OracleModel.from_window(win)
+    om.set_mode(0)
+    mdl = NumpyTrajectoryModel(win)
+    origin = mdl.rel_transl0[:, 0].copy()
+    om.update_global_points()
+    w_before = om.world_points()[:, :3].copy()
+    om.centralize()
+    po = om.get_poses()
+    ro, rt = mdl.rel_orient0.copy(), mdl.rel_transl0.copy()
+    rt[:, 0] = 0.0
+    go, gt = relative2global(ro, rt)
+    assert np.abs(po["rel_transl"][:, 0]).max() == 0.0 and rel(po["rel_transl"][:, 1:], rt[:, 1:]) == 0.0 and rel(po["rel_orient"], ro) == 0.0
+    assert rel(po["glob_transl"], gt) < 1e-14 and rel(po["glob_orient"], go) < 1e-12
+    om.update_global_points()
+    w_c = om.world_points()[:, :3]
+    n_scan = len(mdl.local)
+    assert np.array_equal(w_c[n_scan:], (mdl.static - origin.astype(np.float32)).astype(np.float32))  # static points: one float subtraction
+    # the scan points follow the centralised trajectory: same as shifting the uncentralised world points, up to float rounding
+    assert np.abs(w_c[:n_scan] - (w_before[:n_scan].astype(np.float64) - origin)).max() < 1e-5
+    om.decentralize()
+    pd = om.get_poses()
+    assert rel(pd["rel_transl"], mdl.rel_transl0) < 1e-12 and rel(pd["rel_orient"], mdl.rel_orient0) < 1e-10
+    om.update_global_points()
+    assert np.abs(om.world_points()[:, :3] - w_before).max() < 1e-5
