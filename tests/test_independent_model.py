@@ -15,9 +15,12 @@ path's are twin code, so their agreement proves determinism, not correctness):
 Everything here is float64 except the transform / world-point product the reference does in float (the information matrices
 come out of a float64 symmetric eigen-decomposition, the reference's out of EigenSolver<Matrix3f>), so the comparison with the
 FAITHFUL oracle is up to float noise, not equality.  Observed on tiny / cfg1: dense transforms and world points identical after
-the float rounding, information matrices 6e-8 (median) / 5e-5 (worst set), e0 3e-7 / 1e-6, J 5e-5, H 2e-5, g 1e-5 relative.
+the float rounding, information matrices 6e-8 (median) / 5e-5 (worst set), e0 3e-7 / 1e-6, J 5e-5, H 2e-5, g 1e-5 relative;
+at BASELINE config 2 (705 360 points): all 8 956 sets with identical members, information matrices 7e-8 / 1e-5, e0 6e-8.
 Sets are matched by their member lists.
 """
+import os
+
 import numpy as np
 import pytest
 from scipy.interpolate import FloaterHormannInterpolator
@@ -130,19 +133,22 @@ def oracle_sets_as_lists(so):
 
 def match(sets_np, sets_or):
     """index of every oracle set in the numpy list (member lists must be equal as sets of point indices)"""
-    lut = {tuple(m.tolist()): i for i, m in enumerate(sets_np)}
-    return np.array([lut[tuple(np.sort(m).tolist())] for m in sets_or])
+    lut = {}
+    for i, m in enumerate(sets_np):
+        lut.setdefault(tuple(m.tolist()), []).append(i)  # (a fine and a coarse voxel may hold exactly the same points)
+    return np.array([lut[tuple(np.sort(m).tolist())].pop(0) for m in sets_or])
 
 
 def rel(a, b):
     return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) / max(np.linalg.norm(b), 1e-300))
 
 
-@pytest.fixture(scope="module", params=["tiny", "cfg1"])
+@pytest.fixture(scope="module", params=["tiny", "cfg1", "cfg2"])
 def pair(request):
     win = synth.make_config(request.param)
     st = dict(SETTINGS, min_num_points_per_set=6 if request.param == "tiny" else 10)
     om = ob.OracleModel.from_window(win)
+    om.set_threads(os.cpu_count() or 8)
     om.set_mode(0)  # faithful
     om.update_global_points()
     G = om.build_sets(ob.settings(**st))
@@ -191,6 +197,8 @@ def test_sets_information_matrices_weights_and_residuals(pair):
 
 def test_forward_difference_jacobian_H_and_g(pair):
     name, win, st, om, G, mdl = pair
+    if name == "cfg2":
+        pytest.skip("114 numpy cost evaluations of 705 k points: minutes; membership, Gaussians and e0 are checked at cfg2 above")
     world_or = om.world_points()[:, :3]
     sets_np = []
     for f in (2.0, 5.0):
