@@ -539,7 +539,12 @@ def run_sliding(args):
                      "vectors_per_launch": V, "peak_source": peak_src,
                      "fp32": {"algorithmic_flop_per_launch": flop_alg, "achieved_tflops": flop_alg / (avg_ms * 1e-3) / 1e12,
                               "note": "the forward-difference formulation is FP32-issue bound, not HBM bound (SURVEY §8d, DESIGN.md)"},
-                     "set_build": sets_roofline},
+                     "set_build": sets_roofline,
+                     # SURVEY §8d, whole loop body: B_alg = 24 N + 52 M + 144 G + 48 n_total (P + 10) + 8 (P^2 + P + 10) bytes, F_alg = 50 M (P + 10) + 2 G P^2 flop
+                     "whole_iteration": (lambda B, F: {"algorithmic_bytes": B, "achieved": B * value / 1e9, "unit": "GB/s", "frac": B * value / 1e9 / peak,
+                                                       "algorithmic_flop": F, "achieved_tflops": F * value / 1e12})(
+                         24.0 * N_points + 52.0 * float(M) + 144.0 * float(G) + 48.0 * float(traj.timing()["n_total"]) * (P + 10) + 8.0 * (P * P + P + 10),
+                         50.0 * float(M) * (P + 10) + 2.0 * float(G) * P * P)},
         "device_ms_per_step_breakdown": breakdown,
         "clocks": clk,
         "last_step": {"G": last["num_gaussians"], "error0": last["error0"], "best_step": last["best_step"], "stop": last["stop"]},
