@@ -473,3 +473,24 @@ def test_centralize_and_decentralize_independent():
     assert rel(pd["rel_transl"], mdl.rel_transl0) < 1e-12 and rel(pd["rel_orient"], mdl.rel_orient0) < 1e-10
     om.update_global_points()
     assert np.abs(om.world_points()[:, :3] - w_before).max() < 1e-5
+
+
+def test_split_set_membership_on_a_larger_submap():
+    """8 keyframes x 20 000 points, production keyframe settings (gauss_split, 10 points per set): every set of the oracle — the
+    28 split leaves included — with identical members in the numpy restatement of createGaussianSets + splitSet."""
+    sm = synth.make_keyframe_submap(n_keyframes=8, n_points=20000, seed=4)
+    st = dict(num_iter=1, step_length_optim=0.2, max_step=0.01, min_num_points_per_set=10, min_num_gaussians=10, gauss_split=1, epsilon=1e-4)
+    om = ob.OracleModel.from_submap(sm)
+    om.set_threads(os.cpu_count() or 8)
+    om.set_mode(0)
+    om.update_global_points()
+    G = om.build_sets(ob.settings(**st))
+    wo, no = om.world_points()[:, :3], om.world_normals()[:, :3]
+    ring = np.concatenate(sm["rings"]).astype(np.int64)
+    grid = np.float32(min(sm["grid_sizes"]))
+    sets_np = []
+    for f in (2.0, 5.0):
+        sets_np += keyframe_sets(wo, no, ring, np.float32(f) * grid, st["min_num_points_per_set"], 1)
+    so = om.sets()
+    assert (so["sub"] > 0).sum() >= 20 and len(sets_np) == G
+    assert len(set(match(sets_np, oracle_sets_as_lists(so)).tolist())) == G
