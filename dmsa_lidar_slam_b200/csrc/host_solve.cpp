@@ -23,29 +23,60 @@
 // Eigen dynamic inverse() == PartialPivLU: explicit inverse by LU with partial pivoting (DmsaOptimizer.h:113).
 // All n right-hand sides are substituted together, row by row (contiguous axpy loops the host compiler vectorises);
 // every element still sees exactly the operation sequence of a column-by-column substitution (j ascending).
-DMSA_CLONES static void lu_factor_impl(std::vector<double>& a, std::vector<int>& piv, int n) {
+// The elimination is organised in panels of LU_NB pivots: inside a panel the steps run as in the textbook (pivot search,
+// row exchange over the whole row, multipliers, update) but touch the panel's columns only; the columns to the right of
+// the panel then take all of the panel's steps at once, row by row, with a row's columns held in registers while the
+// pivot rows stream past.  Every element still receives a_ij -= f_ik a_kj for ascending k with the very same operands
+// (the multipliers travel with their rows through the exchanges), so the factors equal the unblocked elimination's bit
+// for bit — and the device kernels' (kernels_solve.cuh) — while the matrix is read and written once per panel, not once
+// per step.
+#define LU_NB 16
+template <int CB>
+static inline __attribute__((always_inline)) void lu_trailing_cols(double* __restrict__ a, int n, int i, int k0, int kend, int c) {
+    double* ai = a + (size_t)i * n;
+    double acc[CB];
+    for (int q = 0; q < CB; ++q) acc[q] = ai[c + q];
+    for (int k = k0; k < kend; ++k) {
+        const double f = ai[k];
+        const double* ak = a + (size_t)k * n + c;
+        for (int q = 0; q < CB; ++q) acc[q] -= f * ak[q];
+    }
+    for (int q = 0; q < CB; ++q) ai[c + q] = acc[q];
+}
+DMSA_CLONES static void lu_factor_impl(std::vector<double>& av, std::vector<int>& piv, int n) {
+    double* a = av.data();
     for (int i = 0; i < n; ++i) piv[i] = i;
-    for (int k = 0; k < n; ++k) {
-        int p = k;
-        double best = std::fabs(a[(size_t)k * n + k]);
-        for (int i = k + 1; i < n; ++i) {
-            double v = std::fabs(a[(size_t)i * n + k]);
-            if (v > best) {
-                best = v;
-                p = i;
+    for (int k0 = 0; k0 < n; k0 += LU_NB) {
+        const int k1 = std::min(n, k0 + LU_NB);
+        for (int k = k0; k < k1; ++k) {  // the panel's steps on the panel's columns
+            int p = k;
+            double best = std::fabs(a[(size_t)k * n + k]);
+            for (int i = k + 1; i < n; ++i) {
+                double v = std::fabs(a[(size_t)i * n + k]);
+                if (v > best) {
+                    best = v;
+                    p = i;
+                }
+            }
+            if (p != k) {
+                for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)p * n + j]);
+                std::swap(piv[k], piv[p]);
+            }
+            const double d = a[(size_t)k * n + k];
+            const double* ak = a + (size_t)k * n;
+            for (int i = k + 1; i < n; ++i) {
+                double* ai = a + (size_t)i * n;
+                const double f = ai[k] / d;
+                ai[k] = f;
+                for (int j = k + 1; j < k1; ++j) ai[j] -= f * ak[j];
             }
         }
-        if (p != k) {
-            for (int j = 0; j < n; ++j) std::swap(a[(size_t)k * n + j], a[(size_t)p * n + j]);
-            std::swap(piv[k], piv[p]);
-        }
-        const double d = a[(size_t)k * n + k];
-        const double* __restrict__ ak = &a[(size_t)k * n];
-        for (int i = k + 1; i < n; ++i) {
-            double* __restrict__ ai = &a[(size_t)i * n];
-            const double f = ai[k] / d;
-            ai[k] = f;
-            for (int j = k + 1; j < n; ++j) ai[j] -= f * ak[j];
+        for (int i = k0 + 1; i < n; ++i) {  // the columns right of the panel: row i takes the steps of the pivots above it
+            const int kend = std::min(i, k1);
+            int c = k1;
+            for (; c + 32 <= n; c += 32) lu_trailing_cols<32>(a, n, i, k0, kend, c);
+            for (; c + 8 <= n; c += 8) lu_trailing_cols<8>(a, n, i, k0, kend, c);
+            for (; c < n; ++c) lu_trailing_cols<1>(a, n, i, k0, kend, c);
         }
     }
 }
@@ -55,26 +86,44 @@ DMSA_CLONES static void lu_factor_impl(std::vector<double>& a, std::vector<int>&
 // also scales by the reciprocal diagonal; neither order can be pinned against Eigen here).  This is the order in which
 // a column's dependency chain is 2 n steps long, so the device solver (kernels_solve.cuh) runs the same sequence with one
 // warp per column.
-DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n, int ldx, int c0, int c1) {
+// Both sweeps run row by row with the CB columns of a row held in registers while the row's whole dependency list streams
+// past (one load of x_j per multiply-subtract instead of a load and a store of x_i as well); an element still sees
+// exactly the sequence described above — forward: j ascending; backward: j descending, then the reciprocal diagonal.
+template <int CB>
+static inline __attribute__((always_inline)) void lu_subst_cols(const double* __restrict__ a, double* __restrict__ inv, int n, int ldx, int c) {
     for (int i = 0; i < n; ++i) {  // forward substitution, unit lower triangle
-        double* __restrict__ xi = &inv[(size_t)i * ldx];
-        const double* ai = &a[(size_t)i * n];
+        double* xi = inv + (size_t)i * ldx + c;
+        const double* ai = a + (size_t)i * n;
+        double acc[CB];
+        for (int q = 0; q < CB; ++q) acc[q] = xi[q];
         for (int j = 0; j < i; ++j) {
             const double l = ai[j];
-            const double* __restrict__ xj = &inv[(size_t)j * ldx];
-            for (int c = c0; c < c1; ++c) xi[c] -= l * xj[c];
+            const double* xj = inv + (size_t)j * ldx + c;
+            for (int q = 0; q < CB; ++q) acc[q] -= l * xj[q];
         }
+        for (int q = 0; q < CB; ++q) xi[q] = acc[q];
     }
-    for (int j = n - 1; j >= 0; --j) {  // back substitution
-        double* __restrict__ xj = &inv[(size_t)j * ldx];
-        const double rdiag = 1.0 / a[(size_t)j * n + j];
-        for (int c = c0; c < c1; ++c) xj[c] = xj[c] * rdiag;
-        for (int i = 0; i < j; ++i) {
-            const double u = a[(size_t)i * n + j];
-            double* __restrict__ xi = &inv[(size_t)i * ldx];
-            for (int c = c0; c < c1; ++c) xi[c] -= u * xj[c];
+    for (int i = n - 1; i >= 0; --i) {  // back substitution
+        double* xi = inv + (size_t)i * ldx + c;
+        const double* ai = a + (size_t)i * n;
+        double acc[CB];
+        for (int q = 0; q < CB; ++q) acc[q] = xi[q];
+        for (int j = n - 1; j > i; --j) {
+            const double u = ai[j];
+            const double* xj = inv + (size_t)j * ldx + c;
+            for (int q = 0; q < CB; ++q) acc[q] -= u * xj[q];
         }
+        const double rdiag = 1.0 / ai[i];
+        for (int q = 0; q < CB; ++q) xi[q] = acc[q] * rdiag;
     }
+}
+DMSA_CLONES static void lu_subst_block_impl(const double* a, double* inv, int n, int ldx, int c0, int c1) {
+    if (c0 >= c1) return;
+    if (c1 == n) c1 = std::min(ldx, (n + 7) / 8 * 8);  // the block that ends the matrix also takes the (zero) padding columns of its last line
+    int c = c0;
+    for (; c + 32 <= c1; c += 32) lu_subst_cols<32>(a, inv, n, ldx, c);
+    for (; c + 8 <= c1; c += 8) lu_subst_cols<8>(a, inv, n, ldx, c);
+    for (; c < c1; ++c) lu_subst_cols<1>(a, inv, n, ldx, c);
 }
 
 // A few helper threads for the substitution of the n independent right-hand sides.  The optimizer loop knows when the
