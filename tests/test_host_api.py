@@ -132,6 +132,55 @@ def test_lm_solve_variants():
     assert nan
 
 
+def _textbook_lm_step(hg, n, lam, alpha):
+    """The unblocked operation sequence host_solve.cpp documents (and kernels_solve.cuh reproduces), one IEEE double operation per
+    numpy call: LU with partial pivoting (first maximum wins), the columns of P * I substituted forward with ascending j and
+    backward with descending j and a multiplication by the reciprocal diagonal, the product (-alpha X) g in ascending column order."""
+    a = hg[:n * n].reshape(n, n).copy()
+    a[np.arange(n), np.arange(n)] += lam
+    g = hg[n * n:n * n + n]
+    piv = np.arange(n)
+    for k in range(n):
+        p = k + int(np.argmax(np.abs(a[k:, k])))  # argmax returns the first maximum
+        if p != k:
+            a[[k, p]] = a[[p, k]]
+            piv[[k, p]] = piv[[p, k]]
+        f = a[k + 1:, k] / a[k, k]
+        a[k + 1:, k] = f
+        a[k + 1:, k + 1:] -= f[:, None] * a[k, k + 1:][None, :]  # (a product, then a difference: two roundings, like the C loop)
+    x = np.zeros((n, n))
+    x[np.arange(n), piv] = 1.0
+    for i in range(n):
+        for j in range(i):
+            x[i] -= a[i, j] * x[j]
+    for j in range(n - 1, -1, -1):
+        x[j] = x[j] * (1.0 / a[j, j])
+        for i in range(j):
+            x[i] -= a[i, j] * x[j]
+    step = np.zeros(n)
+    for b in range(n):
+        step = step + (-alpha * x[:, b]) * g[b]
+    return step
+
+
+@pytest.mark.parametrize("n", [1, 7, 16, 17, 40, 75])
+def test_host_lm_step_equals_the_textbook_elimination_bit_for_bit(n):
+    """host_solve.cpp runs the elimination in panels of 16 pivots and both substitution sweeps row by row from registers; every
+    element must still see the unblocked sequence.  Pinned here against a numpy restatement of that sequence (general matrices,
+    so rows are exchanged at most steps)."""
+    from dmsa_lidar_slam_b200.api import lm_solve
+
+    rng = np.random.default_rng(100 + n)
+    for trial in range(3):
+        A = rng.normal(size=(n, n)) if trial < 2 else (lambda J: J.T @ J)(rng.normal(size=(3 * n, n)))
+        g = rng.normal(size=n)
+        hg = np.concatenate([A.ravel(), g, [1.0]])
+        s = api.DmsaOptimSettings(step_length_optim=0.2, max_step=1e300)
+        got, nan = lm_solve(s, hg, n, 1)
+        want = _textbook_lm_step(hg, n, float(np.float32(1e-5)), 0.2)
+        assert not nan and np.array_equal(got, want), np.abs(got - want).max()
+
+
 def test_bench_reference_arm_prints_exactly_one_json_line():
     """bench.py --impl reference (the CPU arm the driver runs next to ours): stdout carries ONE JSON line with the contract's
     keys even when native libraries write banners to file descriptor 1; works under a torchrun-style environment where only
